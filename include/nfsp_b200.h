@@ -1,0 +1,178 @@
+/* nfsp_b200.h -- C ABI of libnfsp_b200.so: the B200-native batched Leduc Hold'em + NFSP rollout
+ * path (env step, NFSP act, replay/reservoir memories).
+ *
+ * The reference (dantodor/Neural-Ficititious-Self-Play-in-Imperfect-Information-Games) has no
+ * FFI: its boundary is four duck-typed Python classes.  Each entry point below names the
+ * reference method it replaces (file:line in the reference tree); INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative NFSP_E_* code on failure; the message of the
+ *     last failure on the calling thread is nfsp_last_error();
+ *   - all `d_*` pointers are DEVICE pointers owned by the caller (the Python host allocates them
+ *     with torch); nothing here allocates or synchronises in a hot call;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - a handle is bound to one device, is not thread-safe, and distinct handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails with
+ *     NFSP_E_CUDA.
+ */
+#ifndef NFSP_B200_H
+#define NFSP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFSP_OK 0
+#define NFSP_E_ARG (-1)
+#define NFSP_E_CUDA (-2)
+#define NFSP_E_STATE (-3)
+
+#define NFSP_RULES_LEGACY 0 /* leduc/env.py    */
+#define NFSP_RULES_NFSP 1   /* leduc/newenv.py */
+
+#define NFSP_OBS_DIM 30        /* newenv.py:68-74 */
+#define NFSP_ACTIONS 3         /* newenv.py:63-66 */
+#define NFSP_HIDDEN 64         /* config.ini:4    */
+#define NFSP_NET_PARAMS 2179   /* 30*64 + 64 + 64*3 + 3 (agent.py:101-103) */
+#define NFSP_EXPORT_FIELDS 24  /* int32 columns of nfsp_env_export   */
+#define NFSP_LEGACY_EXPORT_FIELDS 14
+#define NFSP_STATS_FIELDS 16   /* uint64 counters, see nfsp_rollout  */
+
+typedef struct nfsp_env_s *nfsp_env_t;
+
+int nfsp_version(void);
+const char *nfsp_last_error(void);
+/* number of SMs / device name of `device`, for sizing (no handle needed) */
+int nfsp_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* ------------------------------------------------------------------ lifecycle ------------- */
+/* One packed 64-bit word per game in HBM.  Games are numbered game0 .. game0+n_games-1; all
+ * randomness is Philox4x32-10 keyed by (seed; global game id, step counter, purpose), so a
+ * game's trace does not depend on how games are sharded over GPUs.
+ * Replaces Env.__init__ (env.py:13-32, newenv.py:14-55). */
+int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64_t game0, int device, nfsp_env_t *out);
+int nfsp_env_destroy(nfsp_env_t h);
+int64_t nfsp_env_num_games(nfsp_env_t h);
+int nfsp_env_rules(nfsp_env_t h);
+/* the Philox step counter: advanced by one per reset call and per stepped transition */
+uint64_t nfsp_env_step_counter(nfsp_env_t h);
+int nfsp_env_set_step_counter(nfsp_env_t h, uint64_t step);
+/* device pointer to the n_games packed words */
+void *nfsp_env_state_ptr(nfsp_env_t h);
+/* copy the n_games packed 64-bit words out of / into the handle (checkpoint / resume, sharding tests) */
+int nfsp_env_save_state(nfsp_env_t h, uint64_t *d_out, void *stream);
+int nfsp_env_load_state(nfsp_env_t h, const uint64_t *d_in, void *stream);
+
+/* ------------------------------------------------------------------ ENV_NFSP -------------- */
+/* newenv.Env.reset(dealer) (newenv.py:76-114) for every game: d_dealer int8[n] or NULL
+ * (NULL => global game id & 1).  Deals from Philox; draws the per-hand policies of
+ * main.py:38-45 with P('b') = eta. */
+int nfsp_env_reset(nfsp_env_t h, const int8_t *d_dealer, double eta, void *stream);
+/* replay mode: install explicit hands. d_cards int8[n][3] = ranks popped by p0, p1, public
+ * (deck.py:49-50); d_policy int8[n][2] (0 = 'a', 1 = 'b') or NULL. */
+int nfsp_env_set_hands(nfsp_env_t h, const int8_t *d_dealer, const int8_t *d_cards, const int8_t *d_policy,
+                       void *stream);
+/* newenv.Env.step(action, p_index) (newenv.py:192-349) n_steps times for every game.
+ *   d_actions int8[n_steps][n] or NULL: 0/1/2 = np.argmax(action); 3 = the all-zero vector (a fold
+ *             that Agent.play does not remember, agent.py:134); -1 or NULL = uniform Philox action;
+ *             4 = the game sits this step out (per-game call sequences).
+ *   d_players int8[n_steps][n] or NULL: NULL => main.train's turn order (main.py:55-65).
+ *   auto_reset: re-deal a finished hand at its next step (dealer alternates, main.py:28-31).
+ *   d_trace   uint32[3][n_steps][n] or NULL: planes obs|terminal<<30|player<<31, reward (float
+ *             bits), misc (DESIGN.md "trace record"). */
+int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int n_steps, int auto_reset,
+                  double eta, uint32_t *d_trace, void *stream);
+/* newenv.Env.get_state(p) (newenv.py:116-129), packed: player < 0 => per-game d_players.
+ * Outputs (any may be NULL): d_s snapshot mask, d_s2 current observation mask, d_reward,
+ * d_term, d_last_a (argmax of last_action[p], 3 if it was never set / all-zero). */
+int nfsp_env_observe(nfsp_env_t h, const int8_t *d_players, int player, uint32_t *d_s, uint32_t *d_s2,
+                     float *d_reward, uint8_t *d_term, uint8_t *d_last_a, void *stream);
+/* unpacked view int32[n][NFSP_EXPORT_FIELDS] (tests / debugging) */
+int nfsp_env_export(nfsp_env_t h, int32_t *d_fields, void *stream);
+
+/* ------------------------------------------------------------------ ENV_LEGACY ------------ */
+/* env.Env.reset() (env.py:46-72), Philox deal */
+int nfsp_legacy_reset(nfsp_env_t h, void *stream);
+/* replay mode: d_cards int8[n][2] */
+int nfsp_legacy_set_hands(nfsp_env_t h, const int8_t *d_cards, void *stream);
+/* env.Env.step(action, player_index) (env.py:84-158); d_actions int8[n] = np.argmax(action), 4 = the
+ * game sits this call out; player < 0 => per-game d_players int8[n] (a value > 1 also sits out) */
+int nfsp_legacy_step(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int player, void *stream);
+/* env.Env.get_new_state(player_index) (env.py:160-205); d_out int32[n][5] =
+ * {card, public(-1), pot, reward, terminal} or NULL (state still mutates, as in the reference) */
+int nfsp_legacy_get_new_state(nfsp_env_t h, const int8_t *d_players, int player, int32_t *d_out, void *stream);
+/* n_iters README iterations (README.md:15-38): step(a0,0); step(a1,1); get_new_state(0);
+ * get_new_state(1); auto re-deal when either reports terminal.  d_actions int8[n_iters][n][2] or
+ * NULL (Philox).  d_rec uint32[3][n_iters][n][2] or NULL: planes card|pub<<8|pot<<16|terminal<<24
+ * (signed bytes), reward (int32), misc. 2 transitions per game per iteration. */
+int nfsp_legacy_rollout(nfsp_env_t h, const int8_t *d_actions, int n_iters, uint32_t *d_rec, void *stream);
+int nfsp_legacy_export(nfsp_env_t h, int32_t *d_fields, void *stream);
+
+/* ------------------------------------------------------------------ dense views ----------- */
+/* 30-bit masks -> float32 [n][30] rows of 0/1 (the reference's state vectors, newenv.py:118-122) */
+int nfsp_expand_obs(const uint32_t *d_masks, int64_t n, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------ NFSP acting ----------- */
+/* Four acting nets, index player*2 + policy (policy 0 = average 'a', 1 = best response 'b'),
+ * each NFSP_NET_PARAMS floats in Keras Dense order W1[30][64], b1[64], W2[64][3], b2[3]
+ * (agent.py:90-116).  Repacks them into the kernels' layouts inside the handle. */
+int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *stream);
+/* batched Model.predict (agent.py:126,143): d_obs uint32[n] masks, d_net int8[n] net index;
+ * d_out float[n][3] = Q-values (relu head) for BR nets, softmax probabilities for average nets */
+int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
+                     void *stream);
+
+/* Record formats (16 B each):
+ *   RL  {u32 s, u32 s2, f32 r, u8 a, u8 t, u8 player, u8 flags}   replay_buffer.py:30-41, by value
+ *   SL  {u32 s, f32 a[3]}                                          ReservoirBuffer.py:18-28       */
+typedef struct {
+    void *d_rl[2];        /* per-player staging, RL records                                     */
+    void *d_sl[2];        /* per-player staging, SL records                                     */
+    int64_t cap_rl, cap_sl;
+    uint32_t *d_counts;   /* uint32[4]: rl0, rl1, sl0, sl1 appended so far (device)             */
+    uint64_t *d_stats;    /* uint64[NFSP_STATS_FIELDS] or NULL: actions[2][3], played[2],
+                             reward_half[2] (two's complement), hands, transitions, dropped     */
+    uint32_t *d_trace;    /* as nfsp_env_step, or NULL                                          */
+    float *d_vec;         /* float[n_steps][n][3] score vectors actually used, or NULL          */
+    const float *d_forced_vec; /* float[n_steps][n][3] or NULL: use these instead of the nets   */
+} nfsp_rollout_io;
+
+/* The fused hot path: for n_steps, every game does one Agent.play decision (agent.py:130-156)
+ * -- observe, remember the previous transition, eta-mixed policy (average net argmax /
+ * epsilon-greedy best-response net), env.step -- plus the terminal observations of main.py:55-67,
+ * with auto re-deal.  Records are appended to the staging arrays with warp-aggregated atomics;
+ * move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
+int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io, void *stream);
+
+/* ------------------------------------------------------------------ memories -------------- */
+/* ReplayBuffer.add (replay_buffer.py:30-41) for a batch: FIFO ring, slot = ticket % cap where
+ * ticket counts records ever inserted (*d_total).  d_n = device count of staged records
+ * (<= max_n); records beyond the last `cap` of a batch are skipped (they would be evicted).
+ * The staging array is consumed: *d_total += n and *d_n = 0 on the stream when the insert is done. */
+int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_n,
+                     int64_t max_n, void *stream);
+/* ReservoirBuffer.add (ReservoirBuffer.py:18-28) for a batch.  mode 0 = Algorithm R (Vitter):
+ * ticket t >= cap replaces slot j ~ U[0,t] iff j < cap; mode 1 = the reference's law
+ * (j = randrange(1, cap+1), replace iff j < cap).  Same-slot collisions inside a batch are
+ * resolved as in the sequential algorithm (largest ticket wins) via d_stamp uint64[cap]. */
+int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp, const void *d_recs,
+                          uint32_t *d_n, int64_t max_n, uint64_t seed, int mode, void *stream);
+/* random.sample(buffer, batch) (replay_buffer.py:46-51, ReservoirBuffer.py:33-37): `batch`
+ * distinct positions (Floyd's algorithm, Philox keyed by (seed; call_idx)); d_idx int64[batch]
+ * receives storage slots, d_n_out the number drawn = min(batch, size).  is_ring: positions are
+ * deque positions (oldest first) mapped to ring slots. */
+int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_total, int64_t cap, int is_ring,
+                        int batch, int64_t *d_idx, uint32_t *d_n_out, void *stream);
+/* gather + expand to the dense float32 batches the learner consumes (replay_buffer.py:53-59):
+ * s [b][30], a [b][3] (one-hot of the stored argmax), r [b], s2 [b][30], t [b] */
+int nfsp_gather_rl(const void *d_ring, const int64_t *d_idx, int batch, float *d_s, float *d_a, float *d_r,
+                   float *d_s2, float *d_t, void *stream);
+/* ReservoirBuffer.sample_batch (ReservoirBuffer.py:39-43): s [b][30], a [b][3] */
+int nfsp_gather_sl(const void *d_res, const int64_t *d_idx, int batch, float *d_s, float *d_a, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFSP_B200_H */

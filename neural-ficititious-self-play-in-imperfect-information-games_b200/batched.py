@@ -1,0 +1,424 @@
+"""Batched engines over the C ABI: N independent Leduc games per call, tensors stay on the GPU.
+
+These are the classes the single-game drop-ins (leduc/env.py, leduc/newenv.py, agent/agent.py,
+utils/*.py of this package) are thin batch-of-1 views of.  Names follow the reference's domain:
+games, hands, deals, transitions, memories.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _device(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.NfspError("no CUDA device: this package has no CPU path")
+    d = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if d.type != "cuda":
+        raise _lib.NfspError("device must be a CUDA device, got %s" % d)
+    return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
+def _stream(dev: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _as(t, dtype, dev, shape=None):
+    """Host or device array-like -> contiguous device tensor of `dtype` (a copy only when needed)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    t = t.to(device=dev, dtype=dtype).contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(t.shape)))
+    return t
+
+
+def expand_obs(masks: torch.Tensor) -> torch.Tensor:
+    """30-bit observation masks -> float32 [n, 30] (the reference's state vector, newenv.py:118-122)."""
+    m = masks.contiguous().view(torch.int32).reshape(-1)
+    out = torch.empty((m.numel(), _lib.OBS_DIM), dtype=torch.float32, device=m.device)
+    check(lib().nfsp_expand_obs(_ptr(m), m.numel(), _ptr(out), _stream(m.device)))
+    return out
+
+
+def obs_to_mask(x) -> torch.Tensor:
+    """float 0/1 state vectors [..., 30] -> int32 masks [...]; raises on non-binary input (the packed
+    record formats only hold the reference's binary observations)."""
+    x = torch.as_tensor(x)
+    if x.shape[-1] != _lib.OBS_DIM:
+        raise ValueError("state vectors must have 30 entries")
+    if not bool(((x == 0) | (x == 1)).all()):
+        raise ValueError("state vectors must be 0/1 (newenv.py:118 encoding)")
+    w = (2 ** torch.arange(_lib.OBS_DIM, dtype=torch.int64, device=x.device))
+    return (x.to(torch.int64) * w).sum(-1).to(torch.int32)
+
+
+class _EnvBase:
+    rules = None
+
+    def __init__(self, n_games: int, seed: int = 1234, game0: int = 0, device=None):
+        self.device = _device(device)
+        self.n = int(n_games)
+        self._h = C.c_void_p()
+        check(lib().nfsp_env_create(self.rules, self.n, seed & (2 ** 64 - 1), game0, self.device.index,
+                                    C.byref(self._h)))
+        self.seed, self.game0 = seed, game0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().nfsp_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def step_counter(self) -> int:
+        return int(lib().nfsp_env_step_counter(self._h))
+
+    @step_counter.setter
+    def step_counter(self, v: int):
+        check(lib().nfsp_env_set_step_counter(self._h, int(v)))
+
+    def state_words(self) -> torch.Tensor:
+        """A copy of the packed 64-bit game words (checkpointing, multi-GPU invariance tests)."""
+        out = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        check(lib().nfsp_env_save_state(self._h, _ptr(out), _stream(self.device)))
+        return out
+
+    def load_state_words(self, words: torch.Tensor):
+        w = _as(words, torch.int64, self.device, (self.n,))
+        check(lib().nfsp_env_load_state(self._h, _ptr(w), _stream(self.device)))
+
+
+class BatchedNfspEnv(_EnvBase):
+    """N games of leduc/newenv.py.  `step` is newenv.Env.step for every game in one kernel launch."""
+
+    rules = _lib.RULES_NFSP
+
+    def __init__(self, n_games, seed=1234, game0=0, device=None, eta=0.1):
+        super().__init__(n_games, seed, game0, device)
+        self.eta = float(eta)
+
+    def reset(self, dealer=None):
+        """newenv.Env.reset(dealer) for every game; dealer: None (game id & 1), int, or [n] array."""
+        if dealer is not None and not isinstance(dealer, torch.Tensor) and np.ndim(dealer) == 0:
+            dealer = torch.full((self.n,), int(dealer), dtype=torch.int8)
+        d = _as(dealer, torch.int8, self.device, (self.n,))
+        check(lib().nfsp_env_reset(self._h, _ptr(d), self.eta, _stream(self.device)))
+
+    def set_hands(self, dealer, cards, policy=None):
+        d = _as(dealer, torch.int8, self.device, (self.n,))
+        c = _as(cards, torch.int8, self.device, (self.n, 3))
+        p = _as(policy, torch.int8, self.device, (self.n, 2))
+        check(lib().nfsp_env_set_hands(self._h, _ptr(d), _ptr(c), _ptr(p), _stream(self.device)))
+
+    def step(self, actions=None, players=None, n_steps=1, auto_reset=True, trace=False):
+        """actions: None (uniform Philox) or int8 [n_steps, n] codes 0 fold / 1 call / 2 raise /
+        3 all-zero vector / -1 random; players: None = main.train's turn order.  Returns the trace
+        planes dict when trace=True."""
+        shape = (n_steps, self.n)
+        a = _as(actions, torch.int8, self.device)
+        p = _as(players, torch.int8, self.device)
+        if a is not None:
+            a = a.reshape(shape)
+        if p is not None:
+            p = p.reshape(shape)
+        tr = torch.empty((3,) + shape, dtype=torch.int32, device=self.device) if trace else None
+        check(lib().nfsp_env_step(self._h, _ptr(a), _ptr(p), n_steps, int(bool(auto_reset)), self.eta, _ptr(tr),
+                                  _stream(self.device)))
+        return None if tr is None else decode_trace(tr)
+
+    def get_state(self, player):
+        """newenv.Env.get_state(p), packed: (s mask, last action id, reward, s2 mask, terminated)."""
+        per_game = isinstance(player, (torch.Tensor, np.ndarray, list, tuple))
+        pl = _as(player, torch.int8, self.device, (self.n,)) if per_game else None
+        s = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        s2 = torch.empty_like(s)
+        r = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        t = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        a = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        check(lib().nfsp_env_observe(self._h, _ptr(pl), -1 if per_game else int(player), _ptr(s), _ptr(s2), _ptr(r),
+                                     _ptr(t), _ptr(a), _stream(self.device)))
+        return s, a, r, s2, t
+
+    FIELDS = ("hist", "c0", "c1", "pub", "dealer", "round", "k", "bets0", "bets1", "terminated", "need_reset", "pol0",
+              "pol1", "last_a0", "last_a1", "nz0", "nz1", "obs0", "obs1", "snap0", "snap1", "rew0_half", "rew1_half",
+              "anomaly")
+
+    def export(self):
+        out = torch.empty((self.n, _lib.EXPORT_FIELDS), dtype=torch.int32, device=self.device)
+        check(lib().nfsp_env_export(self._h, _ptr(out), _stream(self.device)))
+        return {k: out[:, i] for i, k in enumerate(self.FIELDS)}
+
+
+def decode_trace(tr: torch.Tensor):
+    """uint32 planes [3, n_steps, n] -> named fields (DESIGN.md "trace record")."""
+    obs, rew, misc = tr[0], tr[1], tr[2]
+    return dict(raw=tr, obs=obs & 0x3FFFFFFF, terminated=(obs >> 30) & 1, player=(obs >> 31) & 1,
+                reward=rew.view(torch.float32), action=misc & 3, effective=(misc >> 2) & 3, round=(misc >> 4) & 1,
+                dealer=(misc >> 5) & 1, c0=(misc >> 6) & 3, c1=(misc >> 8) & 3, pub=(misc >> 10) & 3,
+                bets0=(misc >> 13) & 15, bets1=(misc >> 17) & 15, started=(misc >> 21) & 1,
+                pol0=(misc >> 22) & 1, pol1=(misc >> 23) & 1)
+
+
+class BatchedLegacyEnv(_EnvBase):
+    """N games of leduc/env.py (the README's documented env)."""
+
+    rules = _lib.RULES_LEGACY
+    FIELDS = ("c0", "c1", "left0", "left1", "pot0", "pot1", "term0", "term1", "st_pot0", "st_pot1", "st_act0",
+              "st_act1", "rew0", "rew1")
+
+    def reset(self):
+        check(lib().nfsp_legacy_reset(self._h, _stream(self.device)))
+
+    def set_hands(self, cards):
+        c = _as(cards, torch.int8, self.device, (self.n, 2))
+        check(lib().nfsp_legacy_set_hands(self._h, _ptr(c), _stream(self.device)))
+
+    def step(self, actions, player):
+        per_game = isinstance(player, (torch.Tensor, np.ndarray, list, tuple))
+        pl = _as(player, torch.int8, self.device, (self.n,)) if per_game else None
+        a = _as(actions, torch.int8, self.device, (self.n,))
+        check(lib().nfsp_legacy_step(self._h, _ptr(a), _ptr(pl), -1 if per_game else int(player),
+                                     _stream(self.device)))
+
+    def get_new_state(self, player, want_out=True):
+        per_game = isinstance(player, (torch.Tensor, np.ndarray, list, tuple))
+        pl = _as(player, torch.int8, self.device, (self.n,)) if per_game else None
+        out = torch.empty((self.n, 5), dtype=torch.int32, device=self.device) if want_out else None
+        check(lib().nfsp_legacy_get_new_state(self._h, _ptr(pl), -1 if per_game else int(player), _ptr(out),
+                                              _stream(self.device)))
+        return out
+
+    def rollout(self, n_iters=1, actions=None, trace=False):
+        a = _as(actions, torch.int8, self.device)
+        if a is not None:
+            a = a.reshape(n_iters, self.n, 2)
+        rec = torch.empty((3, n_iters, self.n, 2), dtype=torch.int32, device=self.device) if trace else None
+        check(lib().nfsp_legacy_rollout(self._h, _ptr(a), n_iters, _ptr(rec), _stream(self.device)))
+        if rec is None:
+            return None
+        w = rec[0]
+        sb = lambda x: ((x & 0xFF) ^ 0x80) - 0x80  # noqa: E731  signed byte
+        return dict(raw=rec, card=sb(w), pub=sb(w >> 8), pot=sb(w >> 16), terminal=sb(w >> 24), reward=rec[1],
+                    action=rec[2] & 3, left=((rec[2] >> 2) & 7) - 1, pot_own=(rec[2] >> 5) & 7,
+                    started=(rec[2] >> 8) & 1)
+
+    def export(self):
+        out = torch.empty((self.n, _lib.LEGACY_EXPORT_FIELDS), dtype=torch.int32, device=self.device)
+        check(lib().nfsp_legacy_export(self._h, _ptr(out), _stream(self.device)))
+        return {k: out[:, i] for i, k in enumerate(self.FIELDS)}
+
+
+# ---------------------------------------------------------------------------------------------
+# memories (16-byte packed records in HBM)
+# ---------------------------------------------------------------------------------------------
+RL_DT = np.dtype([("s", "<u4"), ("s2", "<u4"), ("r", "<f4"), ("a", "u1"), ("t", "u1"), ("player", "u1"),
+                  ("flags", "u1")])
+SL_DT = np.dtype([("s", "<u4"), ("a", "<f4", (3,))])
+
+
+class _Memory:
+    is_ring = True
+
+    def __init__(self, capacity: int, seed: int = 1234, device=None):
+        self.device = _device(device)
+        self.capacity = int(capacity)
+        self.seed = int(seed) & (2 ** 64 - 1)
+        self.data = torch.zeros((self.capacity, 4), dtype=torch.int32, device=self.device)
+        self.total = torch.zeros(1, dtype=torch.int64, device=self.device)  # records ever inserted
+        self.sample_calls = 0
+
+    def size(self) -> int:
+        """count saturates at capacity (replay_buffer.py:36-44).  Reads one device word (syncs)."""
+        return int(min(int(self.total.item()), self.capacity))
+
+    def sample_slots(self, batch: int):
+        idx = torch.empty(batch, dtype=torch.int64, device=self.device)
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(lib().nfsp_sample_indices(self.seed, self.sample_calls, _ptr(self.total), self.capacity,
+                                        int(self.is_ring), batch, _ptr(idx), _ptr(n), _stream(self.device)))
+        self.sample_calls += 1
+        return idx, n
+
+    def records(self) -> np.ndarray:
+        """Host copy of the stored records in storage-slot order (tests)."""
+        dt = RL_DT if self.is_ring else SL_DT
+        return self.data.cpu().numpy().view(np.uint8).reshape(-1).view(dt)[: self.size()].copy()
+
+    def clear(self):
+        self.total.zero_()
+
+
+class DeviceRing(_Memory):
+    """Circular replay memory M_RL: FIFO ring of RL records (utils/replay_buffer.py)."""
+
+    is_ring = True
+
+    def insert(self, recs: torch.Tensor, count: torch.Tensor, max_n: Optional[int] = None):
+        """recs int32 [m,4] staged records, count int32[1] device count (consumed: zeroed after)."""
+        max_n = recs.shape[0] if max_n is None else max_n
+        check(lib().nfsp_ring_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(recs), _ptr(count),
+                                     int(max_n), _stream(self.device)))
+
+    def sample(self, batch: int):
+        idx, n = self.sample_slots(batch)
+        b = batch
+        s = torch.empty((b, 30), dtype=torch.float32, device=self.device)
+        s2 = torch.empty_like(s)
+        a = torch.empty((b, 3), dtype=torch.float32, device=self.device)
+        r = torch.empty(b, dtype=torch.float32, device=self.device)
+        t = torch.empty(b, dtype=torch.float32, device=self.device)
+        check(lib().nfsp_gather_rl(_ptr(self.data), _ptr(idx), b, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(t),
+                                   _stream(self.device)))
+        return s, a, r, s2, t, idx, n
+
+
+class DeviceReservoir(_Memory):
+    """Reservoir memory M_SL (utils/ReservoirBuffer.py).  mode "R" = Algorithm R (default, what
+    BASELINE.json's north_star specifies); mode "reference" = the reference's constant-probability law."""
+
+    is_ring = False
+
+    def __init__(self, capacity, seed=1234, device=None, mode="R"):
+        super().__init__(capacity, seed, device)
+        if mode not in ("R", "reference"):
+            raise ValueError("mode must be 'R' or 'reference'")
+        self.mode = 0 if mode == "R" else 1
+        self.stamp = torch.zeros(self.capacity, dtype=torch.int64, device=self.device)
+
+    def insert(self, recs, count, max_n=None):
+        max_n = recs.shape[0] if max_n is None else max_n
+        check(lib().nfsp_reservoir_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(self.stamp),
+                                          _ptr(recs), _ptr(count), int(max_n), self.seed, self.mode,
+                                          _stream(self.device)))
+
+    def sample(self, batch: int):
+        idx, n = self.sample_slots(batch)
+        s = torch.empty((batch, 30), dtype=torch.float32, device=self.device)
+        a = torch.empty((batch, 3), dtype=torch.float32, device=self.device)
+        check(lib().nfsp_gather_sl(_ptr(self.data), _ptr(idx), batch, _ptr(s), _ptr(a), _stream(self.device)))
+        return s, a, idx, n
+
+    def clear(self):
+        super().clear()
+        self.stamp.zero_()
+
+
+# ---------------------------------------------------------------------------------------------
+# acting nets + fused self-play rollout
+# ---------------------------------------------------------------------------------------------
+def glorot_nets(seed=1234, device=None) -> torch.Tensor:
+    """Four acting nets [player*2 + policy] with Keras' default init (glorot_uniform kernels, zero
+    biases; agent.py:101-103,110-112): float32 [4, 2179] = W1[30][64], b1[64], W2[64][3], b2[3]."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.zeros((4, _lib.NET_PARAMS), dtype=torch.float32)
+    l1, l2 = (6.0 / (30 + 64)) ** 0.5, (6.0 / (64 + 3)) ** 0.5
+    for k in range(4):
+        w[k, :1920] = (torch.rand(1920, generator=g) * 2 - 1) * l1
+        w[k, 1984:2176] = (torch.rand(192, generator=g) * 2 - 1) * l2
+    return w.to(_device(device)) if device is not None or torch.cuda.is_available() else w
+
+
+def split_net(w_row):
+    """flat [2179] -> dict W1 (30,64), b1, W2 (64,3), b2 (numpy / tensor views)."""
+    return dict(W1=w_row[:1920].reshape(30, 64), b1=w_row[1920:1984], W2=w_row[1984:2176].reshape(64, 3),
+                b2=w_row[2176:2179])
+
+
+class SelfPlay:
+    """The fused NFSP rollout: env + acting nets + both players' memories on one GPU.
+
+    One `rollout(n_steps)` call = n_steps Agent.play decisions for every game, records staged by the
+    kernel and then moved into the ring (M_RL) / reservoir (M_SL) of the player they belong to."""
+
+    STAT_NAMES = ("a0_fold", "a0_call", "a0_raise", "a1_fold", "a1_call", "a1_raise", "played0", "played1",
+                  "reward0_half", "reward1_half", "hands", "transitions", "dropped")
+
+    def __init__(self, n_games, weights=None, seed=1234, game0=0, device=None, eta=0.1, epsilon=0.06,
+                 rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R"):
+        self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
+        self.device, self.n = self.env.device, self.env.n
+        self.eta, self.epsilon = float(eta), float(epsilon)
+        self.max_steps = int(max_steps_per_call)
+        self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
+        self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
+        # worst case per player and step: 2 RL records (previous + terminal) and 1 SL record per game
+        self.cap_rl = 2 * self.n * self.max_steps
+        self.cap_sl = self.n * self.max_steps
+        self.stage_rl = [torch.empty((self.cap_rl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.stage_sl = [torch.empty((self.cap_sl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.counts = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.stats = torch.zeros(_lib.STATS_FIELDS, dtype=torch.int64, device=self.device)
+        self.set_weights(glorot_nets(seed, self.device) if weights is None else weights)
+        self.env.reset()
+
+    def set_weights(self, weights):
+        self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
+        check(lib().nfsp_act_set_weights(self.env._h, _ptr(self.weights), _stream(self.device)))
+
+    def forward(self, obs_masks, net_idx):
+        """Batched Model.predict: Q-values (BR nets, odd index) / softmax probabilities (average nets)."""
+        o = _as(obs_masks, torch.int32, self.device).reshape(-1)
+        k = _as(net_idx, torch.int8, self.device).reshape(-1)
+        out = torch.empty((o.numel(), 3), dtype=torch.float32, device=self.device)
+        check(lib().nfsp_act_forward(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
+        return out
+
+    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None):
+        if n_steps > self.max_steps:
+            raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
+        io = _lib.RolloutIO()
+        for p in range(2):
+            io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
+        io.cap_rl, io.cap_sl = self.cap_rl, self.cap_sl
+        io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
+        dbg = None
+        if debug or forced_vec is not None:
+            tr = torch.empty((3, n_steps, self.n), dtype=torch.int32, device=self.device)
+            vec = torch.empty((n_steps, self.n, 3), dtype=torch.float32, device=self.device)
+            fv = _as(forced_vec, torch.float32, self.device, (n_steps, self.n, 3))
+            io.d_trace, io.d_vec = tr.data_ptr(), vec.data_ptr()
+            io.d_forced_vec = None if fv is None else fv.data_ptr()
+            dbg = (tr, vec, fv)
+        check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilon, C.byref(io), _stream(self.device)))
+        out = None
+        if dbg is not None:
+            out = decode_trace(dbg[0])
+            out["vec"] = dbg[1]
+        if insert:
+            self.flush()
+        return out
+
+    def staged(self):
+        """Host copies of the staged records (tests): ([rl0, rl1], [sl0, sl1]) structured arrays."""
+        c = self.counts.cpu().numpy()
+        rl = [self.stage_rl[p][: int(c[p])].cpu().numpy().view(np.uint8).reshape(-1).view(RL_DT) for p in range(2)]
+        sl = [self.stage_sl[p][: int(c[2 + p])].cpu().numpy().view(np.uint8).reshape(-1).view(SL_DT) for p in range(2)]
+        return rl, sl
+
+    def flush(self):
+        """Move the staged records into the memories (stream-ordered, no host sync)."""
+        for p in range(2):
+            self.rl[p].insert(self.stage_rl[p], self.counts[p:p + 1], self.cap_rl)
+            self.sl[p].insert(self.stage_sl[p], self.counts[2 + p:3 + p], self.cap_sl)
+
+    def read_stats(self):
+        v = self.stats.cpu().numpy()
+        return {k: int(v[i]) for i, k in enumerate(self.STAT_NAMES)}

@@ -1,0 +1,313 @@
+// K2 (CUDA-core variant): NFSP acting fused with the env step.
+//
+// One thread per game.  Per step a game does exactly one Agent.play decision (agent.py:130-156):
+// observation -> one of four 30-64-3 MLPs (player x {average, best-response}) -> eta-mixed /
+// epsilon-greedy score vector -> argmax -> newenv step, and emits the RL / SL memory records of
+// agent.py:134-136,151 and the terminal observations of main.py:55-67.  The observation is a
+// 30-bit mask that never leaves registers; because it is binary and sparse (<= 9 bits set) the
+// first layer is a SUM OF <= 9 WEIGHT ROWS, read from shared memory as conflict-free float4s,
+// instead of a dense 30x64 product.
+#include "common.cuh"
+#include "nfsp_rules.cuh"
+#include "philox.cuh"
+
+namespace nfsp {
+
+constexpr int kActThreads = 128;
+// packed weight image (floats): W1 rows as [16 col-quads][128 rows = net*32 + input][4], where input 30 is
+// the bias b1; then W2 as [64 hidden][4 nets][4 = 3 outputs + pad]; then b2 as [4 nets][4].
+constexpr int kW1Floats = 16 * 128 * 4;
+constexpr int kW2Floats = 64 * 4 * 4;
+constexpr int kB2Floats = 4 * 4;
+constexpr int kPackFloats = kW1Floats + kW2Floats + kB2Floats;
+
+__global__ void pack_weights_kernel(const float *__restrict__ w, float *__restrict__ pack) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats; e += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (e < kW1Floats) {
+            const int c = e & 3, row = (e >> 2) & 127, q = e >> 9;
+            const int net = row >> 5, i = row & 31, j = q * 4 + c;
+            const float *wn = w + net * NFSP_NET_PARAMS;
+            if (i < 30) v = wn[i * 64 + j];
+            else if (i == 30) v = wn[1920 + j];
+        } else if (e < kW1Floats + kW2Floats) {
+            const int f = e - kW1Floats, c = f & 3, net = (f >> 2) & 3, j = f >> 4;
+            if (c < 3) v = w[net * NFSP_NET_PARAMS + 1984 + j * 3 + c];
+        } else {
+            const int f = e - kW1Floats - kW2Floats, c = f & 3, net = f >> 2;
+            if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
+        }
+        pack[e] = v;
+    }
+}
+
+// forward of one net on one observation mask; sw = packed image in shared memory
+__device__ __forceinline__ void mlp_forward(const float *__restrict__ sw, uint32_t obs, int net, float out[3]) {
+    const float4 *w1 = reinterpret_cast<const float4 *>(sw);
+    const int row0 = net * 32;
+    float h[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) h[j] = 0.f;
+    uint32_t bits = (obs & 0x3FFFFFFFu) | (1u << 30);  // input 30 = constant 1 -> adds the bias row last
+    while (bits) {
+        const int i = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        const float4 *r = w1 + row0 + i;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 v = r[q * 128];
+            h[4 * q + 0] += v.x; h[4 * q + 1] += v.y; h[4 * q + 2] += v.z; h[4 * q + 3] += v.w;
+        }
+    }
+    const float4 *w2 = reinterpret_cast<const float4 *>(sw + kW1Floats) + net;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const float hj = fmaxf(h[j], 0.f);  // Dense(64, relu), agent.py:102,111
+        const float4 v = w2[j * 4];
+        z0 = fmaf(hj, v.x, z0); z1 = fmaf(hj, v.y, z1); z2 = fmaf(hj, v.z, z2);
+    }
+    const float4 b2 = reinterpret_cast<const float4 *>(sw + kW1Floats + kW2Floats)[net];
+    z0 += b2.x; z1 += b2.y; z2 += b2.z;
+    if (net & 1) {  // best-response net: Dense(3, relu), agent.py:103
+        out[0] = fmaxf(z0, 0.f); out[1] = fmaxf(z1, 0.f); out[2] = fmaxf(z2, 0.f);
+    } else {        // average-policy net: Dense(3, softmax), agent.py:112
+        const float m = fmaxf(z0, fmaxf(z1, z2));
+        const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+        const float inv = 1.0f / (e0 + e1 + e2);
+        out[0] = e0 * inv; out[1] = e1 * inv; out[2] = e2 * inv;
+    }
+}
+
+__device__ __forceinline__ void load_pack(float *sw, const float *__restrict__ pack) {
+    const float4 *src = reinterpret_cast<const float4 *>(pack);
+    float4 *dst = reinterpret_cast<float4 *>(sw);
+    for (int e = threadIdx.x; e < kPackFloats / 4; e += blockDim.x) dst[e] = src[e];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kActThreads)
+act_forward_kernel(const float *__restrict__ pack, const uint32_t *__restrict__ obs, const int8_t *__restrict__ net,
+                   int64_t n, float *__restrict__ out) {
+    __shared__ __align__(16) float sw[kPackFloats];
+    load_pack(sw, pack);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[3];
+        mlp_forward(sw, obs[i], (int)(net[i] & 3), v);
+        out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+    }
+}
+
+// ---- warp-aggregated record append -------------------------------------------------------------
+// Every lane contributes cnt in {0,1,2} records for one destination array; one atomicAdd per warp
+// claims the tickets, lanes write their 16-byte records at consecutive slots.
+__device__ __forceinline__ uint32_t warp_claim(uint32_t *counter, int cnt, uint32_t &my_off) {
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, cnt >= 1), m2 = __ballot_sync(0xFFFFFFFFu, cnt >= 2);
+    const uint32_t total = __popc(m1) + __popc(m2);
+    my_off = __popc(m1 & lt) + __popc(m2 & lt);
+    uint32_t base = 0;
+    if (total) {
+        if (lane == 0) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    }
+    return base;
+}
+
+struct RolloutArgs {
+    uint64_t *state;
+    int64_t n;
+    uint64_t seed, game0, step0;
+    int n_steps;
+    uint32_t eta_u32, eps_u32;
+    const float *pack;
+    uint4 *rl[2];
+    uint4 *sl[2];
+    int64_t cap_rl, cap_sl;
+    uint32_t *counts;
+    unsigned long long *stats;
+    uint32_t *trace;
+    float *vec;
+    const float *forced;
+};
+
+__device__ __forceinline__ uint4 make_rl(uint32_t s, uint32_t s2, int r_half, uint32_t a, uint32_t t, uint32_t p) {
+    return make_uint4(s, s2, __float_as_uint(0.5f * (float)r_half), a | (t << 8) | (p << 16));
+}
+
+template <bool kDebug>
+__global__ void __launch_bounds__(kActThreads)
+rollout_kernel(const RolloutArgs A) {
+    __shared__ __align__(16) float sw[kPackFloats];
+    __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
+    if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
+    load_pack(sw, A.pack);
+
+    int st_act[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int st_rew[2] = {0, 0};
+    int st_hands = 0, st_trans = 0, st_drop = 0;
+    const int64_t plane = (int64_t)A.n_steps * A.n;
+    // all lanes of a warp stay in the loop together (ballots below): iterate on the warp's base index
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < A.n; base += stride) {
+        const int64_t i = base + (threadIdx.x & 31);
+        const bool live = i < A.n;
+        const uint64_t game = A.game0 + (uint64_t)i;
+        NfspW g{live ? A.state[i] : 0ull};
+        for (int t = 0; t < A.n_steps; ++t) {
+            const uint64_t step = A.step0 + (uint64_t)t;
+            uint4 recA, recB, recC, recS;
+            bool vA = false, vB = false, vC = false, vS = false;
+            int p = 0;
+            if (live) {
+                bool started = false;
+                if (g.need_reset()) {
+                    const Philox4 y = game_block(A.seed, game, step, STREAM_RESET);
+                    g.reset(g.dealer() ^ 1u, deal_ranks(__umulhi(y.x, 120u)), y.y < A.eta_u32, y.z < A.eta_u32);
+                    started = true;
+                    ++st_hands;
+                }
+                p = g.to_act();
+                const uint32_t obs = g.obs(p);
+                if (g.acted_nz(p)) {  // agent.py:132-136: remember the previous transition
+                    vA = true;
+                    recA = make_rl(g.snapshot(p), obs, 0, g.last_a(p), 0u, (uint32_t)p);
+                }
+                const uint32_t pol = g.policy(p);
+                const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
+                float v[3];
+                if (pol && x.x < A.eps_u32) {  // agent.py:125-128: np.random.rand(1,1,3)
+                    v[0] = (float)(x.y >> 8) * (1.0f / 16777216.0f);
+                    v[1] = (float)(x.z >> 8) * (1.0f / 16777216.0f);
+                    v[2] = (float)(x.w >> 8) * (1.0f / 16777216.0f);
+                } else {
+                    mlp_forward(sw, obs, p * 2 + (int)pol, v);
+                }
+                const int64_t at = (int64_t)t * A.n + i;
+                if (kDebug) {
+                    if (A.vec) { A.vec[3 * at] = v[0]; A.vec[3 * at + 1] = v[1]; A.vec[3 * at + 2] = v[2]; }
+                    if (A.forced) { v[0] = A.forced[3 * at]; v[1] = A.forced[3 * at + 1]; v[2] = A.forced[3 * at + 2]; }
+                }
+                if (pol) {  // agent.py:151: the raw score vector goes to the SL memory
+                    vS = true;
+                    recS = make_uint4(obs, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]));
+                }
+                int a = 0;  // np.argmax: first maximum
+                if (v[1] > v[a]) a = 1;
+                if (v[2] > v[a]) a = 2;
+                const bool nz = (v[0] != 0.f) || (v[1] != 0.f) || (v[2] != 0.f);
+                const int eff = g.step(a, nz, p);
+                ++st_act[p][a];
+                ++st_trans;
+                if (g.terminated()) {  // main.py:55-67: both players observe the terminal state once
+                    const int o = p ^ 1;
+                    st_rew[0] += g.reward_half(0);
+                    st_rew[1] += g.reward_half(1);
+                    if (g.acted_nz(p)) {
+                        vB = true;
+                        recB = make_rl(g.snapshot(p), g.obs(p), g.reward_half(p), g.last_a(p), 1u, (uint32_t)p);
+                    }
+                    if (g.acted_nz(o)) {
+                        vC = true;
+                        recC = make_rl(g.snapshot(o), g.obs(o), g.reward_half(o), g.last_a(o), 1u, (uint32_t)o);
+                    }
+                    g.w |= 1ull << 43;
+                }
+                if (kDebug && A.trace) {
+                    A.trace[at] = g.obs(p) | ((uint32_t)g.terminated() << 30) | ((uint32_t)p << 31);
+                    A.trace[plane + at] = __float_as_uint(0.5f * (float)g.reward_half(p));
+                    A.trace[2 * plane + at] = g.trace_misc(a, eff, started);
+                }
+            }
+            // ---- append records (warp-uniform control flow) ----
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const bool mine = live && (p == q);
+                const int cnt = mine ? ((int)vA + (int)vB) : (int)(live && vC);
+                uint32_t off;
+                const uint32_t b = warp_claim(A.counts + q, cnt, off);
+                uint4 *dst = A.rl[q];
+                if (mine) {
+                    if (vA) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recA; else ++st_drop; ++off; }
+                    if (vB) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recB; else ++st_drop; }
+                } else if (live && vC) {
+                    if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recC; else ++st_drop;
+                }
+                const int cs = (mine && vS) ? 1 : 0;
+                const uint32_t bs = warp_claim(A.counts + 2 + q, cs, off);
+                if (cs) { if ((int64_t)(bs + off) < A.cap_sl) A.sl[q][bs + off] = recS; else ++st_drop; }
+            }
+        }
+        if (live) A.state[i] = g.w;
+    }
+    if (A.stats) {
+        // block-level reduction of the per-thread counters, then 13 global atomics per CTA
+        atomicAdd(&s_stats[0], (unsigned long long)st_act[0][0]); atomicAdd(&s_stats[1], (unsigned long long)st_act[0][1]);
+        atomicAdd(&s_stats[2], (unsigned long long)st_act[0][2]); atomicAdd(&s_stats[3], (unsigned long long)st_act[1][0]);
+        atomicAdd(&s_stats[4], (unsigned long long)st_act[1][1]); atomicAdd(&s_stats[5], (unsigned long long)st_act[1][2]);
+        atomicAdd(&s_stats[6], (unsigned long long)(st_act[0][0] + st_act[0][1] + st_act[0][2]));
+        atomicAdd(&s_stats[7], (unsigned long long)(st_act[1][0] + st_act[1][1] + st_act[1][2]));
+        atomicAdd(&s_stats[8], (unsigned long long)(long long)st_rew[0]);
+        atomicAdd(&s_stats[9], (unsigned long long)(long long)st_rew[1]);
+        atomicAdd(&s_stats[10], (unsigned long long)st_hands);
+        atomicAdd(&s_stats[11], (unsigned long long)st_trans);
+        atomicAdd(&s_stats[12], (unsigned long long)st_drop);
+        __syncthreads();
+        if (threadIdx.x < 13 && s_stats[threadIdx.x]) atomicAdd(A.stats + threadIdx.x, s_stats[threadIdx.x]);
+    }
+}
+
+}  // namespace nfsp
+
+using namespace nfsp;
+
+extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *stream) {
+    NFSP_CHECK_ARG(h != nullptr && d_weights != nullptr, "null argument");
+    NFSP_CHECK_ARG(h->rules == NFSP_RULES_NFSP, "acting nets need NFSP rules");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
+    if (!h->d_wpack) NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * kPackFloats));
+    pack_weights_kernel<<<(kPackFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
+    NFSP_LAUNCH_CHECK();
+    h->has_weights = true;
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
+                                void *stream) {
+    NFSP_CHECK_ARG(h != nullptr && d_obs && d_net && d_out && n >= 0, "bad arguments");
+    if (!h->has_weights) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
+    if (n == 0) return NFSP_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
+    const int grid = grid_for(n, kActThreads, h->sm_count, 4);
+    act_forward_kernel<<<grid, kActThreads, 0, (cudaStream_t)stream>>>(h->d_wpack, d_obs, d_net, n, d_out);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io,
+                            void *stream) {
+    NFSP_CHECK_ARG(h != nullptr && io != nullptr, "null argument");
+    NFSP_CHECK_ARG(h->rules == NFSP_RULES_NFSP, "rollout needs NFSP rules");
+    NFSP_CHECK_ARG(n_steps >= 1, "n_steps must be >= 1");
+    NFSP_CHECK_ARG(io->d_rl[0] && io->d_rl[1] && io->d_sl[0] && io->d_sl[1] && io->d_counts, "missing staging arrays");
+    NFSP_CHECK_ARG(io->cap_rl > 0 && io->cap_sl > 0 && io->cap_rl < ((int64_t)1 << 32) && io->cap_sl < ((int64_t)1 << 32),
+                   "staging capacity out of range");
+    if (!h->has_weights) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
+    RolloutArgs A;
+    A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
+    A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack;
+    for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
+    A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.counts = io->d_counts;
+    A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
+    const int grid = grid_for(h->n, kActThreads, h->sm_count, 4);
+    const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
+    if (debug) rollout_kernel<true><<<grid, kActThreads, 0, (cudaStream_t)stream>>>(A);
+    else rollout_kernel<false><<<grid, kActThreads, 0, (cudaStream_t)stream>>>(A);
+    NFSP_LAUNCH_CHECK();
+    h->step += (uint64_t)n_steps;
+    return NFSP_OK;
+}

@@ -1,0 +1,215 @@
+// K3/K4/K5: the agent memories.
+//   K3 circular replay insert  (utils/replay_buffer.py:30-41)   16-byte records, streaming copy
+//   K4 reservoir insert        (utils/ReservoirBuffer.py:18-28) Philox Algorithm R, two passes
+//   K5 minibatch sample        (replay_buffer.py:46-59, ReservoirBuffer.py:33-43) Floyd + gather/expand
+// All counts live in device memory: no host synchronisation on the hot path.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace nfsp {
+
+constexpr int kBufThreads = 256;
+
+__device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+
+// ---- K3 ------------------------------------------------------------------------------------------
+// staged record i gets ticket total+i and lands in slot ticket % cap; of a batch larger than the ring
+// only the last `cap` records survive (the others would be evicted by popleft(), replay_buffer.py:40).
+__global__ void __launch_bounds__(kBufThreads)
+ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__restrict__ total_p,
+                   const uint4 *__restrict__ recs, const uint32_t *__restrict__ n_p, uint64_t max_n) {
+    const uint64_t total = *total_p;
+    uint64_t m = *n_p;
+    if (m > max_n) m = max_n;
+    const uint64_t first = m > cap ? m - cap : 0;
+    for (uint64_t i = first + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
+        ring[(total + i) % cap] = recs[i];
+}
+
+// runs after the insert kernel(s) of a batch: total += n, staged count cleared for the next rollout
+__global__ void commit_kernel(uint64_t *total_p, uint32_t *n_p, uint64_t max_n) {
+    uint64_t m = *n_p;
+    if (m > max_n) m = max_n;
+    *total_p += m;
+    *n_p = 0;
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket, uint64_t cap, int mode) {
+    if (ticket < cap) return (int64_t)ticket;  // fill phase, ReservoirBuffer.py:22-24
+    const uint64_t u = buffer_u64(seed, ticket, 0, STREAM_RESERVOIR);
+    if (mode == 1) {  // the reference's law: j = randrange(1, B+1); replace iff j < B (ReservoirBuffer.py:26-28)
+        const uint64_t j = 1u + mulhi64(u, cap);
+        return j < cap ? (int64_t)j : -1;
+    }
+    const uint64_t j = mulhi64(u, ticket + 1u);  // Algorithm R: j ~ U[0, ticket]
+    return j < cap ? (int64_t)j : -1;
+}
+
+// pass 1: every accepted record stamps its slot with ticket+1; atomicMax keeps the latest
+__global__ void __launch_bounds__(kBufThreads)
+reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, const uint64_t *__restrict__ total_p,
+                       const uint32_t *__restrict__ n_p, uint64_t max_n, uint64_t seed, int mode) {
+    const uint64_t total = *total_p;
+    uint64_t m = *n_p;
+    if (m > max_n) m = max_n;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t slot = reservoir_slot(seed, total + i, cap, mode);
+        if (slot >= 0) atomicMax(stamp + slot, (unsigned long long)(total + i + 1u));
+    }
+}
+
+// pass 2: the record whose ticket owns the stamp writes the payload (== sequential order of adds)
+__global__ void __launch_bounds__(kBufThreads)
+reservoir_write_kernel(uint4 *__restrict__ res, const unsigned long long *__restrict__ stamp, uint64_t cap,
+                       const uint64_t *__restrict__ total_p, const uint4 *__restrict__ recs,
+                       const uint32_t *__restrict__ n_p, uint64_t max_n, uint64_t seed, int mode) {
+    const uint64_t total = *total_p;
+    uint64_t m = *n_p;
+    if (m > max_n) m = max_n;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t slot = reservoir_slot(seed, total + i, cap, mode);
+        if (slot >= 0 && stamp[slot] == (unsigned long long)(total + i + 1u)) res[slot] = recs[i];
+    }
+}
+
+// ---- K5 ------------------------------------------------------------------------------------------
+// Floyd's algorithm (1987) for `batch` distinct positions out of `count`: for i = count-batch .. count-1
+// draw t ~ U[0,i]; take t unless already taken, else take i.  One CTA: the draws are computed in
+// parallel, the "already taken" scan is a warp-parallel compare over the prefix.
+constexpr int kMaxBatch = 1024;
+
+__global__ void __launch_bounds__(kBufThreads)
+sample_kernel(uint64_t seed, uint64_t call_idx, const uint64_t *__restrict__ total_p, uint64_t cap, int is_ring,
+              int batch, int64_t *__restrict__ idx_out, uint32_t *__restrict__ n_out) {
+    __shared__ uint64_t draw[kMaxBatch];
+    __shared__ uint64_t pick[kMaxBatch];
+    const uint64_t total = *total_p;
+    const uint64_t count = total < cap ? total : cap;
+    const int b = (uint64_t)batch < count ? batch : (int)count;
+    const uint64_t lo = count - (uint64_t)b;
+    for (int m = threadIdx.x; m < b; m += blockDim.x)
+        draw[m] = mulhi64(buffer_u64(seed, (uint64_t)m, call_idx, STREAM_SAMPLE), lo + (uint64_t)m + 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        for (int m = 0; m < b; ++m) {
+            const uint64_t t = draw[m];
+            bool dup = false;
+            for (int k = threadIdx.x; k < m; k += 32) dup |= (pick[k] == t);
+            dup = __any_sync(0xFFFFFFFFu, dup);
+            if (threadIdx.x == 0) pick[m] = dup ? lo + (uint64_t)m : t;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // deque position (oldest first) -> storage slot
+    const uint64_t head = (is_ring && total >= cap) ? total % cap : 0;
+    for (int m = threadIdx.x; m < batch; m += blockDim.x) {
+        int64_t slot = -1;
+        if (m < b) slot = is_ring ? (int64_t)((head + pick[m]) % cap) : (int64_t)pick[m];
+        idx_out[m] = slot;
+    }
+    if (threadIdx.x == 0 && n_out) *n_out = (uint32_t)b;
+}
+
+__global__ void __launch_bounds__(kBufThreads)
+gather_rl_kernel(const uint4 *__restrict__ ring, const int64_t *__restrict__ idx, int batch, float *__restrict__ s,
+                 float *__restrict__ a, float *__restrict__ r, float *__restrict__ s2, float *__restrict__ t) {
+    // one thread per output element of the widest rows (30 + 30 + 3 + 1 + 1 = 65 columns)
+    const int total = batch * 65;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int row = e / 65, col = e - row * 65;
+        const int64_t slot = idx[row];
+        const uint4 rec = slot >= 0 ? ring[slot] : make_uint4(0, 0, 0, 0);
+        if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
+        else if (col < 60) s2[row * 30 + (col - 30)] = (float)((rec.y >> (col - 30)) & 1u);
+        else if (col < 63) a[row * 3 + (col - 60)] = ((rec.w & 0xFFu) == (uint32_t)(col - 60)) ? 1.f : 0.f;
+        else if (col == 63) r[row] = __uint_as_float(rec.z);
+        else t[row] = (float)((rec.w >> 8) & 0xFFu);
+    }
+}
+
+__global__ void __launch_bounds__(kBufThreads)
+gather_sl_kernel(const uint4 *__restrict__ res, const int64_t *__restrict__ idx, int batch, float *__restrict__ s,
+                 float *__restrict__ a) {
+    const int total = batch * 33;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int row = e / 33, col = e - row * 33;
+        const int64_t slot = idx[row];
+        const uint4 rec = slot >= 0 ? res[slot] : make_uint4(0, 0, 0, 0);
+        if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
+        else a[row * 3 + (col - 30)] = __uint_as_float(col == 30 ? rec.y : (col == 31 ? rec.z : rec.w));
+    }
+}
+
+static int insert_grid(int64_t max_n) {
+    int64_t g = (max_n + kBufThreads - 1) / kBufThreads;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace nfsp
+
+using namespace nfsp;
+
+extern "C" int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_n,
+                                int64_t max_n, void *stream) {
+    NFSP_CHECK_ARG(d_ring && d_total && d_recs && d_n && cap > 0 && max_n >= 0, "bad arguments");
+    if (max_n == 0) return NFSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ring_insert_kernel<<<insert_grid(max_n), kBufThreads, 0, st>>>((uint4 *)d_ring, (uint64_t)cap, d_total,
+                                                                   (const uint4 *)d_recs, d_n, (uint64_t)max_n);
+    NFSP_LAUNCH_CHECK();
+    commit_kernel<<<1, 1, 0, st>>>(d_total, d_n, (uint64_t)max_n);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp,
+                                     const void *d_recs, uint32_t *d_n, int64_t max_n, uint64_t seed, int mode,
+                                     void *stream) {
+    NFSP_CHECK_ARG(d_res && d_total && d_stamp && d_recs && d_n && cap > 0 && max_n >= 0, "bad arguments");
+    NFSP_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
+    if (max_n == 0) return NFSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = insert_grid(max_n);
+    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>((unsigned long long *)d_stamp, (uint64_t)cap, d_total, d_n,
+                                                         (uint64_t)max_n, seed, mode);
+    NFSP_LAUNCH_CHECK();
+    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>((uint4 *)d_res, (const unsigned long long *)d_stamp,
+                                                         (uint64_t)cap, d_total, (const uint4 *)d_recs, d_n,
+                                                         (uint64_t)max_n, seed, mode);
+    NFSP_LAUNCH_CHECK();
+    commit_kernel<<<1, 1, 0, st>>>(d_total, d_n, (uint64_t)max_n);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_total, int64_t cap,
+                                   int is_ring, int batch, int64_t *d_idx, uint32_t *d_n_out, void *stream) {
+    NFSP_CHECK_ARG(d_total && d_idx && cap > 0, "bad arguments");
+    NFSP_CHECK_ARG(batch >= 1 && batch <= kMaxBatch, "batch must be in [1,%d]", kMaxBatch);
+    sample_kernel<<<1, kBufThreads, 0, (cudaStream_t)stream>>>(seed, call_idx, d_total, (uint64_t)cap, is_ring, batch,
+                                                               d_idx, d_n_out);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_gather_rl(const void *d_ring, const int64_t *d_idx, int batch, float *d_s, float *d_a, float *d_r,
+                              float *d_s2, float *d_t, void *stream) {
+    NFSP_CHECK_ARG(d_ring && d_idx && d_s && d_a && d_r && d_s2 && d_t && batch >= 1, "bad arguments");
+    gather_rl_kernel<<<(batch * 65 + kBufThreads - 1) / kBufThreads, kBufThreads, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)d_ring, d_idx, batch, d_s, d_a, d_r, d_s2, d_t);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_gather_sl(const void *d_res, const int64_t *d_idx, int batch, float *d_s, float *d_a,
+                              void *stream) {
+    NFSP_CHECK_ARG(d_res && d_idx && d_s && d_a && batch >= 1, "bad arguments");
+    gather_sl_kernel<<<(batch * 33 + kBufThreads - 1) / kBufThreads, kBufThreads, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)d_res, d_idx, batch, d_s, d_a);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}

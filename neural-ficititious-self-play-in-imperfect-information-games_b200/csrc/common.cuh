@@ -1,0 +1,70 @@
+// Shared host-side plumbing of libnfsp_b200.so: the handle, error reporting, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/nfsp_b200.h"
+
+struct nfsp_env_s {
+    int rules;
+    int device;
+    int sm_count;
+    int64_t n;
+    uint64_t seed, game0, step;
+    uint64_t *d_state;   // n packed words
+    float *d_wpack;      // acting nets repacked for the kernels (act_kernels.cu), or nullptr
+    void *d_wtc;         // tensor-core operand image of layer 1 (act_tc_kernels.cu), or nullptr
+    bool has_weights;
+};
+
+namespace nfsp {
+
+int set_error(int code, const char *fmt, ...);
+
+#define NFSP_CHECK_ARG(cond, ...)                                    \
+    do {                                                             \
+        if (!(cond)) return nfsp::set_error(NFSP_E_ARG, __VA_ARGS__); \
+    } while (0)
+
+#define NFSP_CUDA(call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return nfsp::set_error(NFSP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                   __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define NFSP_LAUNCH_CHECK() NFSP_CUDA(cudaGetLastError())
+
+// floor(x * 2^32) clamped: the integer threshold a Philox u32 is compared with for P(event) = x
+inline uint32_t frac_u32(double x) {
+    if (!(x > 0.0)) return 0u;
+    const double v = x * 4294967296.0;
+    return v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
+}
+
+// grid for a grid-stride loop over n items: whole waves of the SM count, capped by the work
+inline int grid_for(int64_t n, int threads, int sm_count, int ctas_per_sm) {
+    const int64_t need = (n + threads - 1) / threads;
+    const int64_t full = (int64_t)sm_count * ctas_per_sm;
+    int64_t g = need < full ? need : full;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace nfsp

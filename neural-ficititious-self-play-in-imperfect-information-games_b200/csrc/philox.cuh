@@ -1,0 +1,59 @@
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11), device side.
+// Replaces the reference's global Mersenne-Twister `random` (deck.py:2,42-44; main.py:38-45;
+// agent.py:125-128) with a stateless stream keyed by (seed; game id, step, purpose) so that a
+// game's randomness does not depend on how games are sharded over GPUs.
+#pragma once
+#include <cstdint>
+
+namespace nfsp {
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// purposes (counter word 3); must match DESIGN.md "Philox streams"
+enum : uint32_t { STREAM_STEP = 0, STREAM_RESET = 1, STREAM_RESERVOIR = 2, STREAM_SAMPLE = 3 };
+
+__device__ __forceinline__ Philox4 game_block(uint64_t seed, uint64_t game, uint64_t step, uint32_t stream) {
+    return philox4x32_10((uint32_t)game, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ uint64_t buffer_u64(uint64_t seed, uint64_t idx, uint64_t call, uint32_t stream) {
+    const Philox4 o = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)call, stream, (uint32_t)seed,
+                                    (uint32_t)(seed >> 32));
+    return (uint64_t)o.x | ((uint64_t)o.y << 32);
+}
+
+// Uniform ordered draw of 3 distinct cards out of the 6-card deck [r0s0,r0s1,r1s0,r1s1,r2s0,r2s1]
+// (deck.py:35-50: shuffle, then pop p0, p1, public).  idx in [0,120).  Returns ranks packed
+// c0 | c1<<2 | pub<<4.
+__device__ __forceinline__ uint32_t deal_ranks(uint32_t idx) {
+    const uint32_t i0 = idx / 20u, r = idx - i0 * 20u;
+    const uint32_t j1 = r >> 2, j2 = r & 3u;
+    const uint32_t i1 = j1 + (j1 >= i0);
+    const uint32_t lo = min(i0, i1), hi = max(i0, i1);
+    uint32_t i2 = j2;
+    i2 += (i2 >= lo);
+    i2 += (i2 >= hi);
+    return (i0 >> 1) | ((i1 >> 1) << 2) | ((i2 >> 1) << 4);
+}
+
+}  // namespace nfsp

@@ -391,7 +391,6 @@ static uint32_t trace_misc(const NfspGame *g, int raw, int started) {
     m |= (uint32_t)started << 21;
     m |= (uint32_t)g->policy[0] << 22;
     m |= (uint32_t)g->policy[1] << 23;
-    m |= ((uint32_t)g->hand_count & 0xffu) << 24;
     return m;
 }
 
@@ -607,8 +606,7 @@ void orc_legacy_batch_rollout(OrcLegacyBatch *b, uint64_t step0, int n_iters, co
                     r->terminal = (int8_t)o5[4];
                     r->reward = o5[3];
                     r->misc = (uint32_t)a[p] | ((uint32_t)(g->env.left[p] + 1) << 2) |
-                              ((uint32_t)g->env.pot[p] << 5) | ((uint32_t)started << 8) |
-                              (((uint32_t)g->hand_count & 0xffffu) << 16);
+                              ((uint32_t)g->env.pot[p] << 5) | ((uint32_t)started << 8);
                 }
             }
             if (term) g->need_reset = 1;

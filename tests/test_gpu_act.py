@@ -1,0 +1,337 @@
+"""-m gpu: NFSP acting (K2) and the memories (K3/K4/K5) against the CPU oracle.
+
+Integer work (records, slots, indices, counters) is bit-exact; the MLP outputs (Q-values and
+policy probabilities) are compared at 1e-5 absolute in fp32, the tolerance BASELINE.json states.
+Action selection is checked on the kernel's OWN score vectors (teacher forcing), so a last-bit
+difference in a near-tie cannot derail the env trace comparison.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402
+
+TOL = 1e-5  # BASELINE.json north_star: "within 1e-5 absolute (fp32)"
+
+
+def load(golden_dir, name):
+    with np.load(os.path.join(golden_dir, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nfsp_b200
+
+    assert torch.cuda.is_available()
+    return nfsp_b200
+
+
+def canon(recs):
+    """16-byte records as a lexicographically sorted [n,4] uint32 matrix (order-free comparison)."""
+    a = np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def raw16(recs):
+    return np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4)
+
+
+def random_nets(seed, scale=1.0):
+    rng = np.random.RandomState(seed)
+    w = np.zeros((4, 2179), np.float32)
+    for k in range(4):
+        w[k, :1920] = rng.uniform(-0.2526, 0.2526, 1920) * scale
+        w[k, 1920:1984] = rng.uniform(-0.2, 0.2, 64)
+        w[k, 1984:2176] = rng.uniform(-0.2993, 0.2993, 192) * scale
+        w[k, 2176:] = rng.uniform(-0.2, 0.2, 3)
+    return w
+
+
+def oracle_nets(nb, w):
+    return orc.Nets([nb.split_net(w[k]) for k in range(4)])
+
+
+def test_forward_q_values_and_policy_probabilities(nb, golden_dir):
+    """Every observation the game can produce x four nets: |GPU - oracle| <= 1e-5, and the fp32 oracle
+    itself is bounded by a float64 evaluation."""
+    g = load(golden_dir, "nfsp_exhaustive.npz")
+    obs = np.unique(np.concatenate([g["obs_before"].ravel(), g["obs_after"].ravel()])).astype(np.uint32)
+    for seed, scale in ((0, 1.0), (1, 4.0)):
+        w = random_nets(seed, scale)
+        sp = nb.SelfPlay(64, weights=torch.from_numpy(w), rl_capacity=1024, sl_capacity=1024)
+        nets = oracle_nets(nb, w)
+        x = ((obs[:, None] >> np.arange(30)) & 1).astype(np.float32)
+        for k in range(4):
+            got = sp.forward(torch.from_numpy(obs.astype(np.int32)), torch.full((len(obs),), k, dtype=torch.int8))
+            got = got.cpu().numpy()
+            ref = nets.forward(k, x, "br" if k & 1 else "avg")
+            assert np.abs(got - ref).max() <= TOL, (seed, k, np.abs(got - ref).max())
+            # float64 bound
+            wk = {a: b.astype(np.float64) for a, b in nb.split_net(w[k]).items()}
+            h = np.maximum(x @ wk["W1"] + wk["b1"], 0)
+            z = h @ wk["W2"] + wk["b2"]
+            if k & 1:
+                ref64 = np.maximum(z, 0)
+            else:
+                e = np.exp(z - z.max(1, keepdims=True))
+                ref64 = e / e.sum(1, keepdims=True)
+                assert np.abs(got.sum(1) - 1).max() < 1e-5
+            assert np.abs(got - ref64).max() <= TOL
+
+
+@pytest.mark.parametrize("n,steps,eta,eps", [(1, 30, 0.5, 0.5), (1000, 12, 0.1, 0.06), (50_000, 8, 0.3, 0.2)])
+def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps):
+    """The fused act+step+remember kernel vs the oracle's restatement of Agent.play/main.train."""
+    seed = 2024
+    w = random_nets(5)
+    sp = nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=eps, rl_capacity=1 << 12,
+                     sl_capacity=1 << 12, max_steps_per_call=steps)
+    out = sp.rollout(steps, insert=False, debug=True)
+    rl, sl = sp.staged()
+    vec = out["vec"].cpu().numpy()
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(eta))
+    ref = b.rollout_act(1, steps, oracle_nets(nb, w), orc.u32_frac(eta), orc.u32_frac(eps), forced_vec=vec)
+    tr = out["raw"].cpu().numpy().view(np.uint32)
+    assert np.array_equal(tr[0], ref["trace"]["obs"])
+    assert np.array_equal(tr[1].view(np.float32), ref["trace"]["reward"])
+    assert np.array_equal(tr[2], ref["trace"]["misc"])
+    assert np.abs(vec - ref["vec"]).max() <= TOL
+    for p in range(2):
+        assert len(rl[p]) == len(ref["rl"][p]) and len(sl[p]) == len(ref["sl"][p])
+        assert np.array_equal(canon(rl[p]), canon(ref["rl"][p]))
+        assert np.array_equal(canon(sl[p]), canon(ref["sl"][p]))
+    st = sp.read_stats()
+    assert [st["a0_fold"], st["a0_call"], st["a0_raise"]] == list(ref["actions"][0])
+    assert [st["a1_fold"], st["a1_call"], st["a1_raise"]] == list(ref["actions"][1])
+    assert [st["played0"], st["played1"]] == list(ref["played"])
+    to_s = lambda v: v - (1 << 64) if v >= 1 << 63 else v  # noqa: E731
+    assert [to_s(st["reward0_half"]), to_s(st["reward1_half"])] == list(ref["reward_half"])
+    assert st["hands"] == ref["hands"] and st["transitions"] == n * steps and st["dropped"] == 0
+    # epsilon / eta frequencies are what was asked for
+    if n >= 1000:
+        frac_b = sum(len(x) for x in sl) / float(n * steps)
+        assert abs(frac_b - eta) < 0.02
+
+
+def test_fused_rollout_golden_hands(nb, golden_dir):
+    """All 20 352 reference hands (incl. zero vectors and argmax ties) through the fused kernel with the
+    reference's scripted score vectors; records must equal the oracle's, which is pinned to the
+    reference's own Agent.play / main.train on exactly these hands."""
+    g = load(golden_dir, "nfsp_exhaustive.npz")
+    T, D = g["kind"].shape
+    w = random_nets(9)
+    sp = nb.SelfPlay(T, weights=torch.from_numpy(w), seed=3, rl_capacity=1024, sl_capacity=1024, max_steps_per_call=D)
+    sp.env.set_hands(g["dealer"], g["cards"], g["policy"])
+    forced = np.ascontiguousarray(g["vec"].transpose(1, 0, 2))  # [D, T, 3]; zeros after a hand's last decision
+    sp.env.step_counter = 1
+    out = sp.rollout(D, insert=False, forced_vec=forced)
+    rl, sl = sp.staged()
+    b = orc.NfspBatch(T, 3)
+    for i in range(T):
+        b.inject(i, g["dealer"][i], g["cards"][i], g["policy"][i])
+    ref = b.rollout_act(1, D, oracle_nets(nb, w), orc.u32_frac(0.1), orc.u32_frac(0.06), forced_vec=forced)
+    tr = out["raw"].cpu().numpy().view(np.uint32)
+    assert np.array_equal(tr[0], ref["trace"]["obs"]) and np.array_equal(tr[2], ref["trace"]["misc"])
+    for p in range(2):
+        assert np.array_equal(canon(rl[p]), canon(ref["rl"][p]))
+        assert np.array_equal(canon(sl[p]), canon(ref["sl"][p]))
+    # and directly against the fixture for the first hand of every game: RL adds of player 0
+    first = np.zeros(T, bool)
+    n0 = sum(int((g["rl_player"][i, : g["n_rl"][i]] == 0).sum()) for i in range(T))
+    assert len(rl[0]) >= n0
+
+
+# ------------------------------------------------------------------------------- memories
+def _stage(nb, recs, dev):
+    d = torch.from_numpy(recs.view(np.int32).reshape(-1, 4).copy()).to(dev)
+    n = torch.tensor([len(recs)], dtype=torch.int32, device=dev)
+    return d, n
+
+
+def test_ring_insert_vs_oracle_and_reference(nb, golden_dir):
+    g = load(golden_dir, "buffers.npz")
+    cap, n = int(g["cap"]), int(g["n_add"])
+    recs = np.zeros(n, orc.RL_DT)
+    recs["s"], recs["s2"], recs["a"], recs["r"], recs["t"] = g["in_s"], g["in_s2"], g["in_a"], g["in_r"], g["in_t"]
+    ring = nb.DeviceRing(cap, seed=1)
+    # uneven batches, one of them larger than the ring
+    for lo, hi in ((0, 7), (7, 40), (40, 41), (41, 120), (120, n)):
+        ring.insert(*_stage(nb, recs[lo:hi], ring.device))
+    data, count, total = orc.ring_insert_all(recs, cap)
+    assert ring.size() == count == cap and int(ring.total.item()) == total
+    got = ring.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)
+    assert np.array_equal(raw16(got), raw16(data))
+    # deque order == the reference's buffer contents
+    head = total % cap
+    order = [(head + i) % cap for i in range(cap)]
+    assert np.array_equal(got["s"][order], g["ring_s"]) and np.array_equal(got["r"][order], g["ring_r"])
+    # one batch much larger than the ring
+    big = nb.DeviceRing(16, seed=1)
+    big.insert(*_stage(nb, recs, big.device))
+    d2, _, _ = orc.ring_insert_all(recs, 16)
+    assert np.array_equal(big.data.cpu().numpy().view(np.uint32), raw16(d2))
+
+
+@pytest.mark.parametrize("mode", ["R", "reference"])
+def test_reservoir_insert_vs_oracle(nb, mode):
+    """Algorithm R with Philox keyed by ticket; batches with same-slot collisions resolve like the
+    sequential algorithm (largest ticket wins)."""
+    cap, seed = 97, 77
+    rng = np.random.RandomState(3)
+    recs = np.zeros(20000, orc.SL_DT)
+    recs["s"] = rng.randint(0, 1 << 30, len(recs))
+    recs["a"] = rng.rand(len(recs), 3).astype(np.float32)
+    res = nb.DeviceReservoir(cap, seed=seed, mode=mode)
+    edges = [0, 5, 96, 97, 98, 500, 501, 9000, 20000]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        res.insert(*_stage(nb, recs[lo:hi], res.device))
+    data, count, total = orc.reservoir_insert_all(recs, cap, seed, mode=0 if mode == "R" else 1)
+    assert res.size() == count and int(res.total.item()) == total == len(recs)
+    got = res.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+    assert np.array_equal(raw16(got), raw16(data))
+    if mode == "reference":  # slot 0 is never replaced (ReservoirBuffer.py:26-28)
+        assert got[0].tobytes() == recs[0].tobytes()
+
+
+def test_sample_indices_and_gather(nb):
+    seed = 11
+    rng = np.random.RandomState(5)
+    for cap, n_ins, batch in ((1000, 400, 256), (1000, 2600, 256), (300, 300, 256), (64, 10, 256), (5000, 5000, 1024)):
+        recs = np.zeros(n_ins, orc.RL_DT)
+        recs["s"] = rng.randint(0, 1 << 30, n_ins)
+        recs["s2"] = rng.randint(0, 1 << 30, n_ins)
+        recs["a"] = rng.randint(0, 3, n_ins)
+        recs["r"] = rng.randint(-10, 11, n_ins) * 0.5
+        recs["t"] = rng.randint(0, 2, n_ins)
+        ring = nb.DeviceRing(cap, seed=seed)
+        ring.insert(*_stage(nb, recs, ring.device))
+        for call in range(3):
+            b = min(batch, ring.size())
+            s, a, r, s2, t, idx, nn = ring.sample(b)
+            count, total = ring.size(), n_ins
+            pos = orc.sample_indices(seed, call, count, b)
+            head = total % cap if total >= cap else 0
+            slots = (head + pos) % cap
+            assert int(nn.item()) == b and np.array_equal(idx.cpu().numpy(), slots)
+            assert len(set(slots.tolist())) == b
+            stored = ring.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)[slots]
+            bits = lambda m: ((m[:, None] >> np.arange(30)) & 1).astype(np.float32)  # noqa: E731
+            assert np.array_equal(s.cpu().numpy(), bits(stored["s"])) and np.array_equal(s2.cpu().numpy(), bits(stored["s2"]))
+            assert np.array_equal(a.cpu().numpy(), np.eye(3, dtype=np.float32)[stored["a"]])
+            assert np.array_equal(r.cpu().numpy(), stored["r"]) and np.array_equal(t.cpu().numpy(), stored["t"].astype(np.float32))
+    res = nb.DeviceReservoir(500, seed=seed)
+    sl = np.zeros(1200, orc.SL_DT)
+    sl["s"] = rng.randint(0, 1 << 30, len(sl))
+    sl["a"] = rng.rand(len(sl), 3)
+    res.insert(*_stage(nb, sl, res.device))
+    s, a, idx, nn = res.sample(256)
+    pos = orc.sample_indices(seed, 0, 500, 256)
+    assert np.array_equal(idx.cpu().numpy(), pos)
+    stored = res.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)[pos]
+    assert np.array_equal(a.cpu().numpy(), stored["a"])
+
+
+def test_memories_after_rollout_match_sequential_oracle(nb):
+    """rollout -> flush: ring / reservoir contents equal the oracle fed with the staged records in ticket order."""
+    n, steps, seed = 3000, 6, 8
+    sp = nb.SelfPlay(n, seed=seed, eta=0.4, epsilon=0.1, rl_capacity=5000, sl_capacity=2000, max_steps_per_call=steps)
+    rings = [np.zeros(0, orc.RL_DT), np.zeros(0, orc.RL_DT)]
+    ress = [np.zeros(0, orc.SL_DT), np.zeros(0, orc.SL_DT)]
+    for _ in range(3):
+        sp.rollout(steps, insert=False)
+        rl, sl = sp.staged()
+        for p in range(2):
+            rings[p] = np.concatenate([rings[p], rl[p].astype(orc.RL_DT)])
+            ress[p] = np.concatenate([ress[p], sl[p].astype(orc.SL_DT)])
+        sp.flush()
+    for p in range(2):
+        data, count, total = orc.ring_insert_all(rings[p], 5000)
+        got = sp.rl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)
+        assert int(sp.rl[p].total.item()) == total and np.array_equal(raw16(got), raw16(data))
+        data, count, total = orc.reservoir_insert_all(ress[p], 2000, sp.sl[p].seed)
+        got = sp.sl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+        assert int(sp.sl[p].total.item()) == total and np.array_equal(raw16(got), raw16(data))
+    assert int(sp.counts.sum().item()) == 0
+
+
+def test_dropin_buffers_reference_shapes(nb, golden_dir):
+    """utils.replay_buffer.ReplayBuffer / utils.ReservoirBuffer.ReservoirBuffer: the reference's call
+    signatures, return shapes and FIFO / saturation behaviour."""
+    nb.install_dropin()
+    import utils.replay_buffer as RB
+    import utils.ReservoirBuffer as RS
+
+    g = load(golden_dir, "buffers.npz")
+    cap, n = int(g["cap"]), int(g["n_add"])
+    bits = lambda m: ((np.uint32(m) >> np.arange(30)) & 1).astype(np.float64)  # noqa: E731
+    rb = RB.ReplayBuffer(cap, 1234)
+    for i in range(n):
+        rb.add(bits(g["in_s"][i]).reshape(1, 1, 30), np.eye(3)[g["in_a"][i]].reshape(1, 1, 3), float(g["in_r"][i]),
+               bits(g["in_s2"][i]).reshape(1, 1, 30), bool(g["in_t"][i]))
+        if i in (0, 48, 49, 50, n - 1):
+            assert rb.size() == g["ring_sizes"][i]
+    s, a, r, s2, t = rb.sample_batch(16)
+    assert [s.shape, a.shape, s2.shape] == [tuple(x) for x in g["ring_sample_shapes"]] and r.shape == (16,) and t.shape == (16,)
+    stored = {(int(x), float(y)) for x, y in zip(g["ring_s"], g["ring_r"])}
+    for k in range(16):
+        m = sum(1 << j for j in range(30) if s[k, 0, j])
+        assert (m, float(r[k])) in stored
+    small = RB.ReplayBuffer(cap, 1234)
+    for i in range(5):
+        small.add(bits(g["in_s"][i]), np.eye(3)[g["in_a"][i]], 0.5, bits(g["in_s2"][i]), False)
+    assert small.sample_batch(16)[0].shape[0] == int(g["ring_small_rows"]) == 5
+    rb.clear()
+    assert rb.size() == 0
+    rs = RS.ReservoirBuffer(cap, 1234, mode="reference")
+    for i in range(n):
+        rs.add(bits(g["in_s"][i]).reshape(1, 1, 30), g["in_avec"][i].reshape(1, 1, 3))
+    assert rs.size() == cap
+    s, a = rs.sample_batch(16)
+    assert [s.shape, a.shape] == [tuple(x) for x in g["res_sample_shapes"]]
+    first = rs.memory.records()[0]
+    assert first["s"] == g["res_s"][0] and np.array_equal(first["a"], g["res_a"][0])  # slot 0 never replaced
+    with pytest.raises(ValueError):
+        rb.add(np.full(30, 0.5), np.eye(3)[0], 0.0, np.zeros(30), False)
+
+
+def test_dropin_agent_play_flow(nb):
+    """agent.agent.Agent.play over leduc.newenv.Env: one hand under main.train's call pattern."""
+    nb.install_dropin()
+    import agent.agent as agent
+    import leduc.newenv as leduc
+
+    env = leduc.Env()
+    players = [agent.Agent(None, env.observation_space, env.action_space, "Player%d" % i, env) for i in (0, 1)]
+    for hand in range(6):
+        dealer = hand & 1
+        env.reset(dealer)
+        lhand = 1 - dealer
+        policy = ["a" if (hand >> 1) & 1 else "b", "b" if hand % 3 else "a"]
+        d_s = env.get_state(dealer)[3]
+        d_t = l_t = False
+        first = True
+        for _ in range(8):
+            rnd = env.round_index
+            if not d_t:
+                d_t = players[dealer].play(policy[dealer], dealer, d_s if first else None)
+                first = False
+            if not l_t:
+                l_t = players[lhand].play(policy[lhand], lhand)
+            if rnd == env.round_index and not d_t:
+                d_t = players[dealer].play(policy[dealer], dealer)
+            if d_t and l_t:
+                break
+        assert d_t and l_t and env.terminated
+    assert players[0].played + players[1].played > 0
+    assert abs(players[0].reward + players[1].reward) < 1e-9  # zero-sum (newenv.py:344-345)
+    assert players[0]._rl_memory.size() + players[1]._rl_memory.size() > 0
+    q = players[0].best_response_model.predict(np.zeros((1, 1, 30)))
+    pi = players[0].avg_strategy_model.predict(np.zeros((1, 1, 30)))
+    assert q.shape == pi.shape == (1, 1, 3) and abs(pi.sum() - 1) < 1e-5 and (q >= 0).all()
+    assert hasattr(players[0], "act") and hasattr(players[0], "remember_opponent_behaviour")
