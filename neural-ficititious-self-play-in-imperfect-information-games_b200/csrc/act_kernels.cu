@@ -5,15 +5,16 @@
 // epsilon-greedy score vector -> argmax -> newenv step, and emits the RL / SL memory records of
 // agent.py:134-136,151 and the terminal observations of main.py:55-67.  The observation is a
 // 30-bit mask that never leaves registers; because it is binary and sparse (<= 9 bits set) the
-// first layer is a SUM OF <= 9 WEIGHT ROWS, read from shared memory as conflict-free float4s,
-// instead of a dense 30x64 product.
+// first layer is a SUM OF WEIGHT ROWS read from shared memory as float4s instead of a dense 30x64
+// product: <= 9 rows for arbitrary masks (act_forward_kernel), 3 precombined rows in the rollout.
 #include "common.cuh"
 #include "nfsp_rules.cuh"
 #include "philox.cuh"
 
 namespace nfsp {
 
-constexpr int kActThreads = 128;
+constexpr int kActThreads = 128;   // act_forward_kernel (generic observation masks)
+constexpr int kRollThreads = 256;  // rollout_kernel
 // packed weight image (floats): W1 rows as [16 col-quads][128 rows = net*32 + input][4], where input 30 is
 // the bias b1; then W2 as [64 hidden][4 nets][4 = 3 outputs + pad]; then b2 as [4 nets][4].
 constexpr int kW1Floats = 16 * 128 * 4;
@@ -38,6 +39,95 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
             if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
         }
         pack[e] = v;
+    }
+}
+
+// ---- group-factorised first layer (rollout path) --------------------------------------------------
+// Under main.train's turn order an observation is (cards of the actor, round-0 betting sequence,
+// round-1 betting sequence); each group takes few values, so W1^T x + b1 is the sum of THREE
+// precombined rows: T_cards[c_p][public state] (+ b1), T_r0[dealer][sequence], T_r1[dealer][sequence].
+// The rows are sums of W1 rows only (input independent), rebuilt whenever the weights change.
+//   per net 48 rows: 0-11 cards (c_p*4 + (revealed ? 1+pub : 0)), 12-29 round 0, 30-47 round 1
+//   (dealer*9 + sequence id: 0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC).
+// Image: rows as [16 col-quads][192 rows][4] floats, then W2 as [16 quads][4 nets][3 outputs][4], then b2.
+constexpr int kTabRows = 4 * 48;
+constexpr int kTabFloats = 16 * kTabRows * 4;
+constexpr int kTabW2Floats = 16 * 4 * 3 * 4;
+constexpr int kTabImageFloats = kTabFloats + kTabW2Floats + kB2Floats;
+constexpr int kTabImageBytes = kTabImageFloats * 4;
+
+__global__ void pack_tables_kernel(const float *__restrict__ w, float *__restrict__ img) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kTabImageFloats; e += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (e < kTabFloats) {
+            const int c = e & 3, row = (e >> 2) % kTabRows, q = (e >> 2) / kTabRows;
+            const int net = row / 48, r = row % 48, j = q * 4 + c;
+            const float *W1 = w + net * NFSP_NET_PARAMS;  // W1[i*64 + j]
+            uint32_t bits = 0;                            // observation bits this row stands for
+            if (r < 12) {
+                const int cp = r >> 2, ps = r & 3;
+                if (cp < 3) {
+                    bits = 1u << (24 + cp);
+                    if (ps) bits |= (1u << (27 + cp)) | (1u << (27 + (ps - 1)));
+                }
+            } else {
+                const int rr = (r - 12) / 18, d = ((r - 12) % 18) / 9, id = (r - 12) % 9;
+                // sequence id -> actions of slots 0..2 (1 = call, 2 = raise, 0 = none)
+                const int s0 = id == 0 ? 0 : (id == 1 || id == 3 || id == 4 || id == 7 ? 1 : 2);
+                const int s1 = id < 3 ? 0 : (id == 3 || id == 5 ? 1 : 2);
+                const int s2 = id >= 7 ? 1 : 0;
+                const int sl[3] = {s0, s1, s2};
+                for (int k = 0; k < 3; ++k)
+                    if (sl[k]) bits |= 1u << (((k & 1) ^ d) * 12 + rr * 6 + k * 2 + (sl[k] - 1));
+            }
+            for (int i = 0; i < 30; ++i)
+                if ((bits >> i) & 1u) v += W1[i * 64 + j];
+            if (r < 12 && (r >> 2) < 3) v += W1[1920 + j];  // b1 rides on the card row
+        } else if (e < kTabFloats + kTabW2Floats) {
+            const int f = e - kTabFloats, x = f & 3, c = (f >> 2) % 3, net = ((f >> 2) / 3) & 3, q = (f >> 2) / 12;
+            v = w[net * NFSP_NET_PARAMS + 1984 + (q * 4 + x) * 3 + c];
+        } else {
+            const int f = e - kTabFloats - kTabW2Floats, c = f & 3, net = f >> 2;
+            if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
+        }
+        img[e] = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t seq_id(uint32_t rnd) {  // 6 slot bits of one round -> sequence id 0..8
+    const uint32_t s0 = rnd & 3u, s1 = (rnd >> 2) & 3u, s2 = (rnd >> 4) & 3u;
+    return s2 ? 6u + s0 : (s1 ? 2u * s0 + s1 : s0);
+}
+
+// one decision of net `net` on the game word: layer 1 as 3 row reads streamed into layer 2
+__device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st, uint32_t hist, uint32_t cp,
+                                                   uint32_t pubstate, uint32_t dealer, int net, float out[3]) {
+    const float4 *T = reinterpret_cast<const float4 *>(st);
+    const uint32_t both = hist | (hist >> 12);
+    const float4 *rc = T + net * 48 + cp * 4 + pubstate;
+    const float4 *r0 = T + net * 48 + 12 + dealer * 9 + seq_id(both & 63u);
+    const float4 *r1 = T + net * 48 + 30 + dealer * 9 + seq_id((both >> 6) & 63u);
+    const float4 *w2 = reinterpret_cast<const float4 *>(st + kTabFloats) + net * 3;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float4 a = rc[q * kTabRows], b = r0[q * kTabRows], c = r1[q * kTabRows];
+        const float hx = fmaxf((b.x + c.x) + a.x, 0.f), hy = fmaxf((b.y + c.y) + a.y, 0.f);
+        const float hz = fmaxf((b.z + c.z) + a.z, 0.f), hw = fmaxf((b.w + c.w) + a.w, 0.f);
+        const float4 u0 = w2[q * 12], u1 = w2[q * 12 + 1], u2 = w2[q * 12 + 2];
+        z0 = fmaf(hx, u0.x, z0); z0 = fmaf(hy, u0.y, z0); z0 = fmaf(hz, u0.z, z0); z0 = fmaf(hw, u0.w, z0);
+        z1 = fmaf(hx, u1.x, z1); z1 = fmaf(hy, u1.y, z1); z1 = fmaf(hz, u1.z, z1); z1 = fmaf(hw, u1.w, z1);
+        z2 = fmaf(hx, u2.x, z2); z2 = fmaf(hy, u2.y, z2); z2 = fmaf(hz, u2.z, z2); z2 = fmaf(hw, u2.w, z2);
+    }
+    const float4 b2 = reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net];
+    z0 += b2.x; z1 += b2.y; z2 += b2.z;
+    if (net & 1) {
+        out[0] = fmaxf(z0, 0.f); out[1] = fmaxf(z1, 0.f); out[2] = fmaxf(z2, 0.f);
+    } else {
+        const float m = fmaxf(z0, fmaxf(z1, z2));
+        const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+        const float inv = 1.0f / (e0 + e1 + e2);
+        out[0] = e0 * inv; out[1] = e1 * inv; out[2] = e2 * inv;
     }
 }
 
@@ -136,16 +226,29 @@ __device__ __forceinline__ uint4 make_rl(uint32_t s, uint32_t s2, int r_half, ui
 }
 
 template <bool kDebug>
-__global__ void __launch_bounds__(kActThreads)
+__global__ void __launch_bounds__(kRollThreads, 3)
 rollout_kernel(const RolloutArgs A) {
-    __shared__ __align__(16) float sw[kPackFloats];
+    extern __shared__ __align__(16) float sw[];  // table image, kTabImageBytes
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
-    load_pack(sw, A.pack);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(A.pack);
+        float4 *dst = reinterpret_cast<float4 *>(sw);
+        for (int e = threadIdx.x; e < kTabImageFloats / 4; e += blockDim.x) dst[e] = src[e];
+        __syncthreads();
+    }
 
-    int st_act[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    int st_rew[2] = {0, 0};
+    // per-thread counters; the action histogram packs 3 x 21-bit fields per player (flushed before overflow)
+    unsigned long long st_act0 = 0ull, st_act1 = 0ull;
+    int st_rew0 = 0, st_rew1 = 0;
     int st_hands = 0, st_trans = 0, st_drop = 0;
+    auto flush_hist = [&]() {
+        atomicAdd(&s_stats[0], st_act0 & 0x1FFFFFull); atomicAdd(&s_stats[1], (st_act0 >> 21) & 0x1FFFFFull);
+        atomicAdd(&s_stats[2], st_act0 >> 42);
+        atomicAdd(&s_stats[3], st_act1 & 0x1FFFFFull); atomicAdd(&s_stats[4], (st_act1 >> 21) & 0x1FFFFFull);
+        atomicAdd(&s_stats[5], st_act1 >> 42);
+        st_act0 = st_act1 = 0ull;
+    };
     const int64_t plane = (int64_t)A.n_steps * A.n;
     // all lanes of a warp stay in the loop together (ballots below): iterate on the warp's base index
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -175,34 +278,40 @@ rollout_kernel(const RolloutArgs A) {
                 }
                 const uint32_t pol = g.policy(p);
                 const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
-                float v[3];
+                float v0, v1, v2;
                 if (pol && x.x < A.eps_u32) {  // agent.py:125-128: np.random.rand(1,1,3)
-                    v[0] = (float)(x.y >> 8) * (1.0f / 16777216.0f);
-                    v[1] = (float)(x.z >> 8) * (1.0f / 16777216.0f);
-                    v[2] = (float)(x.w >> 8) * (1.0f / 16777216.0f);
+                    v0 = (float)(x.y >> 8) * (1.0f / 16777216.0f);
+                    v1 = (float)(x.z >> 8) * (1.0f / 16777216.0f);
+                    v2 = (float)(x.w >> 8) * (1.0f / 16777216.0f);
                 } else {
-                    mlp_forward(sw, obs, p * 2 + (int)pol, v);
+                    float v[3];
+                    mlp_forward_tables(sw, g.hist(), g.card(p), g.round() ? 1u + g.pub() : 0u, g.dealer(),
+                                       p * 2 + (int)pol, v);
+                    v0 = v[0]; v1 = v[1]; v2 = v[2];
                 }
                 const int64_t at = (int64_t)t * A.n + i;
                 if (kDebug) {
-                    if (A.vec) { A.vec[3 * at] = v[0]; A.vec[3 * at + 1] = v[1]; A.vec[3 * at + 2] = v[2]; }
-                    if (A.forced) { v[0] = A.forced[3 * at]; v[1] = A.forced[3 * at + 1]; v[2] = A.forced[3 * at + 2]; }
+                    if (A.vec) { A.vec[3 * at] = v0; A.vec[3 * at + 1] = v1; A.vec[3 * at + 2] = v2; }
+                    if (A.forced) { v0 = A.forced[3 * at]; v1 = A.forced[3 * at + 1]; v2 = A.forced[3 * at + 2]; }
                 }
                 if (pol) {  // agent.py:151: the raw score vector goes to the SL memory
                     vS = true;
-                    recS = make_uint4(obs, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]));
+                    recS = make_uint4(obs, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2));
                 }
                 int a = 0;  // np.argmax: first maximum
-                if (v[1] > v[a]) a = 1;
-                if (v[2] > v[a]) a = 2;
-                const bool nz = (v[0] != 0.f) || (v[1] != 0.f) || (v[2] != 0.f);
+                float best = v0;
+                if (v1 > best) { a = 1; best = v1; }
+                if (v2 > best) a = 2;
+                const bool nz = (v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f);
                 const int eff = g.step(a, nz, p);
-                ++st_act[p][a];
-                ++st_trans;
+                const unsigned long long inc = 1ull << (21 * a);
+                st_act0 += p == 0 ? inc : 0ull;
+                st_act1 += p == 1 ? inc : 0ull;
+                if ((++st_trans & 0xFFFFF) == 0) flush_hist();
                 if (g.terminated()) {  // main.py:55-67: both players observe the terminal state once
                     const int o = p ^ 1;
-                    st_rew[0] += g.reward_half(0);
-                    st_rew[1] += g.reward_half(1);
+                    st_rew0 += g.reward_half(0);
+                    st_rew1 += g.reward_half(1);
                     if (g.acted_nz(p)) {
                         vB = true;
                         recB = make_rl(g.snapshot(p), g.obs(p), g.reward_half(p), g.last_a(p), 1u, (uint32_t)p);
@@ -242,17 +351,15 @@ rollout_kernel(const RolloutArgs A) {
     }
     if (A.stats) {
         // block-level reduction of the per-thread counters, then 13 global atomics per CTA
-        atomicAdd(&s_stats[0], (unsigned long long)st_act[0][0]); atomicAdd(&s_stats[1], (unsigned long long)st_act[0][1]);
-        atomicAdd(&s_stats[2], (unsigned long long)st_act[0][2]); atomicAdd(&s_stats[3], (unsigned long long)st_act[1][0]);
-        atomicAdd(&s_stats[4], (unsigned long long)st_act[1][1]); atomicAdd(&s_stats[5], (unsigned long long)st_act[1][2]);
-        atomicAdd(&s_stats[6], (unsigned long long)(st_act[0][0] + st_act[0][1] + st_act[0][2]));
-        atomicAdd(&s_stats[7], (unsigned long long)(st_act[1][0] + st_act[1][1] + st_act[1][2]));
-        atomicAdd(&s_stats[8], (unsigned long long)(long long)st_rew[0]);
-        atomicAdd(&s_stats[9], (unsigned long long)(long long)st_rew[1]);
+        flush_hist();
+        atomicAdd(&s_stats[8], (unsigned long long)(long long)st_rew0);
+        atomicAdd(&s_stats[9], (unsigned long long)(long long)st_rew1);
         atomicAdd(&s_stats[10], (unsigned long long)st_hands);
         atomicAdd(&s_stats[11], (unsigned long long)st_trans);
         atomicAdd(&s_stats[12], (unsigned long long)st_drop);
         __syncthreads();
+        if (threadIdx.x == 6) s_stats[6] = s_stats[0] + s_stats[1] + s_stats[2];  // played = sum of the histogram
+        if (threadIdx.x == 7) s_stats[7] = s_stats[3] + s_stats[4] + s_stats[5];
         if (threadIdx.x < 13 && s_stats[threadIdx.x]) atomicAdd(A.stats + threadIdx.x, s_stats[threadIdx.x]);
     }
 }
@@ -266,8 +373,15 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     NFSP_CHECK_ARG(h->rules == NFSP_RULES_NFSP, "acting nets need NFSP rules");
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
-    if (!h->d_wpack) NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * kPackFloats));
+    if (!h->d_wpack) {
+        NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats)));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+    }
     pack_weights_kernel<<<(kPackFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
+    NFSP_LAUNCH_CHECK();
+    pack_tables_kernel<<<(kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights,
+                                                                                         h->d_wpack + kPackFloats);
     NFSP_LAUNCH_CHECK();
     h->has_weights = true;
     return NFSP_OK;
@@ -290,7 +404,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
                             void *stream) {
     NFSP_CHECK_ARG(h != nullptr && io != nullptr, "null argument");
     NFSP_CHECK_ARG(h->rules == NFSP_RULES_NFSP, "rollout needs NFSP rules");
-    NFSP_CHECK_ARG(n_steps >= 1, "n_steps must be >= 1");
+    NFSP_CHECK_ARG(n_steps >= 1 && n_steps <= 4096, "n_steps must be in [1,4096]");
     NFSP_CHECK_ARG(io->d_rl[0] && io->d_rl[1] && io->d_sl[0] && io->d_sl[1] && io->d_counts, "missing staging arrays");
     NFSP_CHECK_ARG(io->cap_rl > 0 && io->cap_sl > 0 && io->cap_rl < ((int64_t)1 << 32) && io->cap_sl < ((int64_t)1 << 32),
                    "staging capacity out of range");
@@ -299,14 +413,14 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     RolloutArgs A;
     A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
-    A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack;
+    A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack + kPackFloats;
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
     A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.counts = io->d_counts;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
-    const int grid = grid_for(h->n, kActThreads, h->sm_count, 4);
+    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 3);
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
-    if (debug) rollout_kernel<true><<<grid, kActThreads, 0, (cudaStream_t)stream>>>(A);
-    else rollout_kernel<false><<<grid, kActThreads, 0, (cudaStream_t)stream>>>(A);
+    if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
+    else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     NFSP_LAUNCH_CHECK();
     h->step += (uint64_t)n_steps;
     return NFSP_OK;
