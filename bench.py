@@ -165,7 +165,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     game0, n = sharding.shard_games(GAMES_PER_GPU * world, rank, world)
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
-                            sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL)
+                            sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
 
@@ -246,10 +246,24 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # the other first-layer variant, kernel only, for the record
+    other = "tcgen05" if args.variant in ("default", "cuda") else "cuda"
+    other_ms = 0.0
+    for k in range(3 + args.steps):
+        flush_buf.zero_()
+        a, b = ev(), ev()
+        a.record()
+        sp.rollout(T_PER_CALL, insert=False, variant=other)
+        b.record()
+        b.synchronize()
+        sp.counts.zero_()
+        if k >= 3:
+            other_ms += a.elapsed_time(b)
+    other_rate = n * T_PER_CALL * args.steps / (other_ms * 1e-3)
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
-    roofline = {"bound": "hbm", "kernel": "rollout_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "rollout_tc_kernel" if args.variant == "tcgen05" else "rollout_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_transition": BYTES_PER_TRANSITION,
                 "kernel_ms_per_launch": ker_ms / args.steps, "useful_tflops": kernel_rate * 4224 / 1e12}
@@ -278,6 +292,8 @@ def run_gpu(args):
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION},
+                      "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
+                                                                 "kernel_ms_per_launch": other_ms / args.steps},
                       "hands": int(st[10]), "transitions_counted": int(st[11]), "records_dropped": int(st[12])}}
     print(json.dumps(line))
     if world > 1:
@@ -290,6 +306,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="default", choices=["default", "cuda", "tcgen05"],
+                    help="first layer of the acting nets: CUDA-core row sums or tcgen05 tensor-core tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -124,6 +124,11 @@ int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *stream);
 int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
                      void *stream);
 
+/* Same contract as nfsp_act_forward, first layer on the 5th-generation tensor cores: tcgen05.mma with the
+ * accumulator in TMEM, the four nets stacked along K, fp32 weights as an exact 3-way bf16 split. */
+int nfsp_act_forward_tc(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
+                        void *stream);
+
 /* Record formats (16 B each):
  *   RL  {u32 s, u32 s2, f32 r, u8 a, u8 t, u8 player, u8 flags}   replay_buffer.py:30-41, by value
  *   SL  {u32 s, f32 a[3]}                                          ReservoirBuffer.py:18-28       */
@@ -137,7 +142,10 @@ typedef struct {
     uint32_t *d_trace;    /* as nfsp_env_step, or NULL                                          */
     float *d_vec;         /* float[n_steps][n][3] score vectors actually used, or NULL          */
     const float *d_forced_vec; /* float[n_steps][n][3] or NULL: use these instead of the nets   */
+    int32_t variant;      /* first layer on: 1 = CUDA cores (group-factorised row sums),
+                             2 = tensor cores (tcgen05.mma, TMEM accumulator), 0 = library default */
 } nfsp_rollout_io;
+#define NFSP_ROLLOUT_DEFAULT_VARIANT 1
 
 /* The fused hot path: for n_steps, every game does one Agent.play decision (agent.py:130-156)
  * -- observe, remember the previous transition, eta-mixed policy (average net argmax /

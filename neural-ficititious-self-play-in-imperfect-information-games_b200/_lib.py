@@ -25,7 +25,7 @@ SYMBOLS = [
     "nfsp_legacy_reset", "nfsp_legacy_set_hands", "nfsp_legacy_step", "nfsp_legacy_get_new_state",
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
-    "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_rollout",
+    "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_sample_indices", "nfsp_gather_rl", "nfsp_gather_sl",
 ]
 
@@ -33,7 +33,7 @@ SYMBOLS = [
 class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
                 ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
-                ("d_forced_vec", C.c_void_p)]
+                ("d_forced_vec", C.c_void_p), ("variant", C.c_int32)]
 
 
 class NfspError(RuntimeError):
@@ -83,6 +83,7 @@ def lib():
     L.nfsp_expand_obs.argtypes = [vp, C.c_int64, vp, vp]
     L.nfsp_act_set_weights.argtypes = [vp, vp, vp]
     L.nfsp_act_forward.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
+    L.nfsp_act_forward_tc.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
     L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int64, vp]
     L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int64, C.c_uint64, C.c_int, vp]

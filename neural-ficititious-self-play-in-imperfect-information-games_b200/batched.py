@@ -352,7 +352,9 @@ class SelfPlay:
                   "reward0_half", "reward1_half", "hands", "transitions", "dropped")
 
     def __init__(self, n_games, weights=None, seed=1234, game0=0, device=None, eta=0.1, epsilon=0.06,
-                 rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R"):
+                 rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R",
+                 variant="default"):
+        self.variant = variant
         self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
         self.device, self.n = self.env.device, self.env.n
         self.eta, self.epsilon = float(eta), float(epsilon)
@@ -373,15 +375,21 @@ class SelfPlay:
         self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
         check(lib().nfsp_act_set_weights(self.env._h, _ptr(self.weights), _stream(self.device)))
 
-    def forward(self, obs_masks, net_idx):
-        """Batched Model.predict: Q-values (BR nets, odd index) / softmax probabilities (average nets)."""
+    def forward(self, obs_masks, net_idx, tensor_cores=False):
+        """Batched Model.predict: Q-values (BR nets, odd index) / softmax probabilities (average nets).
+        tensor_cores=True runs the first layer as tcgen05.mma tiles (TMEM accumulator)."""
         o = _as(obs_masks, torch.int32, self.device).reshape(-1)
         k = _as(net_idx, torch.int8, self.device).reshape(-1)
         out = torch.empty((o.numel(), 3), dtype=torch.float32, device=self.device)
-        check(lib().nfsp_act_forward(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
+        fn = lib().nfsp_act_forward_tc if tensor_cores else lib().nfsp_act_forward
+        check(fn(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
         return out
 
-    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None):
+    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2}
+
+    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None):
+        """variant: "cuda" (first layer as row sums on CUDA cores), "tcgen05" (first layer as tensor-core
+        tiles with the accumulator in TMEM) or None = self.variant."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
         io = _lib.RolloutIO()
@@ -389,6 +397,7 @@ class SelfPlay:
             io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
         io.cap_rl, io.cap_sl = self.cap_rl, self.cap_sl
         io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
+        io.variant = self.VARIANTS[variant or self.variant]
         dbg = None
         if debug or forced_vec is not None:
             tr = torch.empty((3, n_steps, self.n), dtype=torch.int32, device=self.device)

@@ -7,9 +7,7 @@
 // 30-bit mask that never leaves registers; because it is binary and sparse (<= 9 bits set) the
 // first layer is a SUM OF WEIGHT ROWS read from shared memory as float4s instead of a dense 30x64
 // product: <= 9 rows for arbitrary masks (act_forward_kernel), 3 precombined rows in the rollout.
-#include "common.cuh"
-#include "nfsp_rules.cuh"
-#include "philox.cuh"
+#include "rollout_common.cuh"
 
 namespace nfsp {
 
@@ -188,43 +186,6 @@ act_forward_kernel(const float *__restrict__ pack, const uint32_t *__restrict__ 
     }
 }
 
-// ---- warp-aggregated record append -------------------------------------------------------------
-// Every lane contributes cnt in {0,1,2} records for one destination array; one atomicAdd per warp
-// claims the tickets, lanes write their 16-byte records at consecutive slots.
-__device__ __forceinline__ uint32_t warp_claim(uint32_t *counter, int cnt, uint32_t &my_off) {
-    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, cnt >= 1), m2 = __ballot_sync(0xFFFFFFFFu, cnt >= 2);
-    const uint32_t total = __popc(m1) + __popc(m2);
-    my_off = __popc(m1 & lt) + __popc(m2 & lt);
-    uint32_t base = 0;
-    if (total) {
-        if (lane == 0) base = atomicAdd(counter, total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    }
-    return base;
-}
-
-struct RolloutArgs {
-    uint64_t *state;
-    int64_t n;
-    uint64_t seed, game0, step0;
-    int n_steps;
-    uint32_t eta_u32, eps_u32;
-    const float *pack;
-    uint4 *rl[2];
-    uint4 *sl[2];
-    int64_t cap_rl, cap_sl;
-    uint32_t *counts;
-    unsigned long long *stats;
-    uint32_t *trace;
-    float *vec;
-    const float *forced;
-};
-
-__device__ __forceinline__ uint4 make_rl(uint32_t s, uint32_t s2, int r_half, uint32_t a, uint32_t t, uint32_t p) {
-    return make_uint4(s, s2, __float_as_uint(0.5f * (float)r_half), a | (t << 8) | (p << 16));
-}
-
 template <bool kDebug>
 __global__ void __launch_bounds__(kRollThreads, 3)
 rollout_kernel(const RolloutArgs A) {
@@ -237,20 +198,9 @@ rollout_kernel(const RolloutArgs A) {
         for (int e = threadIdx.x; e < kTabImageFloats / 4; e += blockDim.x) dst[e] = src[e];
         __syncthreads();
     }
-
-    // per-thread counters; the action histogram packs 3 x 21-bit fields per player (flushed before overflow)
-    unsigned long long st_act0 = 0ull, st_act1 = 0ull;
-    int st_rew0 = 0, st_rew1 = 0;
-    int st_hands = 0, st_trans = 0, st_drop = 0;
-    auto flush_hist = [&]() {
-        atomicAdd(&s_stats[0], st_act0 & 0x1FFFFFull); atomicAdd(&s_stats[1], (st_act0 >> 21) & 0x1FFFFFull);
-        atomicAdd(&s_stats[2], st_act0 >> 42);
-        atomicAdd(&s_stats[3], st_act1 & 0x1FFFFFull); atomicAdd(&s_stats[4], (st_act1 >> 21) & 0x1FFFFFull);
-        atomicAdd(&s_stats[5], st_act1 >> 42);
-        st_act0 = st_act1 = 0ull;
-    };
+    Counters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
-    // all lanes of a warp stay in the loop together (ballots below): iterate on the warp's base index
+    // all lanes of a warp stay in the loop together (warp collectives in decide_finish)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < A.n; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
@@ -258,110 +208,24 @@ rollout_kernel(const RolloutArgs A) {
         const uint64_t game = A.game0 + (uint64_t)i;
         NfspW g{live ? A.state[i] : 0ull};
         for (int t = 0; t < A.n_steps; ++t) {
-            const uint64_t step = A.step0 + (uint64_t)t;
-            uint4 recA, recB, recC, recS;
-            bool vA = false, vB = false, vC = false, vS = false;
-            int p = 0;
+            Decision d;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
             if (live) {
-                bool started = false;
-                if (g.need_reset()) {
-                    const Philox4 y = game_block(A.seed, game, step, STREAM_RESET);
-                    g.reset(g.dealer() ^ 1u, deal_ranks(__umulhi(y.x, 120u)), y.y < A.eta_u32, y.z < A.eta_u32);
-                    started = true;
-                    ++st_hands;
-                }
-                p = g.to_act();
-                const uint32_t obs = g.obs(p);
-                if (g.acted_nz(p)) {  // agent.py:132-136: remember the previous transition
-                    vA = true;
-                    recA = make_rl(g.snapshot(p), obs, 0, g.last_a(p), 0u, (uint32_t)p);
-                }
-                const uint32_t pol = g.policy(p);
-                const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
-                float v0, v1, v2;
-                if (pol && x.x < A.eps_u32) {  // agent.py:125-128: np.random.rand(1,1,3)
-                    v0 = (float)(x.y >> 8) * (1.0f / 16777216.0f);
-                    v1 = (float)(x.z >> 8) * (1.0f / 16777216.0f);
-                    v2 = (float)(x.w >> 8) * (1.0f / 16777216.0f);
+                decide_begin(g, A, game, A.step0 + (uint64_t)t, d, c);
+                if (d.random) {
+                    v0 = d.v0; v1 = d.v1; v2 = d.v2;
                 } else {
                     float v[3];
-                    mlp_forward_tables(sw, g.hist(), g.card(p), g.round() ? 1u + g.pub() : 0u, g.dealer(),
-                                       p * 2 + (int)pol, v);
+                    mlp_forward_tables(sw, g.hist(), g.card(d.p), g.round() ? 1u + g.pub() : 0u, g.dealer(),
+                                       d.p * 2 + (int)d.pol, v);
                     v0 = v[0]; v1 = v[1]; v2 = v[2];
                 }
-                const int64_t at = (int64_t)t * A.n + i;
-                if (kDebug) {
-                    if (A.vec) { A.vec[3 * at] = v0; A.vec[3 * at + 1] = v1; A.vec[3 * at + 2] = v2; }
-                    if (A.forced) { v0 = A.forced[3 * at]; v1 = A.forced[3 * at + 1]; v2 = A.forced[3 * at + 2]; }
-                }
-                if (pol) {  // agent.py:151: the raw score vector goes to the SL memory
-                    vS = true;
-                    recS = make_uint4(obs, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2));
-                }
-                int a = 0;  // np.argmax: first maximum
-                float best = v0;
-                if (v1 > best) { a = 1; best = v1; }
-                if (v2 > best) a = 2;
-                const bool nz = (v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f);
-                const int eff = g.step(a, nz, p);
-                const unsigned long long inc = 1ull << (21 * a);
-                st_act0 += p == 0 ? inc : 0ull;
-                st_act1 += p == 1 ? inc : 0ull;
-                if ((++st_trans & 0xFFFFF) == 0) flush_hist();
-                if (g.terminated()) {  // main.py:55-67: both players observe the terminal state once
-                    const int o = p ^ 1;
-                    st_rew0 += g.reward_half(0);
-                    st_rew1 += g.reward_half(1);
-                    if (g.acted_nz(p)) {
-                        vB = true;
-                        recB = make_rl(g.snapshot(p), g.obs(p), g.reward_half(p), g.last_a(p), 1u, (uint32_t)p);
-                    }
-                    if (g.acted_nz(o)) {
-                        vC = true;
-                        recC = make_rl(g.snapshot(o), g.obs(o), g.reward_half(o), g.last_a(o), 1u, (uint32_t)o);
-                    }
-                    g.w |= 1ull << 43;
-                }
-                if (kDebug && A.trace) {
-                    A.trace[at] = g.obs(p) | ((uint32_t)g.terminated() << 30) | ((uint32_t)p << 31);
-                    A.trace[plane + at] = __float_as_uint(0.5f * (float)g.reward_half(p));
-                    A.trace[2 * plane + at] = g.trace_misc(a, eff, started);
-                }
             }
-            // ---- append records (warp-uniform control flow) ----
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const bool mine = live && (p == q);
-                const int cnt = mine ? ((int)vA + (int)vB) : (int)(live && vC);
-                uint32_t off;
-                const uint32_t b = warp_claim(A.counts + q, cnt, off);
-                uint4 *dst = A.rl[q];
-                if (mine) {
-                    if (vA) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recA; else ++st_drop; ++off; }
-                    if (vB) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recB; else ++st_drop; }
-                } else if (live && vC) {
-                    if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recC; else ++st_drop;
-                }
-                const int cs = (mine && vS) ? 1 : 0;
-                const uint32_t bs = warp_claim(A.counts + 2 + q, cs, off);
-                if (cs) { if ((int64_t)(bs + off) < A.cap_sl) A.sl[q][bs + off] = recS; else ++st_drop; }
-            }
+            decide_finish<kDebug>(g, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c, s_stats);
         }
         if (live) A.state[i] = g.w;
     }
-    if (A.stats) {
-        // block-level reduction of the per-thread counters, then 13 global atomics per CTA
-        flush_hist();
-        atomicAdd(&s_stats[8], (unsigned long long)(long long)st_rew0);
-        atomicAdd(&s_stats[9], (unsigned long long)(long long)st_rew1);
-        atomicAdd(&s_stats[10], (unsigned long long)st_hands);
-        atomicAdd(&s_stats[11], (unsigned long long)st_trans);
-        atomicAdd(&s_stats[12], (unsigned long long)st_drop);
-        __syncthreads();
-        if (threadIdx.x == 6) s_stats[6] = s_stats[0] + s_stats[1] + s_stats[2];  // played = sum of the histogram
-        if (threadIdx.x == 7) s_stats[7] = s_stats[3] + s_stats[4] + s_stats[5];
-        if (threadIdx.x < 13 && s_stats[threadIdx.x]) atomicAdd(A.stats + threadIdx.x, s_stats[threadIdx.x]);
-    }
+    if (A.stats) c.commit(s_stats, A.stats);
 }
 
 }  // namespace nfsp
@@ -383,6 +247,8 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     pack_tables_kernel<<<(kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights,
                                                                                          h->d_wpack + kPackFloats);
     NFSP_LAUNCH_CHECK();
+    const int rc = nfsp_pack_tc_image(h, d_weights, (cudaStream_t)stream);
+    if (rc != NFSP_OK) return rc;
     h->has_weights = true;
     return NFSP_OK;
 }
@@ -417,8 +283,16 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
     A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.counts = io->d_counts;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
-    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 3);
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
+    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 2, "variant must be 0 (default), 1 (CUDA cores) or 2 (tcgen05)");
+    const int variant = io->variant == 0 ? NFSP_ROLLOUT_DEFAULT_VARIANT : io->variant;
+    if (variant == 2) {
+        const int rc = nfsp_rollout_tc_launch(h, A, debug, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        h->step += (uint64_t)n_steps;
+        return NFSP_OK;
+    }
+    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 3);
     if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     NFSP_LAUNCH_CHECK();

@@ -20,6 +20,9 @@ struct nfsp_env_s {
     bool has_weights;
 };
 
+// builds the tensor-core operand image of the acting nets (act_tc_kernels.cu)
+int nfsp_pack_tc_image(nfsp_env_t h, const float *d_weights, cudaStream_t st);
+
 namespace nfsp {
 
 int set_error(int code, const char *fmt, ...);

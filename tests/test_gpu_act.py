@@ -66,11 +66,12 @@ def test_forward_q_values_and_policy_probabilities(nb, golden_dir):
         sp = nb.SelfPlay(64, weights=torch.from_numpy(w), rl_capacity=1024, sl_capacity=1024)
         nets = oracle_nets(nb, w)
         x = ((obs[:, None] >> np.arange(30)) & 1).astype(np.float32)
-        for k in range(4):
-            got = sp.forward(torch.from_numpy(obs.astype(np.int32)), torch.full((len(obs),), k, dtype=torch.int8))
+        for k, tc in [(k, tc) for k in range(4) for tc in (False, True)]:
+            got = sp.forward(torch.from_numpy(obs.astype(np.int32)), torch.full((len(obs),), k, dtype=torch.int8),
+                             tensor_cores=tc)
             got = got.cpu().numpy()
             ref = nets.forward(k, x, "br" if k & 1 else "avg")
-            assert np.abs(got - ref).max() <= TOL, (seed, k, np.abs(got - ref).max())
+            assert np.abs(got - ref).max() <= TOL, (seed, k, tc, np.abs(got - ref).max())
             # float64 bound
             wk = {a: b.astype(np.float64) for a, b in nb.split_net(w[k]).items()}
             h = np.maximum(x @ wk["W1"] + wk["b1"], 0)
@@ -84,13 +85,34 @@ def test_forward_q_values_and_policy_probabilities(nb, golden_dir):
             assert np.abs(got - ref64).max() <= TOL
 
 
+def test_forward_tensor_core_mixed_nets_ragged(nb):
+    """tcgen05 forward with every tile holding a random mix of the four nets, and a ragged last tile."""
+    rng = np.random.RandomState(4)
+    w = random_nets(2, 2.0)
+    sp = nb.SelfPlay(64, weights=torch.from_numpy(w), rl_capacity=1024, sl_capacity=1024)
+    nets = oracle_nets(nb, w)
+    for n in (1, 127, 128, 129, 5000):
+        obs = rng.randint(0, 1 << 30, n).astype(np.int32)
+        k = rng.randint(0, 4, n).astype(np.int8)
+        got = sp.forward(torch.from_numpy(obs), torch.from_numpy(k), tensor_cores=True).cpu().numpy()
+        base = sp.forward(torch.from_numpy(obs), torch.from_numpy(k)).cpu().numpy()
+        x = ((obs.astype(np.uint32)[:, None] >> np.arange(30)) & 1).astype(np.float32)
+        ref = np.zeros((n, 3), np.float32)
+        for kk in range(4):
+            m = k == kk
+            if m.any():
+                ref[m] = nets.forward(kk, x[m], "br" if kk & 1 else "avg")
+        assert np.abs(got - ref).max() <= TOL and np.abs(base - ref).max() <= TOL, n
+
+
+@pytest.mark.parametrize("variant", ["cuda", "tcgen05"])
 @pytest.mark.parametrize("n,steps,eta,eps", [(1, 30, 0.5, 0.5), (1000, 12, 0.1, 0.06), (50_000, 8, 0.3, 0.2)])
-def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps):
+def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps, variant):
     """The fused act+step+remember kernel vs the oracle's restatement of Agent.play/main.train."""
     seed = 2024
     w = random_nets(5)
     sp = nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=eps, rl_capacity=1 << 12,
-                     sl_capacity=1 << 12, max_steps_per_call=steps)
+                     sl_capacity=1 << 12, max_steps_per_call=steps, variant=variant)
     out = sp.rollout(steps, insert=False, debug=True)
     rl, sl = sp.staged()
     vec = out["vec"].cpu().numpy()
@@ -120,14 +142,16 @@ def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps):
         assert abs(float(pol.mean()) - eta) < 5 * (eta * (1 - eta) / pol.numel()) ** 0.5 + 1e-3
 
 
-def test_fused_rollout_golden_hands(nb, golden_dir):
+@pytest.mark.parametrize("variant", ["cuda", "tcgen05"])
+def test_fused_rollout_golden_hands(nb, golden_dir, variant):
     """All 20 352 reference hands (incl. zero vectors and argmax ties) through the fused kernel with the
     reference's scripted score vectors; records must equal the oracle's, which is pinned to the
     reference's own Agent.play / main.train on exactly these hands."""
     g = load(golden_dir, "nfsp_exhaustive.npz")
     T, D = g["kind"].shape
     w = random_nets(9)
-    sp = nb.SelfPlay(T, weights=torch.from_numpy(w), seed=3, rl_capacity=1024, sl_capacity=1024, max_steps_per_call=D)
+    sp = nb.SelfPlay(T, weights=torch.from_numpy(w), seed=3, rl_capacity=1024, sl_capacity=1024, max_steps_per_call=D,
+                     variant=variant)
     sp.env.set_hands(g["dealer"], g["cards"], g["policy"])
     forced = np.ascontiguousarray(g["vec"].transpose(1, 0, 2))  # [D, T, 3]; zeros after a hand's last decision
     sp.env.step_counter = 1
@@ -236,6 +260,22 @@ def test_sample_indices_and_gather(nb):
     assert np.array_equal(idx.cpu().numpy(), pos)
     stored = res.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)[pos]
     assert np.array_equal(a.cpu().numpy(), stored["a"])
+
+
+def test_rollout_variants_agree_without_debug(nb):
+    """Production (non-debug) kernels of both variants leave identical game words, counters and record sets
+    whenever no decision is a last-bit near-tie (seeded so that none is)."""
+    n, steps = 20_000, 8
+    res = []
+    for variant in ("cuda", "tcgen05"):
+        sp = nb.SelfPlay(n, seed=77, eta=0.2, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12,
+                         max_steps_per_call=steps, variant=variant)
+        sp.rollout(steps, insert=False)
+        rl, sl = sp.staged()
+        res.append((sp.env.state_words().cpu().numpy(), sp.read_stats(), [canon(x) for x in rl]))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
 
 
 def test_memories_after_rollout_match_sequential_oracle(nb):
