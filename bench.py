@@ -149,6 +149,45 @@ def workload_config():
             "baseline_config": "BASELINE.json configs[4] per GPU (configs[2] at 1M games)"}
 
 
+def buffer_kernels(nfsp_b200, dev, ev, n_rec=1 << 23):
+    """K3/K4/K5 beside the headline (SURVEY 8d cfg 4): insert batches of 2^23 staged records into a 2^24-slot
+    ring / reservoir (HBM streaming / scatter), and the 256-row sample+gather (latency)."""
+    import torch
+
+    hbm, _ = peaks()
+    recs = torch.randint(0, 1 << 30, (n_rec, 4), dtype=torch.int32, device=dev)
+    out = {}
+    ring = nfsp_b200.DeviceRing(1 << 24, 1, dev)
+    res = nfsp_b200.DeviceReservoir(1 << 24, 2, dev)
+    for name, mem, bytes_per in (("ring_insert", ring, 32.0), ("reservoir_insert", res, 40.0)):
+        ms = []
+        for k in range(8):
+            cnt = torch.tensor([n_rec], dtype=torch.int32, device=dev)
+            a, b = ev(), ev()
+            a.record()
+            mem.insert(recs, cnt)
+            b.record()
+            b.synchronize()
+            if k >= 3:
+                ms.append(a.elapsed_time(b))
+        t = sum(ms) / len(ms)
+        gbs = n_rec * bytes_per / (t * 1e-3) / 1e9
+        out[name] = {"records": n_rec, "ms": t, "records_per_sec": n_rec / (t * 1e-3), "achieved_gbs": gbs,
+                     "algorithmic_bytes_per_record": bytes_per, "frac_of_hbm_peak": gbs / hbm}
+    ms = []
+    for k in range(13):
+        a, b = ev(), ev()
+        a.record()
+        ring.sample(BATCH)
+        res.sample(BATCH)
+        b.record()
+        b.synchronize()
+        if k >= 3:
+            ms.append(a.elapsed_time(b))
+    out["sample_256_rl_plus_sl_us"] = 1e3 * sum(ms) / len(ms)
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -220,6 +259,22 @@ def run_gpu(args):
     e2e_value = trans_all / (e2e_ms * 1e-3)
     st = sharding.allreduce_stats(sp.stats)
 
+    # learner beside it (BASELINE configs[4]): update_strategy() of both agents = 8 SGD steps of the
+    # four nets, each with ONE all-reduce of the flat gradient+stats buffer (NCCL when world > 1)
+    from nfsp_b200.learner import Learner
+
+    learner = Learner(sp, cfg=nfsp_b200.load_config(None))
+    for _ in range(2):
+        learner.update()
+    barrier()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        lstats = learner.update()
+    b.record()
+    b.synchronize()
+    learner_ms = sharding.max_over_ranks(a.elapsed_time(b) / 5, dev)
+
     # env-only K1 (BASELINE configs[1]) beside it, same games count, trace planes written
     env = nfsp_b200.BatchedNfspEnv(n, seed=SEED, game0=game0, device=dev)
     env.reset()
@@ -246,6 +301,7 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    buffers = buffer_kernels(nfsp_b200, dev, ev) if world == 1 else None
     # the other first-layer variant, kernel only, for the record
     other = "tcgen05" if args.variant in ("default", "cuda") else "cuda"
     other_ms = 0.0
@@ -294,6 +350,9 @@ def run_gpu(args):
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION},
                       "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
                                                                  "kernel_ms_per_launch": other_ms / args.steps},
+                      "buffers": buffers,
+                      "learner": {"update_ms": learner_ms, "sgd_steps_per_update": 8, "allreduce_floats": 4 * 2179 + 8,
+                                  "exploitability_proxy": lstats.get("exploitability"), "trained_mask": lstats.get("trained")},
                       "hands": int(st[10]), "transitions_counted": int(st[11]), "records_dropped": int(st[12])}}
     print(json.dumps(line))
     if world > 1:

@@ -180,6 +180,30 @@ int nfsp_gather_rl(const void *d_ring, const int64_t *d_idx, int batch, float *d
 /* ReservoirBuffer.sample_batch (ReservoirBuffer.py:39-43): s [b][30], a [b][3] */
 int nfsp_gather_sl(const void *d_res, const int64_t *d_idx, int batch, float *d_s, float *d_a, void *stream);
 
+/* ------------------------------------------------------------------ learner */
+#define NFSP_LEARNER_STATS 8
+typedef struct {
+    const float *d_weights;        /* [4][NFSP_NET_PARAMS] acting nets, index player*2 + policy               */
+    const float *d_target_weights; /* [2][NFSP_NET_PARAMS] target best-response nets (agent.py:70-72)         */
+    const void *d_rl[2];           /* the players' rings and the sampled slots (nfsp_sample_indices)          */
+    const int64_t *d_rl_idx[2];
+    const void *d_sl[2];           /* the players' reservoirs and the sampled slots                           */
+    const int64_t *d_sl_idx[2];
+    int32_t row0, rows;            /* minibatch = sampled rows [row0, row0+rows) (Keras fit batches of 32)    */
+    float gamma;                   /* config.ini Agent.Gamma                                                  */
+    int32_t net_mask;              /* bit k: net k trains (its memory holds > MiniBatchSize, agent.py:215,259) */
+    int32_t terminal_bootstraps;   /* 1 = reference quirk agent.py:227 (terminal transitions bootstrap too)   */
+    float *d_grad;                 /* out [4][NFSP_NET_PARAMS] mean gradients: the flat all-reduce buffer ... */
+    float *d_stats;                /* out [NFSP_LEARNER_STATS], laid out right behind it by the host:
+                                      expl_sum_p0, expl_sum_p1, rows_p0, rows_p1, loss sums of the 4 nets      */
+} nfsp_learner_io;
+/* Agent.update_best_response_network / update_avg_response_network (agent.py:209-264), gradient part:
+ * forward + backward of all four nets on one minibatch, read straight from the packed memories. */
+int nfsp_learner_grads(const nfsp_learner_io *io, void *stream);
+/* keras SGD step (agent.py:45-46,243,261): w[k] -= lr[k] * scale * grad[k]; scale = 1/world after a SUM
+ * all-reduce.  lr is a HOST array of 4 floats. */
+int nfsp_sgd_apply(float *d_weights, const float *d_grad, const float lr[4], float scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SYMBOLS = [
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_sample_indices", "nfsp_gather_rl", "nfsp_gather_sl",
+    "nfsp_learner_grads", "nfsp_sgd_apply",
 ]
 
 
@@ -34,6 +35,13 @@ class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
                 ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
                 ("d_forced_vec", C.c_void_p), ("variant", C.c_int32)]
+
+
+class LearnerIO(C.Structure):
+    _fields_ = [("d_weights", C.c_void_p), ("d_target_weights", C.c_void_p), ("d_rl", C.c_void_p * 2),
+                ("d_rl_idx", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("d_sl_idx", C.c_void_p * 2),
+                ("row0", C.c_int32), ("rows", C.c_int32), ("gamma", C.c_float), ("net_mask", C.c_int32),
+                ("terminal_bootstraps", C.c_int32), ("d_grad", C.c_void_p), ("d_stats", C.c_void_p)]
 
 
 class NfspError(RuntimeError):
@@ -90,6 +98,8 @@ def lib():
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.nfsp_gather_rl.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.nfsp_gather_sl.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.nfsp_learner_grads.argtypes = [C.POINTER(LearnerIO), vp]
+    L.nfsp_sgd_apply.argtypes = [vp, vp, C.POINTER(C.c_float * 4), C.c_float, vp]
     _lib = L
     return L
 

@@ -1,12 +1,174 @@
-"""Learner half of agent.Agent (agent.py:209-273) -- SURVEY.md section 8 f-1, marked NEXT: it is
-outside the rollout hot path of this round.  The API is kept so that Agent.play's
-`game_step % 128 == 0 -> update_strategy()` hook resolves; calling it with enough data raises
-until the fused forward+backward+SGD kernels land."""
+"""Learner half of agent.Agent (agent.py:209-273), SURVEY.md section 8 f-1.
+
+`Learner.update()` is `update_strategy()` (agent.py:192-194) of BOTH agents at once: it samples a
+minibatch from each of the four memories, then runs Keras' `fit(..., epochs=2)` (default batch 32,
+so 8 SGD steps) for the four nets.  Every SGD step is: one `nfsp_learner_grads` launch (all four
+nets, gradients into one flat fp32 buffer with the exploitability statistics behind them), ONE
+all-reduce of that buffer over the GPUs (NCCL; C1 + C2 of SURVEY 2a), one `nfsp_sgd_apply` launch.
+Weights therefore stay bit-identical on every rank.
+
+What follows the reference literally (host arithmetic): the schedules of agent.py:245-253
+(`iteration` advanced twice per update, temperature, BR learning-rate decay, `epsilon ** 1/iteration`
+== epsilon/iteration by operator precedence) and the target-net copy every TargetModelUpdateRate
+updates (agent.py:266-273).  What does NOT (documented in DESIGN.md): the reference overwrites only row
+0 of the target batch (agent.py:241) and never treats a transition as terminal (agent.py:227, kept
+behind `terminal_bootstraps=True`); here every row gets its own TD target.  Keras shuffles the rows
+each epoch with an unseeded RNG; the minibatches here are the sampled rows in order.  The NN
+arithmetic itself is unpinned (no Keras/TensorFlow to compare with).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib
+from .batched import _ptr, _stream
+
+GRAD = 4 * _lib.NET_PARAMS
+N_STATS = 8
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class Learner:
+    def __init__(self, selfplay, cfg=None, minibatch=128, fit_batch=32, epochs=2, lr_br=0.05, lr_ar=0.1, gamma=0.95,
+                 target_update_rate=150, terminal_bootstraps=False):
+        if cfg is not None:
+            minibatch = cfg.getint("Agent", "MiniBatchSize")
+            lr_br, lr_ar = cfg.getfloat("Agent", "LearningRateBR"), cfg.getfloat("Agent", "LearningRateAR")
+            gamma = cfg.getfloat("Agent", "Gamma")
+            target_update_rate = cfg.getint("Agent", "TargetModelUpdateRate")
+        self.sp = selfplay
+        self.device = selfplay.device
+        self.minibatch, self.fit_batch, self.epochs = int(minibatch), int(fit_batch), int(epochs)
+        self.lr_br0, self.lr_ar, self.gamma = float(lr_br), float(lr_ar), float(gamma)
+        self.lr_br = [self.lr_br0, self.lr_br0]
+        self.target_update_rate = int(target_update_rate)
+        self.terminal_bootstraps = bool(terminal_bootstraps)
+        self.target = selfplay.weights[[1, 3]].clone().contiguous()   # agent.py:70-72
+        self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
+        self.iteration = [0, 0]
+        self.target_update_count = [0, 0]
+        self.temp = [1.0, 1.0]
+        self.exploitability = [0.0, 0.0]
+        self.updates = 0
+
+    # ---- one SGD step for all four nets -------------------------------------------------------------
+    def _step(self, idx_rl, idx_sl, row0, rows, mask):
+        sp = self.sp
+        io = _lib.LearnerIO()
+        io.d_weights, io.d_target_weights = sp.weights.data_ptr(), self.target.data_ptr()
+        for p in range(2):
+            io.d_rl[p], io.d_rl_idx[p] = sp.rl[p].data.data_ptr(), idx_rl[p].data_ptr()
+            io.d_sl[p], io.d_sl_idx[p] = sp.sl[p].data.data_ptr(), idx_sl[p].data_ptr()
+        io.row0, io.rows, io.gamma, io.net_mask = row0, rows, self.gamma, mask
+        io.terminal_bootstraps = int(self.terminal_bootstraps)
+        io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
+        check(lib().nfsp_learner_grads(C.byref(io), _stream(self.device)))
+        world = _world()
+        if world > 1:  # C1 (gradients) + C2 (exploitability stats) in one collective
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
+        check(lib().nfsp_sgd_apply(_ptr(sp.weights), _ptr(self.flat), C.byref(lr), 1.0 / world, _stream(self.device)))
+
+    def update(self):
+        """update_strategy() of both agents.  Returns a dict of statistics (host floats)."""
+        sp = self.sp
+        mask = 0
+        for p in range(2):  # agent.py:215,259: train only once the memory holds more than a minibatch
+            if sp.sl[p].size() > self.minibatch:
+                mask |= 1 << (2 * p)
+            if sp.rl[p].size() > self.minibatch:
+                mask |= 1 << (2 * p + 1)
+        if _world() > 1:  # every rank must take the same decision or the replicas diverge
+            m = torch.tensor([(mask >> k) & 1 for k in range(4)], dtype=torch.int32, device=self.device)
+            dist.all_reduce(m, op=dist.ReduceOp.MIN)
+            mask = sum(int(v) << k for k, v in enumerate(m.tolist()))
+        if mask == 0:
+            return {"trained": 0}
+        for p in range(2):
+            if (mask >> (2 * p + 1)) & 1:
+                self.iteration[p] += 1          # agent.py:216
+        idx_rl = [sp.rl[p].sample_slots(self.minibatch)[0] for p in range(2)]
+        idx_sl = [sp.sl[p].sample_slots(self.minibatch)[0] for p in range(2)]
+        stats = None
+        for _ in range(self.epochs):             # Keras fit(epochs=2), batch_size 32 (agent.py:243,261)
+            for row0 in range(0, self.minibatch, self.fit_batch):
+                self._step(idx_rl, idx_sl, row0, min(self.fit_batch, self.minibatch - row0), mask)
+                if stats is None:                # exploitability proxy of the sampled batch, first pass
+                    stats = self.flat[GRAD:].clone()
+        s = stats.cpu().tolist()
+        for p in range(2):
+            if (mask >> (2 * p + 1)) & 1:
+                self.exploitability[p] = s[p] / max(s[2 + p], 1.0)   # agent.py:234-238 (mean over ranks too)
+                self.iteration[p] += 1                               # agent.py:245
+                it = self.iteration[p]
+                self.temp[p] = (1 + 0.02 * math.sqrt(it)) ** (-1)    # agent.py:247
+                if self.target_update_count[p] % self.target_update_rate == 0:   # agent.py:266-273
+                    self.target[p].copy_(sp.weights[2 * p + 1])
+                self.target_update_count[p] += 1
+                self.lr_br[p] = self.lr_br0 / (1 + 0.003 * math.sqrt(it))        # agent.py:251
+        if any((mask >> (2 * p + 1)) & 1 for p in range(2)):
+            it = max(self.iteration)
+            sp.epsilon = sp.epsilon ** 1 / it                                    # agent.py:253 (sic)
+        sp.set_weights(sp.weights)  # rebuild the kernels' weight images
+        self.updates += 1
+        return {"trained": mask, "exploitability": sum(self.exploitability), "loss": s[4:8], "epsilon": sp.epsilon,
+                "lr_br": list(self.lr_br)}
+
+
+# ---- single-game drop-in: agent.Agent.update_*_network ----------------------------------------------------
+def _agent_fit(agent, net):
+    """Keras fit(epochs=2, batch 32) of one of the agent's nets on a fresh sample of its own memory."""
+    dev = agent.device
+    zeros = torch.zeros(_lib.NET_PARAMS, dtype=torch.float32, device=dev)
+    w = torch.stack([agent.weights[agent.AVG], agent.weights[agent.BR], zeros, zeros]).contiguous()
+    target = torch.stack([agent.weights[agent.TARGET], zeros]).contiguous()
+    flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=dev)
+    mem = agent._rl_memory.memory if net == 1 else agent._sl_memory.memory
+    idx = mem.sample_slots(agent.minibatch_size)[0]
+    io = _lib.LearnerIO()
+    io.d_weights, io.d_target_weights = w.data_ptr(), target.data_ptr()
+    io.d_rl[0], io.d_rl_idx[0] = agent._rl_memory.memory.data.data_ptr(), idx.data_ptr()
+    io.d_sl[0], io.d_sl_idx[0] = agent._sl_memory.memory.data.data_ptr(), idx.data_ptr()
+    io.gamma, io.net_mask, io.terminal_bootstraps = agent.gamma, 1 << net, 0
+    io.d_grad, io.d_stats = flat.data_ptr(), flat[GRAD:].data_ptr()
+    lr = (C.c_float * 4)(agent.lr_ar, agent.lr_br_now, 0.0, 0.0)
+    first = None
+    for _ in range(2):
+        for row0 in range(0, agent.minibatch_size, 32):
+            io.row0, io.rows = row0, min(32, agent.minibatch_size - row0)
+            check(lib().nfsp_learner_grads(C.byref(io), _stream(dev)))
+            if first is None:
+                first = flat[GRAD:].clone()
+            check(lib().nfsp_sgd_apply(_ptr(w), _ptr(flat), C.byref(lr), 1.0, _stream(dev)))
+    agent.weights[agent.AVG], agent.weights[agent.BR] = w[0].clone(), w[1].clone()
+    agent._upload()
+    return first.cpu().tolist()
 
 
 def update_best_response(agent):
-    raise NotImplementedError("update_best_response_network: learner kernels are SURVEY 8 f-1 (next round)")
+    """agent.py:209-253."""
+    if not hasattr(agent, "lr_br_now"):
+        agent.lr_br_now = agent.lr_br
+    agent.iteration += 1
+    s = _agent_fit(agent, 1)
+    agent.exploitability = s[0] / max(s[2], 1.0)
+    agent.iteration += 1
+    agent.temp = (1 + 0.02 * math.sqrt(agent.iteration)) ** (-1)
+    agent.update_br_target_network()
+    agent.lr_br_now = agent.lr_br / (1 + 0.003 * math.sqrt(agent.iteration))
+    agent.epsilon = agent.epsilon ** 1 / agent.iteration
 
 
 def update_average_policy(agent):
-    raise NotImplementedError("update_avg_response_network: learner kernels are SURVEY 8 f-1 (next round)")
+    """agent.py:255-264."""
+    if not hasattr(agent, "lr_br_now"):
+        agent.lr_br_now = agent.lr_br
+    _agent_fit(agent, 0)

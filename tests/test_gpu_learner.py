@@ -1,0 +1,150 @@
+"""-m gpu: learner kernels against a float64 numpy restatement (oracle/learner_oracle.py).
+Floating point: 1e-5 absolute on gradients (values are O(0.1)); NN parity is unpinned (no Keras)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import learner_oracle as lo  # noqa: E402
+from oracle import orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nfsp_b200
+
+    assert torch.cuda.is_available()
+    return nfsp_b200
+
+
+def _filled_selfplay(nb, n=4096, steps=8, rounds=4, **kw):
+    sp = nb.SelfPlay(n, seed=5, eta=0.3, epsilon=0.2, rl_capacity=1 << 16, sl_capacity=1 << 16,
+                     max_steps_per_call=steps, **kw)
+    w = sp.weights.clone()
+    w[:, 1920:1984] = 0.05   # non-zero biases so that relu gates are exercised on both sides
+    w[:, 2176:] = 0.1
+    sp.set_weights(w)
+    for _ in range(rounds):
+        sp.rollout(steps)
+    return sp
+
+
+def test_gradients_match_float64_oracle(nb):
+    from nfsp_b200 import _lib
+    from nfsp_b200.learner import GRAD, Learner
+
+    sp = _filled_selfplay(nb)
+    L = Learner(sp, minibatch=128, gamma=0.95)
+    L.target = (sp.weights[[1, 3]] * 0.9 + 0.01).contiguous()
+    idx_rl = [sp.rl[p].sample_slots(128)[0] for p in range(2)]
+    idx_sl = [sp.sl[p].sample_slots(128)[0] for p in range(2)]
+    w0 = sp.weights.clone()
+    for row0, rows in ((0, 32), (96, 32), (0, 128)):
+        sp.weights.copy_(w0)
+        L.lr_br, L.lr_ar = [0.0, 0.0], 0.0          # gradients only
+        L._step(idx_rl, idx_sl, row0, rows, 0xF)
+        flat = L.flat.cpu().numpy().astype(np.float64)
+        W = w0.cpu().numpy()
+        T = L.target.cpu().numpy()
+        for p in range(2):
+            rl = sp.rl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)[idx_rl[p].cpu().numpy()][row0:row0 + rows]
+            g, expl, loss = lo.br_grad(W[2 * p + 1], T[p], rl["s"], rl["s2"], rl["a"].astype(int), rl["r"], rl["t"], 0.95)
+            got = flat[(2 * p + 1) * 2179:(2 * p + 2) * 2179]
+            assert np.abs(got - g).max() < 1e-5, (p, np.abs(got - g).max())
+            assert abs(flat[GRAD + p] - expl) < 1e-3 and flat[GRAD + 2 + p] == rows
+            assert abs(flat[GRAD + 4 + 2 * p + 1] - loss) < 1e-3
+            sl = sp.sl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)[idx_sl[p].cpu().numpy()][row0:row0 + rows]
+            g, loss = lo.avg_grad(W[2 * p], sl["s"], sl["a"])
+            got = flat[(2 * p) * 2179:(2 * p + 1) * 2179]
+            assert np.abs(got - g).max() < 1e-5, (p, np.abs(got - g).max())
+            assert abs(flat[GRAD + 4 + 2 * p] - loss) < 1e-2
+    assert float(np.abs(flat[:GRAD]).max()) > 1e-4  # not vacuous
+
+
+def test_sgd_apply_and_net_mask(nb):
+    from nfsp_b200.learner import GRAD, Learner
+
+    sp = _filled_selfplay(nb, n=1024, rounds=2)
+    L = Learner(sp, lr_br=0.05, lr_ar=0.1)
+    idx_rl = [sp.rl[p].sample_slots(128)[0] for p in range(2)]
+    idx_sl = [sp.sl[p].sample_slots(128)[0] for p in range(2)]
+    w0 = sp.weights.clone()
+    L._step(idx_rl, idx_sl, 0, 32, 0b0110)          # only p0's BR net and p1's average net train
+    g = L.flat[:GRAD].reshape(4, 2179)
+    assert float(g[0].abs().max()) == 0 and float(g[3].abs().max()) == 0
+    lr = torch.tensor([0.1, 0.05, 0.1, 0.05], device=sp.device)[:, None]
+    assert torch.allclose(sp.weights, w0 - lr * g, atol=1e-7)
+    assert torch.equal(sp.weights[0], w0[0]) and not torch.equal(sp.weights[1], w0[1])
+
+
+def test_update_runs_schedules(nb):
+    """Learner.update(): the reference's schedules (agent.py:245-253) and the target-net sync."""
+    from nfsp_b200.learner import Learner
+
+    sp = _filled_selfplay(nb)
+    L = Learner(sp, cfg=nb.load_config(None))
+    eps0 = sp.epsilon
+    first = L.update()
+    assert first["trained"] == 0xF and L.iteration == [2, 2] and L.target_update_count == [1, 1]
+    assert abs(sp.epsilon - eps0 / 2) < 1e-12                      # epsilon ** 1 / iteration
+    assert abs(L.lr_br[0] - 0.05 / (1 + 0.003 * 2 ** 0.5)) < 1e-12
+    t0 = L.target.clone()                                           # synced at count 0 (before this update's copy)
+    for _ in range(5):
+        L.update()
+    assert L.target_update_count == [6, 6] and torch.equal(L.target, t0)   # next sync only at count 150
+    assert not torch.equal(L.target[0], sp.weights[1])
+    out = sp.rollout(4, insert=False, debug=True)                   # the rollout runs on the trained weights
+    assert torch.isfinite(out["vec"]).all()
+
+
+def test_sgd_reduces_loss_on_a_fixed_minibatch(nb):
+    from nfsp_b200.learner import GRAD, Learner
+
+    sp = _filled_selfplay(nb)
+    L = Learner(sp, lr_br=0.05, lr_ar=0.1)
+    idx_rl = [sp.rl[p].sample_slots(128)[0] for p in range(2)]
+    idx_sl = [sp.sl[p].sample_slots(128)[0] for p in range(2)]
+
+    def losses():
+        lr = (L.lr_br, L.lr_ar)
+        L.lr_br, L.lr_ar = [0.0, 0.0], 0.0
+        L._step(idx_rl, idx_sl, 0, 128, 0xF)
+        L.lr_br, L.lr_ar = lr
+        return L.flat[GRAD + 4:GRAD + 8].cpu().numpy().copy()
+
+    before = losses()
+    for _ in range(40):
+        L._step(idx_rl, idx_sl, 0, 128, 0xF)
+    after = losses()
+    assert (after < before).all(), (before, after)
+
+
+def test_empty_memories_do_not_train(nb):
+    from nfsp_b200.learner import Learner
+
+    sp = nb.SelfPlay(64, rl_capacity=1024, sl_capacity=1024)
+    w0 = sp.weights.clone()
+    assert Learner(sp).update() == {"trained": 0} and torch.equal(sp.weights, w0)
+
+
+def test_dropin_agent_update_networks(nb):
+    """agent.agent.Agent.update_best_response_network / update_avg_response_network on its own memories."""
+    nb.install_dropin()
+    import agent.agent as agent
+    import leduc.newenv as leduc
+
+    env = leduc.Env()
+    ag = agent.Agent(None, env.observation_space, env.action_space, "Player0", env)
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        s = (rng.rand(100, 30) < 0.2).astype(np.float64)
+        s2 = (rng.rand(100, 30) < 0.2).astype(np.float64)
+        ag._rl_memory.add(s, np.eye(3)[rng.randint(0, 3, 100)], rng.randint(-4, 5, 100) * 0.5, s2, rng.rand(100) < 0.3)
+        ag._sl_memory.add(s, rng.rand(100, 3))
+    w_br, w_avg = ag.weights[ag.BR].clone(), ag.weights[ag.AVG].clone()
+    ag.update_strategy()
+    assert not torch.equal(ag.weights[ag.BR], w_br) and not torch.equal(ag.weights[ag.AVG], w_avg)
+    assert ag.iteration == 2 and ag.target_br_model_update_count == 1 and ag.average_payoff_br() >= 0
