@@ -133,10 +133,12 @@ int nfsp_act_forward_tc(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net
  *   RL  {u32 s, u32 s2, f32 r, u8 a, u8 t, u8 player, u8 flags}   replay_buffer.py:30-41, by value
  *   SL  {u32 s, f32 a[3]}                                          ReservoirBuffer.py:18-28       */
 typedef struct {
-    void *d_rl[2];        /* per-player staging, RL records                                     */
-    void *d_sl[2];        /* per-player staging, SL records                                     */
-    int64_t cap_rl, cap_sl;
-    uint32_t *d_counts;   /* uint32[4]: rl0, rl1, sl0, sl1 appended so far (device)             */
+    void *d_rl[2];        /* per-player staging, RL records: [n_segments][cap_rl]               */
+    void *d_sl[2];        /* per-player staging, SL records: [n_segments][cap_sl]               */
+    int64_t cap_rl, cap_sl; /* slots PER SEGMENT                                                */
+    int32_t n_segments;   /* power of two; the 32 consecutive games starting at g append to segment
+                             (g / 32) % n_segments, each segment has its own ticket counter      */
+    uint32_t *d_counts;   /* uint32[4][n_segments]: rl0, rl1, sl0, sl1 appended so far (device)  */
     uint64_t *d_stats;    /* uint64[NFSP_STATS_FIELDS] or NULL: actions[2][3], played[2],
                              reward_half[2] (two's complement), hands, transitions, dropped     */
     uint32_t *d_trace;    /* as nfsp_env_step, or NULL                                          */
@@ -150,23 +152,25 @@ typedef struct {
 /* The fused hot path: for n_steps, every game does one Agent.play decision (agent.py:130-156)
  * -- observe, remember the previous transition, eta-mixed policy (average net argmax /
  * epsilon-greedy best-response net), env.step -- plus the terminal observations of main.py:55-67,
- * with auto re-deal.  Records are appended to the staging arrays with warp-aggregated atomics;
- * move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
+ * with auto re-deal.  Records are appended to the segmented staging arrays with warp-aggregated
+ * atomics; move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
 int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io, void *stream);
 
 /* ------------------------------------------------------------------ memories -------------- */
-/* ReplayBuffer.add (replay_buffer.py:30-41) for a batch: FIFO ring, slot = ticket % cap where
- * ticket counts records ever inserted (*d_total).  d_n = device count of staged records
- * (<= max_n); records beyond the last `cap` of a batch are skipped (they would be evicted).
- * The staging array is consumed: *d_total += n and *d_n = 0 on the stream when the insert is done. */
-int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_n,
-                     int64_t max_n, void *stream);
+/* A staged batch is n_segments segments of seg_cap 16-byte slots with one device count each
+ * (d_counts uint32[n_segments]); n_segments = 1 is a plain dense array.  Batch order = segment order, then
+ * slot order.  The batch is consumed: on the stream, *d_total += records and the counts are zeroed.
+ *
+ * ReplayBuffer.add (replay_buffer.py:30-41) for a batch: FIFO ring, slot = ticket % cap where ticket counts
+ * records ever inserted (*d_total); of a batch larger than the ring only the last `cap` survive. */
+int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
+                     int n_segments, int64_t seg_cap, void *stream);
 /* ReservoirBuffer.add (ReservoirBuffer.py:18-28) for a batch.  mode 0 = Algorithm R (Vitter):
  * ticket t >= cap replaces slot j ~ U[0,t] iff j < cap; mode 1 = the reference's law
  * (j = randrange(1, cap+1), replace iff j < cap).  Same-slot collisions inside a batch are
  * resolved as in the sequential algorithm (largest ticket wins) via d_stamp uint64[cap]. */
 int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp, const void *d_recs,
-                          uint32_t *d_n, int64_t max_n, uint64_t seed, int mode, void *stream);
+                          uint32_t *d_counts, int n_segments, int64_t seg_cap, uint64_t seed, int mode, void *stream);
 /* random.sample(buffer, batch) (replay_buffer.py:46-51, ReservoirBuffer.py:33-37): `batch`
  * distinct positions (Floyd's algorithm, Philox keyed by (seed; call_idx)); d_idx int64[batch]
  * receives storage slots, d_n_out the number drawn = min(batch, size).  is_ring: positions are

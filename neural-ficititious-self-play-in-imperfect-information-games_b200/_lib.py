@@ -33,7 +33,7 @@ SYMBOLS = [
 
 class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
-                ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
+                ("n_segments", C.c_int32), ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
                 ("d_forced_vec", C.c_void_p), ("variant", C.c_int32)]
 
 
@@ -93,8 +93,8 @@ def lib():
     L.nfsp_act_forward.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_act_forward_tc.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
-    L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int64, vp]
-    L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int64, C.c_uint64, C.c_int, vp]
+    L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp]
+    L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp]
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.nfsp_gather_rl.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.nfsp_gather_sl.argtypes = [vp, vp, C.c_int, vp, vp, vp]

@@ -271,11 +271,13 @@ class DeviceRing(_Memory):
 
     is_ring = True
 
-    def insert(self, recs: torch.Tensor, count: torch.Tensor, max_n: Optional[int] = None):
-        """recs int32 [m,4] staged records, count int32[1] device count (consumed: zeroed after)."""
-        max_n = recs.shape[0] if max_n is None else max_n
-        check(lib().nfsp_ring_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(recs), _ptr(count),
-                                     int(max_n), _stream(self.device)))
+    def insert(self, recs: torch.Tensor, counts: torch.Tensor, seg_cap: Optional[int] = None):
+        """recs int32 [n_seg * seg_cap, 4] staged records, counts int32[n_seg] device counts (the batch is
+        consumed: counts are zeroed).  A plain dense batch is n_seg = 1."""
+        n_seg = counts.numel()
+        seg_cap = recs.shape[0] // n_seg if seg_cap is None else seg_cap
+        check(lib().nfsp_ring_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(recs), _ptr(counts),
+                                     n_seg, int(seg_cap), _stream(self.device)))
 
     def sample(self, batch: int):
         idx, n = self.sample_slots(batch)
@@ -303,10 +305,11 @@ class DeviceReservoir(_Memory):
         self.mode = 0 if mode == "R" else 1
         self.stamp = torch.zeros(self.capacity, dtype=torch.int64, device=self.device)
 
-    def insert(self, recs, count, max_n=None):
-        max_n = recs.shape[0] if max_n is None else max_n
+    def insert(self, recs, counts, seg_cap=None):
+        n_seg = counts.numel()
+        seg_cap = recs.shape[0] // n_seg if seg_cap is None else seg_cap
         check(lib().nfsp_reservoir_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(self.stamp),
-                                          _ptr(recs), _ptr(count), int(max_n), self.seed, self.mode,
+                                          _ptr(recs), _ptr(counts), n_seg, int(seg_cap), self.seed, self.mode,
                                           _stream(self.device)))
 
     def sample(self, batch: int):
@@ -361,12 +364,18 @@ class SelfPlay:
         self.max_steps = int(max_steps_per_call)
         self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
         self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
-        # worst case per player and step: 2 RL records (previous + terminal) and 1 SL record per game
-        self.cap_rl = 2 * self.n * self.max_steps
-        self.cap_sl = self.n * self.max_steps
-        self.stage_rl = [torch.empty((self.cap_rl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
-        self.stage_sl = [torch.empty((self.cap_sl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
-        self.counts = torch.zeros(4, dtype=torch.int32, device=self.device)
+        # staging: n_seg segments; the 32 games starting at g append to segment (g/32) % n_seg.  Worst case per
+        # player, game and step: 2 RL records (previous + terminal) and 1 SL record.
+        blocks = (self.n + 31) // 32
+        self.n_seg = 1
+        while self.n_seg * 2 <= min(blocks, 1024):
+            self.n_seg *= 2
+        per_seg = ((blocks + self.n_seg - 1) // self.n_seg) * 32   # games that can map to one segment
+        self.cap_rl = 2 * per_seg * self.max_steps
+        self.cap_sl = per_seg * self.max_steps
+        self.stage_rl = [torch.empty((self.n_seg * self.cap_rl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.stage_sl = [torch.empty((self.n_seg * self.cap_sl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.counts = torch.zeros((4, self.n_seg), dtype=torch.int32, device=self.device)
         self.stats = torch.zeros(_lib.STATS_FIELDS, dtype=torch.int64, device=self.device)
         self.set_weights(glorot_nets(seed, self.device) if weights is None else weights)
         self.env.reset()
@@ -395,7 +404,7 @@ class SelfPlay:
         io = _lib.RolloutIO()
         for p in range(2):
             io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
-        io.cap_rl, io.cap_sl = self.cap_rl, self.cap_sl
+        io.cap_rl, io.cap_sl, io.n_segments = self.cap_rl, self.cap_sl, self.n_seg
         io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
         io.variant = self.VARIANTS[variant or self.variant]
         dbg = None
@@ -416,17 +425,23 @@ class SelfPlay:
         return out
 
     def staged(self):
-        """Host copies of the staged records (tests): ([rl0, rl1], [sl0, sl1]) structured arrays."""
+        """Host copies of the staged records in batch order (segment by segment): ([rl0, rl1], [sl0, sl1])."""
         c = self.counts.cpu().numpy()
-        rl = [self.stage_rl[p][: int(c[p])].cpu().numpy().view(np.uint8).reshape(-1).view(RL_DT) for p in range(2)]
-        sl = [self.stage_sl[p][: int(c[2 + p])].cpu().numpy().view(np.uint8).reshape(-1).view(SL_DT) for p in range(2)]
+
+        def take(stage, cnt, cap, dt):
+            a = stage.cpu().numpy().reshape(self.n_seg, cap, 4)
+            parts = [a[s, : int(cnt[s])] for s in range(self.n_seg)]
+            return np.ascontiguousarray(np.concatenate(parts)).view(np.uint8).reshape(-1).view(dt)
+
+        rl = [take(self.stage_rl[p], c[p], self.cap_rl, RL_DT) for p in range(2)]
+        sl = [take(self.stage_sl[p], c[2 + p], self.cap_sl, SL_DT) for p in range(2)]
         return rl, sl
 
     def flush(self):
         """Move the staged records into the memories (stream-ordered, no host sync)."""
         for p in range(2):
-            self.rl[p].insert(self.stage_rl[p], self.counts[p:p + 1], self.cap_rl)
-            self.sl[p].insert(self.stage_sl[p], self.counts[2 + p:3 + p], self.cap_sl)
+            self.rl[p].insert(self.stage_rl[p], self.counts[p], self.cap_rl)
+            self.sl[p].insert(self.stage_sl[p], self.counts[2 + p], self.cap_sl)
 
     def read_stats(self):
         v = self.stats.cpu().numpy()

@@ -205,6 +205,7 @@ rollout_kernel(const RolloutArgs A) {
     for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < A.n; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
         const bool live = i < A.n;
+        const uint32_t seg = (uint32_t)(base >> 5) & (A.n_seg - 1u);
         const uint64_t game = A.game0 + (uint64_t)i;
         NfspW g{live ? A.state[i] : 0ull};
         for (int t = 0; t < A.n_steps; ++t) {
@@ -221,7 +222,7 @@ rollout_kernel(const RolloutArgs A) {
                     v0 = v[0]; v1 = v[1]; v2 = v[2];
                 }
             }
-            decide_finish<kDebug>(g, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c, s_stats);
+            decide_finish<kDebug>(g, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, seg, c, s_stats);
         }
         if (live) A.state[i] = g.w;
     }
@@ -274,6 +275,8 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     NFSP_CHECK_ARG(io->d_rl[0] && io->d_rl[1] && io->d_sl[0] && io->d_sl[1] && io->d_counts, "missing staging arrays");
     NFSP_CHECK_ARG(io->cap_rl > 0 && io->cap_sl > 0 && io->cap_rl < ((int64_t)1 << 32) && io->cap_sl < ((int64_t)1 << 32),
                    "staging capacity out of range");
+    NFSP_CHECK_ARG(io->n_segments >= 1 && io->n_segments <= 65536 && (io->n_segments & (io->n_segments - 1)) == 0,
+                   "n_segments must be a power of two in [1,65536]");
     if (!h->has_weights) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
@@ -281,7 +284,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
     A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack + kPackFloats;
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
-    A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.counts = io->d_counts;
+    A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.n_seg = (uint32_t)io->n_segments; A.counts = io->d_counts;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
     NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 2, "variant must be 0 (default), 1 (CUDA cores) or 2 (tcgen05)");

@@ -264,82 +264,241 @@ act_forward_tc_kernel(const uint8_t *__restrict__ img, const uint32_t *__restric
 }
 
 // ---- fused rollout, tcgen05 first layer ---------------------------------------------------------------
-// One persistent CTA per SM, kGroups independent groups of 128 threads.  A group owns 128 games at a time
-// (thread = game = operand row = TMEM lane), its own A tile, 64 TMEM columns and an mbarrier; the groups
-// share one weight image and synchronise only among themselves (named barriers), so while one group waits
-// for its MMAs the others run their CUDA-core work (env step, layer 2, record emission).
-constexpr int kGroups = 4;
+// Shape chosen from profiles/r01/umma_microbench.txt (B200): a tcgen05.mma costs ~78 cycles whatever N <= 128
+// and 128 cycles at N = 256, plus ~450 cycles issue->commit latency per chain, so the tile that minimises
+// tensor time is the WIDE one: D[128 rows][256 = 4 nets x 64 hidden] = A[128][32] x B[256][32]^T, 2 k-steps
+// x 3 bf16 splits = 6 MMAs per 128 decisions.  A row needs only its own net's 64 columns, so the rows of a
+// tile are SORTED BY NET (counting sort over the group's 128 threads) before they are written as operand rows:
+// warps then read one 64-column block of TMEM (two at a segment boundary).
+//
+// One persistent CTA per SM, kGroups groups of 128 threads.  A group = 128 games; thread t owns game t
+// (state in registers over the launch's steps) and is the epilogue worker of sorted row t.  The 512 TMEM
+// columns are two accumulator slots that the groups of equal parity use in turn: the issuer of a group waits
+// for the hand-off mbarrier of its predecessor in the ring, the last barrier of the epilogue passes it on.
+constexpr int kGroups = 6;
 constexpr int kRtcThreads = 128 * kGroups;
-constexpr int kRtcSmemBytes = kGroups * kTcABytes + kTcImageBytes + 128;
+constexpr int kWideABytes = 128 * 32 * 2;          // 8 KB operand tile per group
+constexpr int kWideBSplitBytes = 256 * 32 * 2;     // 16 KB
+constexpr int kWideBBytes = 3 * kWideBSplitBytes;  // 48 KB
+constexpr int kWideImageBytes = kWideBBytes + kTcW2Floats * 4;
+constexpr uint32_t kWideSBO = 512;                 // 4 k-chunks of 128 B per 8-row group
+constexpr uint32_t kIdescWide = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// dynamic smem: A tiles | weight image | results float4[kGroups][128] | owner u8[kGroups][128] | counts | barriers
+constexpr int kRtcOffImage = kGroups * kWideABytes;
+constexpr int kRtcOffResult = kRtcOffImage + kWideImageBytes;
+constexpr int kRtcOffOwner = kRtcOffResult + kGroups * 128 * 16;
+constexpr int kRtcOffCnt = kRtcOffOwner + kGroups * 128;
+constexpr int kRtcOffBars = kRtcOffCnt + kGroups * 4 * 4;
+constexpr int kRtcSmemBytes = kRtcOffBars + 8 * (1 + 2 * kGroups) + 16;
+
+__global__ void pack_tc_wide_kernel(const float *__restrict__ w, uint8_t *__restrict__ img) {
+    const int total = 3 * 256 * 32;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int split = e / (256 * 32), n = (e / 32) % 256, k = e % 32;
+        const int net = n >> 6, jj = n & 63;
+        float v = 0.f;
+        if (k < 30) v = w[net * NFSP_NET_PARAMS + k * 64 + jj];
+        else if (k == 30) v = w[net * NFSP_NET_PARAMS + 1920 + jj];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(mid);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+        const __nv_bfloat16 pick = split == 0 ? hi : (split == 1 ? mid : lo);
+        const size_t off = (size_t)split * kWideBSplitBytes + (n >> 3) * kWideSBO + (k >> 3) * kLBO + (n & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(img + off) = pick;
+    }
+    float *w2 = reinterpret_cast<float *>(img + kWideBBytes);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kTcW2Floats; e += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (e < 16 * 4 * 3 * 4) {
+            const int x = e & 3, g = e >> 2, c = g % 3, net = (g / 3) & 3, q = g / 12;
+            v = w[net * NFSP_NET_PARAMS + 1984 + (q * 4 + x) * 3 + c];
+        } else {
+            const int f = e - 16 * 4 * 3 * 4, c = f & 3, net = f >> 2;
+            if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
+        }
+        w2[e] = v;
+    }
+}
+
+__device__ __forceinline__ uint64_t umma_desc_wide(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kWideSBO >> 4) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16_wide(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(kIdescWide), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 template <bool kDebug>
 __global__ void __launch_bounds__(kRtcThreads, 1)
 rollout_tc_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + kGroups * kTcABytes;
-    const float *sW2 = reinterpret_cast<const float *>(sB + kTcBBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kTcImageBytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + kGroups);
-    const uint32_t bar_w = smem_u32(bars);
-    const uint32_t group = threadIdx.x >> 7, gtid = threadIdx.x & 127u;
+    const uint32_t group = threadIdx.x >> 7, gtid = threadIdx.x & 127u, wq = gtid >> 5, lane = gtid & 31u;
+    uint8_t *sA = smem + group * kWideABytes;
+    uint8_t *sB = smem + kRtcOffImage;
+    const float *sW2 = reinterpret_cast<const float *>(sB + kWideBBytes);
+    float4 *sResult = reinterpret_cast<float4 *>(smem + kRtcOffResult) + group * 128;
+    uint8_t *sOwner = smem + kRtcOffOwner + group * 128;
+    uint32_t *sCnt = reinterpret_cast<uint32_t *>(smem + kRtcOffCnt) + group * 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRtcOffBars);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * kGroups);
+    const uint32_t bar_w = smem_u32(bars), bar_done = smem_u32(bars + 1 + group), bar_hand = smem_u32(bars + 1 + kGroups + group);
+    const uint32_t bar_next = smem_u32(bars + 1 + kGroups + (group + 2) % kGroups);
 
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) {
-        mbar_init(bar_w, 1);
-        for (int k = 0; k < kGroups; ++k) mbar_init(smem_u32(bars + 1 + k), 1);
+        for (int k = 0; k < 1 + 2 * kGroups; ++k) mbar_init(smem_u32(bars + k), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = threadIdx.x; e < kGroups * kTcABytes / 16; e += blockDim.x)
-        reinterpret_cast<uint4 *>(sA)[e] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar_w, kTcImageBytes);
-        bulk_g2s(smem_u32(sB), A.pack, kTcImageBytes, bar_w);
+        mbar_expect_tx(bar_w, kWideImageBytes);
+        bulk_g2s(smem_u32(sB), A.pack, kWideImageBytes, bar_w);
+        mbar_arrive(smem_u32(bars + 1 + kGroups + 0));  // the first user of each accumulator slot starts with the baton
+        mbar_arrive(smem_u32(bars + 1 + kGroups + 1));
     }
-    if (threadIdx.x < 32) tmem_alloc(smem_u32(tmem_slot), 64 * kGroups);
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    TcTile t;
-    t.a_smem = smem_u32(sA) + group * kTcABytes;
-    t.b_smem = smem_u32(sB);
-    t.bar = smem_u32(bars + 1 + group);
-    t.tmem = *tmem_slot + group * 64;
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc = tmem_base + (group & 1u) * 256u + (wq << 21);  // this group's slot, this warp's lanes
+    const uint32_t a_smem = smem_u32(sA), b_smem = smem_u32(sB);
     mbar_wait(bar_w, 0);
 
-    uint8_t *a_row = sA + group * kTcABytes + (gtid >> 3) * kSBO + (gtid & 7) * 16;
-    int prev_net = -1;
-    uint32_t phase = 0;
+    uint32_t ph_done = 0, ph_hand = 0;
     Counters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const int64_t tiles = (A.n + 127) / 128;
-    for (int64_t tile = (int64_t)blockIdx.x * kGroups + group; tile < tiles; tile += (int64_t)gridDim.x * kGroups) {
+    const int64_t per_round = (int64_t)gridDim.x * kGroups;
+    const int64_t rounds = (tiles + per_round - 1) / per_round;  // every group runs the same number of rounds
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+        const int64_t tile = (rd * gridDim.x + blockIdx.x) * kGroups + group;
         const int64_t i = tile * 128 + gtid;
-        const bool live = i < A.n;
+        const bool live = tile < tiles && i < A.n;
         const uint64_t game = A.game0 + (uint64_t)i;
+        const uint32_t seg = (uint32_t)((tile * 4 + wq) & (int64_t)(A.n_seg - 1u));  // = (first game of the warp / 32) % n_seg
         NfspW g{live ? A.state[i] : 0ull};
         for (int s = 0; s < A.n_steps; ++s) {
             Decision d;
             if (live) decide_begin(g, A, game, A.step0 + (uint64_t)s, d, c);
-            const int net = live ? d.p * 2 + (int)d.pol : 0;
-            write_a_row(a_row, d.obs, net, prev_net);
-            float h[64];
-            tc_layer1(t, phase, h, 1 + group);
-            phase ^= 1u;
-            float v[3];
-            layer2_head(sW2, h, net, v);
-            if (d.random) { v[0] = d.v0; v[1] = d.v1; v[2] = d.v2; }
-            decide_finish<kDebug>(g, A, d, v[0], v[1], v[2], live, (int64_t)s * A.n + i, plane, c, s_stats);
+            const uint32_t net = live ? (uint32_t)(d.p * 2) + d.pol : 0u;
+            // ---- counting sort of the group's rows by net: packed byte counters, one word per warp
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, net == 0), m1 = __ballot_sync(0xFFFFFFFFu, net == 1);
+            const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, net == 2), m3 = ~(m0 | m1 | m2);
+            const uint32_t mine = net == 0 ? m0 : (net == 1 ? m1 : (net == 2 ? m2 : m3));
+            const uint32_t rank = __popc(mine & ((1u << lane) - 1u));
+            if (lane == 0) sCnt[wq] = __popc(m0) | (__popc(m1) << 8) | (__popc(m2) << 16) | (__popc(m3) << 24);
+            group_bar(1 + group);
+            const uint32_t c0 = sCnt[0], c1 = sCnt[1], c2 = sCnt[2], c3 = sCnt[3];
+            const uint32_t tot = c0 + c1 + c2 + c3;  // bytes: rows of net 0..3 (<= 128 each, no carry)
+            const uint32_t before = (wq > 0 ? c0 : 0u) + (wq > 1 ? c1 : 0u) + (wq > 2 ? c2 : 0u);
+            const uint32_t seg1 = tot & 0xFFu, seg2 = seg1 + ((tot >> 8) & 0xFFu), seg3 = seg2 + ((tot >> 16) & 0xFFu);
+            const uint32_t seg_start = net == 0 ? 0u : (net == 1 ? seg1 : (net == 2 ? seg2 : seg3));
+            const uint32_t pos = seg_start + ((before >> (8 * net)) & 0xFFu) + rank;
+            {  // operand row `pos`: observation bits + the constant 1 that carries b1
+                uint8_t *row = sA + (pos >> 3) * kWideSBO + (pos & 7u) * 16;
+                const uint32_t x = (d.obs & 0x3FFFFFFFu) | (1u << 30);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4 *>(row + k * kLBO) = bits_to_bf16x8((x >> (8 * k)) & 0xFFu);
+                sOwner[pos] = (uint8_t)gtid;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            group_bar(1 + group);
+            if (gtid == 0) {
+                mbar_wait(bar_hand, ph_hand);  // the accumulator slot is ours
+                tc_fence_after();
+#pragma unroll
+                for (int split = 0; split < 3; ++split)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_f16_wide(tmem_base + (group & 1u) * 256u, umma_desc_wide(a_smem + ks * 2 * kLBO),
+                                      umma_desc_wide(b_smem + split * kWideBSplitBytes + ks * 2 * kLBO), (split | ks) != 0);
+                umma_commit(bar_done);
+            }
+            ph_hand ^= 1u;
+            if (wq == 0) mbar_wait(bar_done, ph_done);  // one warp polls the mbarrier, the others sleep on the barrier
+            ph_done ^= 1u;
+            group_bar(1 + group);
+            tc_fence_after();
+            // ---- epilogue of sorted row `gtid`: its net's 64 pre-activations -> layer 2 -> head
+            const uint32_t r = gtid;
+            const uint32_t my_net = (r >= seg1) + (r >= seg2) + (r >= seg3);
+            const uint32_t r_lo = wq * 32u, r_hi = r_lo + 31u;
+            const uint32_t n_lo = (r_lo >= seg1) + (r_lo >= seg2) + (r_lo >= seg3);
+            const uint32_t n_hi = (r_hi >= seg1) + (r_hi >= seg2) + (r_hi >= seg3);
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+            for (uint32_t nn = n_lo; nn <= n_hi; ++nn) {  // warp-uniform; two nets only at a segment boundary
+                const float4 *w2 = reinterpret_cast<const float4 *>(sW2) + nn * 3;
+                float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    float h[16];
+                    tmem_ld16(tmem_acc + nn * 64u + ch * 16u, h);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float hx = fmaxf(h[4 * q], 0.f), hy = fmaxf(h[4 * q + 1], 0.f);
+                        const float hz = fmaxf(h[4 * q + 2], 0.f), hw = fmaxf(h[4 * q + 3], 0.f);
+                        const float4 u0 = w2[(ch * 4 + q) * 12], u1 = w2[(ch * 4 + q) * 12 + 1], u2 = w2[(ch * 4 + q) * 12 + 2];
+                        z0 = fmaf(hx, u0.x, z0); z0 = fmaf(hy, u0.y, z0); z0 = fmaf(hz, u0.z, z0); z0 = fmaf(hw, u0.w, z0);
+                        z1 = fmaf(hx, u1.x, z1); z1 = fmaf(hy, u1.y, z1); z1 = fmaf(hz, u1.z, z1); z1 = fmaf(hw, u1.w, z1);
+                        z2 = fmaf(hx, u2.x, z2); z2 = fmaf(hy, u2.y, z2); z2 = fmaf(hz, u2.z, z2); z2 = fmaf(hw, u2.w, z2);
+                    }
+                }
+                const float4 b2 = reinterpret_cast<const float4 *>(sW2 + 16 * 4 * 3 * 4)[nn];
+                z0 += b2.x; z1 += b2.y; z2 += b2.z;
+                float t0, t1, t2;
+                if (nn & 1u) {
+                    t0 = fmaxf(z0, 0.f); t1 = fmaxf(z1, 0.f); t2 = fmaxf(z2, 0.f);
+                } else {
+                    const float m = fmaxf(z0, fmaxf(z1, z2));
+                    const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+                    const float inv = 1.0f / (e0 + e1 + e2);
+                    t0 = e0 * inv; t1 = e1 * inv; t2 = e2 * inv;
+                }
+                if (nn == my_net) { o0 = t0; o1 = t1; o2 = t2; }
+            }
+            sResult[sOwner[r]] = make_float4(o0, o1, o2, 0.f);
+            tc_fence_before();
+            group_bar(1 + group);                 // all TMEM reads of the slot are done; results are visible
+            if (gtid == 0) mbar_arrive(bar_next);  // pass the accumulator slot on
+            float4 v = sResult[gtid];
+            if (d.random) { v.x = d.v0; v.y = d.v1; v.z = d.v2; }
+            decide_finish<kDebug>(g, A, d, v.x, v.y, v.z, live, (int64_t)s * A.n + i, plane, seg, c, s_stats);
         }
         if (live) A.state[i] = g.w;
     }
     tc_fence_before();
     __syncthreads();
     if (A.stats) c.commit(s_stats, A.stats);
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 64 * kGroups);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace nfsp
@@ -365,7 +524,7 @@ extern "C" int nfsp_act_forward_tc(nfsp_env_t h, const uint32_t *d_obs, const in
 // called from nfsp_rollout (act_kernels.cu) when the tensor-core variant is selected
 int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A0, bool debug, cudaStream_t st) {
     RolloutArgs A = A0;
-    A.pack = h->d_wtc;
+    A.pack = h->d_wtc_wide;
     const int64_t ctas = (A.n + kRtcThreads - 1) / kRtcThreads;
     const int grid = (int)(ctas < h->sm_count ? ctas : h->sm_count);
     if (debug) rollout_tc_kernel<true><<<grid, kRtcThreads, kRtcSmemBytes, st>>>(A);
@@ -378,11 +537,14 @@ int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A0, bool debug
 int nfsp_pack_tc_image(nfsp_env_t h, const float *d_weights, cudaStream_t st) {
     if (!h->d_wtc) {
         NFSP_CUDA(cudaMalloc(&h->d_wtc, kTcImageBytes));
+        NFSP_CUDA(cudaMalloc(&h->d_wtc_wide, kWideImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(act_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtcSmemBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtcSmemBytes));
     }
     pack_tc_kernel<<<96, 256, 0, st>>>(d_weights, (uint8_t *)h->d_wtc);
+    NFSP_LAUNCH_CHECK();
+    pack_tc_wide_kernel<<<96, 256, 0, st>>>(d_weights, (uint8_t *)h->d_wtc_wide);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

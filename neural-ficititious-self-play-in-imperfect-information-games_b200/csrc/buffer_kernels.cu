@@ -12,26 +12,66 @@ constexpr int kBufThreads = 256;
 
 __device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 
-// ---- K3 ------------------------------------------------------------------------------------------
-// staged record i gets ticket total+i and lands in slot ticket % cap; of a batch larger than the ring
-// only the last `cap` records survive (the others would be evicted by popleft(), replay_buffer.py:40).
-__global__ void __launch_bounds__(kBufThreads)
-ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__restrict__ total_p,
-                   const uint4 *__restrict__ recs, const uint32_t *__restrict__ n_p, uint64_t max_n) {
-    const uint64_t total = *total_p;
-    uint64_t m = *n_p;
-    if (m > max_n) m = max_n;
-    const uint64_t first = m > cap ? m - cap : 0;
-    for (uint64_t i = first + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
-        ring[(total + i) % cap] = recs[i];
+// ---- staged batches --------------------------------------------------------------------------------
+// A batch is n_seg segments of seg_cap slots with a device count each (n_seg = 1: a plain dense array).
+// Record i of segment s has batch index prefix(s) + i, where prefix(s) = sum of the counts of the segments
+// before s; its ticket is total + that index.  Each CTA row (blockIdx.y = segment) recomputes its prefix
+// with one block reduction over the <= 65536 counts.
+struct Batch {
+    const uint4 *recs;
+    const uint32_t *counts;
+    uint32_t n_seg;
+    uint64_t seg_cap;
+};
+
+__device__ __forceinline__ void batch_prefix(const Batch &B, uint32_t seg, uint64_t &before, uint64_t &all) {
+    __shared__ unsigned long long s_before, s_all;
+    if (threadIdx.x == 0) { s_before = 0ull; s_all = 0ull; }
+    __syncthreads();
+    unsigned long long lb = 0ull, la = 0ull;
+    for (uint32_t k = threadIdx.x; k < B.n_seg; k += blockDim.x) {
+        unsigned long long cnt = B.counts[k];
+        if (cnt > B.seg_cap) cnt = B.seg_cap;
+        la += cnt;
+        if (k < seg) lb += cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lb += __shfl_xor_sync(0xFFFFFFFFu, lb, o);
+        la += __shfl_xor_sync(0xFFFFFFFFu, la, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_before, lb); atomicAdd(&s_all, la); }
+    __syncthreads();
+    before = s_before;
+    all = s_all;
 }
 
-// runs after the insert kernel(s) of a batch: total += n, staged count cleared for the next rollout
-__global__ void commit_kernel(uint64_t *total_p, uint32_t *n_p, uint64_t max_n) {
-    uint64_t m = *n_p;
-    if (m > max_n) m = max_n;
-    *total_p += m;
-    *n_p = 0;
+// ---- K3 ------------------------------------------------------------------------------------------
+// slot = ticket % cap; of a batch larger than the ring only the last `cap` records survive (the others
+// would be evicted by popleft(), replay_buffer.py:40).
+__global__ void __launch_bounds__(kBufThreads)
+ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__restrict__ total_p, const Batch B) {
+    const uint32_t seg = blockIdx.y;
+    uint64_t before, m;
+    batch_prefix(B, seg, before, m);
+    const uint64_t total = *total_p;
+    const uint64_t first = m > cap ? m - cap : 0;
+    uint64_t cnt = B.counts[seg];
+    if (cnt > B.seg_cap) cnt = B.seg_cap;
+    const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t idx = before + i;
+        if (idx >= first) ring[(total + idx) % cap] = src[i];
+    }
+}
+
+// runs after the insert kernel(s) of a batch: total += n, staged counts cleared for the next rollout
+__global__ void __launch_bounds__(kBufThreads) commit_kernel(uint64_t *total_p, uint32_t *counts, const Batch B) {
+    uint64_t before, m;
+    batch_prefix(B, 0, before, m);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < B.n_seg; k += blockDim.x) counts[k] = 0;
+    if (threadIdx.x == 0) *total_p += m;
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------
@@ -49,27 +89,35 @@ __device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket
 // pass 1: every accepted record stamps its slot with ticket+1; atomicMax keeps the latest
 __global__ void __launch_bounds__(kBufThreads)
 reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, const uint64_t *__restrict__ total_p,
-                       const uint32_t *__restrict__ n_p, uint64_t max_n, uint64_t seed, int mode) {
+                       const Batch B, uint64_t seed, int mode) {
+    const uint32_t seg = blockIdx.y;
+    uint64_t before, m;
+    batch_prefix(B, seg, before, m);
     const uint64_t total = *total_p;
-    uint64_t m = *n_p;
-    if (m > max_n) m = max_n;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
-        const int64_t slot = reservoir_slot(seed, total + i, cap, mode);
-        if (slot >= 0) atomicMax(stamp + slot, (unsigned long long)(total + i + 1u));
+    uint64_t cnt = B.counts[seg];
+    if (cnt > B.seg_cap) cnt = B.seg_cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t ticket = total + before + i;
+        const int64_t slot = reservoir_slot(seed, ticket, cap, mode);
+        if (slot >= 0) atomicMax(stamp + slot, (unsigned long long)(ticket + 1u));
     }
 }
 
 // pass 2: the record whose ticket owns the stamp writes the payload (== sequential order of adds)
 __global__ void __launch_bounds__(kBufThreads)
 reservoir_write_kernel(uint4 *__restrict__ res, const unsigned long long *__restrict__ stamp, uint64_t cap,
-                       const uint64_t *__restrict__ total_p, const uint4 *__restrict__ recs,
-                       const uint32_t *__restrict__ n_p, uint64_t max_n, uint64_t seed, int mode) {
+                       const uint64_t *__restrict__ total_p, const Batch B, uint64_t seed, int mode) {
+    const uint32_t seg = blockIdx.y;
+    uint64_t before, m;
+    batch_prefix(B, seg, before, m);
     const uint64_t total = *total_p;
-    uint64_t m = *n_p;
-    if (m > max_n) m = max_n;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
-        const int64_t slot = reservoir_slot(seed, total + i, cap, mode);
-        if (slot >= 0 && stamp[slot] == (unsigned long long)(total + i + 1u)) res[slot] = recs[i];
+    uint64_t cnt = B.counts[seg];
+    if (cnt > B.seg_cap) cnt = B.seg_cap;
+    const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t ticket = total + before + i;
+        const int64_t slot = reservoir_slot(seed, ticket, cap, mode);
+        if (slot >= 0 && stamp[slot] == (unsigned long long)(ticket + 1u)) res[slot] = src[i];
     }
 }
 
@@ -142,46 +190,56 @@ gather_sl_kernel(const uint4 *__restrict__ res, const int64_t *__restrict__ idx,
     }
 }
 
-static int insert_grid(int64_t max_n) {
-    int64_t g = (max_n + kBufThreads - 1) / kBufThreads;
-    if (g > 148 * 8) g = 148 * 8;
+static dim3 insert_grid(int64_t seg_cap, int n_seg) {
+    int64_t g = (seg_cap + kBufThreads - 1) / kBufThreads;
+    const int64_t lim = n_seg >= 148 * 8 ? 1 : (148 * 8 + n_seg - 1) / n_seg;  // about 8 CTAs per SM in total
+    if (g > lim) g = lim;
     if (g < 1) g = 1;
-    return (int)g;
+    return dim3((unsigned)g, (unsigned)n_seg, 1);
 }
 
 }  // namespace nfsp
 
 using namespace nfsp;
 
-extern "C" int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_n,
-                                int64_t max_n, void *stream) {
-    NFSP_CHECK_ARG(d_ring && d_total && d_recs && d_n && cap > 0 && max_n >= 0, "bad arguments");
-    if (max_n == 0) return NFSP_OK;
+static int check_batch(const void *d_recs, const uint32_t *d_counts, int n_segments, int64_t seg_cap) {
+    NFSP_CHECK_ARG(d_recs && d_counts, "null staged batch");
+    NFSP_CHECK_ARG(n_segments >= 1 && n_segments <= 65535 && seg_cap >= 0, "bad segment geometry");
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
+                                int n_segments, int64_t seg_cap, void *stream) {
+    NFSP_CHECK_ARG(d_ring && d_total && cap > 0, "bad arguments");
+    const int rc = check_batch(d_recs, d_counts, n_segments, seg_cap);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    ring_insert_kernel<<<insert_grid(max_n), kBufThreads, 0, st>>>((uint4 *)d_ring, (uint64_t)cap, d_total,
-                                                                   (const uint4 *)d_recs, d_n, (uint64_t)max_n);
+    const Batch B{(const uint4 *)d_recs, d_counts, (uint32_t)n_segments, (uint64_t)seg_cap};
+    ring_insert_kernel<<<insert_grid(seg_cap, n_segments), kBufThreads, 0, st>>>((uint4 *)d_ring, (uint64_t)cap, d_total, B);
     NFSP_LAUNCH_CHECK();
-    commit_kernel<<<1, 1, 0, st>>>(d_total, d_n, (uint64_t)max_n);
+    commit_kernel<<<1, kBufThreads, 0, st>>>(d_total, d_counts, B);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }
 
 extern "C" int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp,
-                                     const void *d_recs, uint32_t *d_n, int64_t max_n, uint64_t seed, int mode,
-                                     void *stream) {
-    NFSP_CHECK_ARG(d_res && d_total && d_stamp && d_recs && d_n && cap > 0 && max_n >= 0, "bad arguments");
+                                     const void *d_recs, uint32_t *d_counts, int n_segments, int64_t seg_cap,
+                                     uint64_t seed, int mode, void *stream) {
+    NFSP_CHECK_ARG(d_res && d_total && d_stamp && cap > 0, "bad arguments");
     NFSP_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
-    if (max_n == 0) return NFSP_OK;
+    const int rc = check_batch(d_recs, d_counts, n_segments, seg_cap);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = insert_grid(max_n);
-    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>((unsigned long long *)d_stamp, (uint64_t)cap, d_total, d_n,
-                                                         (uint64_t)max_n, seed, mode);
+    const Batch B{(const uint4 *)d_recs, d_counts, (uint32_t)n_segments, (uint64_t)seg_cap};
+    const dim3 grid = insert_grid(seg_cap, n_segments);
+    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>((unsigned long long *)d_stamp, (uint64_t)cap, d_total, B, seed, mode);
     NFSP_LAUNCH_CHECK();
-    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>((uint4 *)d_res, (const unsigned long long *)d_stamp,
-                                                         (uint64_t)cap, d_total, (const uint4 *)d_recs, d_n,
-                                                         (uint64_t)max_n, seed, mode);
+    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>((uint4 *)d_res, (const unsigned long long *)d_stamp, (uint64_t)cap,
+                                                         d_total, B, seed, mode);
     NFSP_LAUNCH_CHECK();
-    commit_kernel<<<1, 1, 0, st>>>(d_total, d_n, (uint64_t)max_n);
+    commit_kernel<<<1, kBufThreads, 0, st>>>(d_total, d_counts, B);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

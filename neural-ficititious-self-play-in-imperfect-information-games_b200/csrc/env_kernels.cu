@@ -14,10 +14,8 @@ constexpr int kThreads = 256;
 // ------------------------------------------------------------------------------------------------
 // ENV_NFSP
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nfsp_redeal(NfspW &g, uint32_t dealer, uint64_t seed, uint64_t game, uint64_t step,
-                                            uint32_t eta_u32) {
-    const Philox4 y = game_block(seed, game, step, STREAM_RESET);
-    g.reset(dealer, deal_ranks(__umulhi(y.x, 120u)), y.y < eta_u32, y.z < eta_u32);
+__device__ __forceinline__ void nfsp_redeal(NfspW &g, uint32_t dealer, const Philox4 &x, uint32_t eta_u32) {
+    g.reset(dealer, deal_ranks(__umulhi(x.y, 120u)), x.z < eta_u32, x.w < eta_u32);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -26,7 +24,8 @@ nfsp_reset_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t game = game0 + (uint64_t)i;
         NfspW g;
-        nfsp_redeal(g, dealer ? (uint32_t)(dealer[i] & 1) : (uint32_t)(game & 1u), seed, game, step, eta_u32);
+        nfsp_redeal(g, dealer ? (uint32_t)(dealer[i] & 1) : (uint32_t)(game & 1u), game_block(seed, game, step, STREAM_STEP),
+                    eta_u32);
         state[i] = g.w;
     }
 }
@@ -55,16 +54,20 @@ nfsp_step_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64_
         NfspW g{state[i]};
         for (int t = 0; t < n_steps; ++t) {
             const uint64_t step = step0 + (uint64_t)t;
-            bool started = false;
-            if (auto_reset && g.need_reset()) {
-                nfsp_redeal(g, g.dealer() ^ 1u, seed, game, step, eta_u32);
-                started = true;
-            }
             const int64_t at = (int64_t)t * n + i;
-            const int p = players ? (int)(players[at] & 1) : g.to_act();
             int code = actions ? (int)actions[at] : -1;
+            bool started = false;
+            const bool redeal = auto_reset && g.need_reset();
+            if (redeal || code < 0) {  // one Philox block serves the re-deal and the random action
+                const Philox4 x = game_block(seed, game, step, STREAM_STEP);
+                if (redeal) {
+                    nfsp_redeal(g, g.dealer() ^ 1u, x, eta_u32);
+                    started = true;
+                }
+                if (code < 0) code = (int)__umulhi(x.x, 3u);
+            }
+            const int p = players ? (int)(players[at] & 1) : g.to_act();
             if (code == 4) continue;  // this game sits the step out (per-game call sequences)
-            if (code < 0) code = (int)__umulhi(game_block(seed, game, step, STREAM_STEP).x, 3u);
             const int raw = code == 3 ? 0 : code;
             const int eff = g.step(raw, code != 3, p);
             if (auto_reset && g.terminated()) g.w |= 1ull << 43;
@@ -115,8 +118,8 @@ nfsp_export_kernel(const uint64_t *__restrict__ state, int64_t n, int32_t *__res
 // ------------------------------------------------------------------------------------------------
 constexpr int kPenalty = -1;  // config.ini:12
 
-__device__ __forceinline__ void legacy_redeal(LegacyW &g, uint64_t seed, uint64_t game, uint64_t step) {
-    const uint32_t c = deal_ranks(__umulhi(game_block(seed, game, step, STREAM_RESET).x, 120u));
+__device__ __forceinline__ void legacy_redeal(LegacyW &g, const Philox4 &x) {
+    const uint32_t c = deal_ranks(__umulhi(x.z, 120u));
     g.reset(c & 3u, (c >> 2) & 3u);
 }
 
@@ -126,7 +129,7 @@ legacy_reset_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         LegacyW g;
         if (cards) g.reset((uint32_t)(cards[2 * i] & 3), (uint32_t)(cards[2 * i + 1] & 3));
-        else legacy_redeal(g, seed, game0 + (uint64_t)i, step);
+        else legacy_redeal(g, game_block(seed, game0 + (uint64_t)i, step, STREAM_STEP));
         state[i] = g.w;
     }
 }
@@ -169,14 +172,14 @@ legacy_rollout_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, ui
         for (int t = 0; t < n_iters; ++t) {
             const uint64_t step = step0 + (uint64_t)t;
             bool started = false;
-            if (g.need_reset()) {
-                legacy_redeal(g, seed, game, step);
-                started = true;
-            }
             const int64_t at = ((int64_t)t * n + i) * 2;
             int a0 = actions ? (int)actions[at] : -1, a1 = actions ? (int)actions[at + 1] : -1;
-            if (a0 < 0 || a1 < 0) {
+            if (g.need_reset() || a0 < 0 || a1 < 0) {
                 const Philox4 x = game_block(seed, game, step, STREAM_STEP);
+                if (g.need_reset()) {
+                    legacy_redeal(g, x);
+                    started = true;
+                }
                 if (a0 < 0) a0 = (int)__umulhi(x.x, 3u);
                 if (a1 < 0) a1 = (int)__umulhi(x.y, 3u);
             }

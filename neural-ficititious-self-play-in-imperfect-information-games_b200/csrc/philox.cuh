@@ -28,8 +28,12 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
-// purposes (counter word 3); must match DESIGN.md "Philox streams"
-enum : uint32_t { STREAM_STEP = 0, STREAM_RESET = 1, STREAM_RESERVOIR = 2, STREAM_SAMPLE = 3 };
+// purposes (counter word 3), DESIGN.md "Philox streams":
+//   STREAM_STEP   one block per (game, step): .x = uniform action (env-only) / epsilon test (NFSP),
+//                 .y = deal index, .z/.w = per-hand policy draws of players 0/1 (used iff the hand is re-dealt
+//                 at this step; legacy rules: .x/.y = the two actions, .z = deal index)
+//   STREAM_VECTOR the random score vector of agent.py:128, computed only in the (rare) epsilon branch
+enum : uint32_t { STREAM_STEP = 0, STREAM_VECTOR = 1, STREAM_RESERVOIR = 2, STREAM_SAMPLE = 3 };
 
 __device__ __forceinline__ Philox4 game_block(uint64_t seed, uint64_t game, uint64_t step, uint32_t stream) {
     return philox4x32_10((uint32_t)game, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed,

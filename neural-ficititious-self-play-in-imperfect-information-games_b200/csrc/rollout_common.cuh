@@ -13,21 +13,11 @@ int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug,
 namespace nfsp {
 
 // ---- warp-aggregated record append -------------------------------------------------------------
-// Every lane contributes cnt in {0,1,2} records for one destination array; one atomicAdd per warp
-// claims the tickets, lanes write their 16-byte records at consecutive slots.
-__device__ __forceinline__ uint32_t warp_claim(uint32_t *counter, int cnt, uint32_t &my_off) {
-    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, cnt >= 1), m2 = __ballot_sync(0xFFFFFFFFu, cnt >= 2);
-    const uint32_t total = __popc(m1) + __popc(m2);
-    my_off = __popc(m1 & lt) + __popc(m2 & lt);
-    uint32_t base = 0;
-    if (total) {
-        if (lane == 0) base = atomicAdd(counter, total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    }
-    return base;
-}
-
+// The staging arrays are split into n_seg segments (a power of two), each with its own ticket counter; a
+// warp's 32 consecutive games always append to segment (first game / 32) % n_seg, so which records land
+// in which segment does not depend on the launch geometry, and counters are not shared across the chip.
+// Per step a warp claims its slots in the four arrays (RL and SL of both players) with FOUR atomics issued
+// by four lanes at once: one global round trip.
 struct RolloutArgs {
     uint64_t *state;
     int64_t n;
@@ -37,8 +27,9 @@ struct RolloutArgs {
     const void *pack;  // weight image of the variant
     uint4 *rl[2];
     uint4 *sl[2];
-    int64_t cap_rl, cap_sl;
-    uint32_t *counts;
+    int64_t cap_rl, cap_sl;  // per segment
+    uint32_t n_seg;          // power of two
+    uint32_t *counts;        // [4][n_seg]: rl0, rl1, sl0, sl1
     unsigned long long *stats;
     uint32_t *trace;
     float *vec;
@@ -61,14 +52,23 @@ struct Counters {
         atomicAdd(&s_stats[5], act1 >> 42);
         act0 = act1 = 0ull;
     }
-    // block-level reduction into s_stats, then 13 global atomics per CTA; call from every thread of the CTA
+    // warp shuffle reduction, one shared atomic per warp and counter, then 13 global atomics per CTA;
+    // call from every thread of the CTA
     __device__ __forceinline__ void commit(unsigned long long *s_stats, unsigned long long *g_stats) {
-        flush_hist(s_stats);
-        atomicAdd(&s_stats[8], (unsigned long long)(long long)rew0);
-        atomicAdd(&s_stats[9], (unsigned long long)(long long)rew1);
-        atomicAdd(&s_stats[10], (unsigned long long)hands);
-        atomicAdd(&s_stats[11], (unsigned long long)trans);
-        atomicAdd(&s_stats[12], (unsigned long long)drop);
+        long long v[11] = {(long long)(act0 & 0x1FFFFFull), (long long)((act0 >> 21) & 0x1FFFFFull), (long long)(act0 >> 42),
+                           (long long)(act1 & 0x1FFFFFull), (long long)((act1 >> 21) & 0x1FFFFFull), (long long)(act1 >> 42),
+                           rew0, rew1, hands, trans, drop};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 11; ++k)
+                if (v[k]) atomicAdd(&s_stats[k < 6 ? k : k + 2], (unsigned long long)v[k]);
+        }
+        act0 = act1 = 0ull;
         __syncthreads();
         if (threadIdx.x == 6) s_stats[6] = s_stats[0] + s_stats[1] + s_stats[2];  // played = sum of the histogram
         if (threadIdx.x == 7) s_stats[7] = s_stats[3] + s_stats[4] + s_stats[5];
@@ -93,9 +93,9 @@ struct Decision {
 // transition, draw the epsilon test / random score vector
 __device__ __forceinline__ void decide_begin(NfspW &g, const RolloutArgs &A, uint64_t game, uint64_t step, Decision &d,
                                              Counters &c) {
+    const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
     if (g.need_reset()) {
-        const Philox4 y = game_block(A.seed, game, step, STREAM_RESET);
-        g.reset(g.dealer() ^ 1u, deal_ranks(__umulhi(y.x, 120u)), y.y < A.eta_u32, y.z < A.eta_u32);
+        g.reset(g.dealer() ^ 1u, deal_ranks(__umulhi(x.y, 120u)), x.z < A.eta_u32, x.w < A.eta_u32);
         d.started = true;
         ++c.hands;
     }
@@ -106,12 +106,12 @@ __device__ __forceinline__ void decide_begin(NfspW &g, const RolloutArgs &A, uin
         d.recA = make_rl(g.snapshot(d.p), d.obs, 0, g.last_a(d.p), 0u, (uint32_t)d.p);
     }
     d.pol = g.policy(d.p);
-    const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
-    if (d.pol && x.x < A.eps_u32) {  // agent.py:125-128: np.random.rand(1,1,3)
+    if (d.pol && x.x < A.eps_u32) {  // agent.py:125-128: np.random.rand(1,1,3); rare, so its own Philox block
+        const Philox4 y = game_block(A.seed, game, step, STREAM_VECTOR);
         d.random = true;
-        d.v0 = (float)(x.y >> 8) * (1.0f / 16777216.0f);
-        d.v1 = (float)(x.z >> 8) * (1.0f / 16777216.0f);
-        d.v2 = (float)(x.w >> 8) * (1.0f / 16777216.0f);
+        d.v0 = (float)(y.x >> 8) * (1.0f / 16777216.0f);
+        d.v1 = (float)(y.y >> 8) * (1.0f / 16777216.0f);
+        d.v2 = (float)(y.z >> 8) * (1.0f / 16777216.0f);
     }
 }
 
@@ -119,8 +119,8 @@ __device__ __forceinline__ void decide_begin(NfspW &g, const RolloutArgs &A, uin
 // Must be called by ALL lanes of a warp (live or not): it contains warp collectives.
 template <bool kDebug>
 __device__ __forceinline__ void decide_finish(NfspW &g, const RolloutArgs &A, const Decision &d, float v0, float v1,
-                                              float v2, bool live, int64_t at, int64_t plane, Counters &c,
-                                              unsigned long long *s_stats) {
+                                              float v2, bool live, int64_t at, int64_t plane, uint32_t seg,
+                                              Counters &c, unsigned long long *s_stats) {
     uint4 recB, recC, recS;
     bool vB = false, vC = false, vS = false;
     const int p = d.p;
@@ -163,22 +163,43 @@ __device__ __forceinline__ void decide_finish(NfspW &g, const RolloutArgs &A, co
             A.trace[2 * plane + at] = g.trace_misc(a, eff, d.started);
         }
     }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const bool mine = live && (p == q);
-        const int cnt = mine ? ((int)d.vA + (int)vB) : (int)(live && vC);
-        uint32_t off;
-        const uint32_t b = warp_claim(A.counts + q, cnt, off);
-        uint4 *dst = A.rl[q];
-        if (mine) {
-            if (d.vA) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = d.recA; else ++c.drop; ++off; }
-            if (vB) { if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recB; else ++c.drop; }
-        } else if (live && vC) {
-            if ((int64_t)(b + off) < A.cap_rl) dst[b + off] = recC; else ++c.drop;
+    // ---- append: counts per destination array k = rl0, rl1, sl0, sl1
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const int n_rl_p = (int)d.vA + (int)vB;  // records for the actor's ring (0..2)
+    const uint32_t a1_0 = __ballot_sync(0xFFFFFFFFu, live && p == 0 && n_rl_p >= 1);
+    const uint32_t a2_0 = __ballot_sync(0xFFFFFFFFu, live && p == 0 && n_rl_p >= 2);
+    const uint32_t a1_1 = __ballot_sync(0xFFFFFFFFu, live && p == 1 && n_rl_p >= 1);
+    const uint32_t a2_1 = __ballot_sync(0xFFFFFFFFu, live && p == 1 && n_rl_p >= 2);
+    const uint32_t c_0 = __ballot_sync(0xFFFFFFFFu, live && vC && p == 1);  // opponent's terminal record -> ring 0
+    const uint32_t c_1 = __ballot_sync(0xFFFFFFFFu, live && vC && p == 0);
+    const uint32_t s_0 = __ballot_sync(0xFFFFFFFFu, live && vS && p == 0);
+    const uint32_t s_1 = __ballot_sync(0xFFFFFFFFu, live && vS && p == 1);
+    const uint32_t tot0 = __popc(a1_0) + __popc(a2_0) + __popc(c_0), tot1 = __popc(a1_1) + __popc(a2_1) + __popc(c_1);
+    const uint32_t tot2 = __popc(s_0), tot3 = __popc(s_1);
+    uint32_t base = 0;
+    if (lane < 4) {
+        const uint32_t t = lane == 0 ? tot0 : (lane == 1 ? tot1 : (lane == 2 ? tot2 : tot3));
+        if (t) base = atomicAdd(A.counts + lane * A.n_seg + seg, t);
+    }
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, 0), b1 = __shfl_sync(0xFFFFFFFFu, base, 1);
+    const uint32_t b2 = __shfl_sync(0xFFFFFFFFu, base, 2), b3 = __shfl_sync(0xFFFFFFFFu, base, 3);
+    if (live) {
+        // slot order inside a warp's claim for ring q: [actor lanes' records in lane order][opponent records]
+        const uint32_t a1 = p == 0 ? a1_0 : a1_1, a2 = p == 0 ? a2_0 : a2_1;
+        const uint32_t bp = p == 0 ? b0 : b1, bo = p == 0 ? b1 : b0;
+        uint4 *rp = A.rl[p] + (size_t)seg * A.cap_rl, *ro = A.rl[p ^ 1] + (size_t)seg * A.cap_rl;
+        uint32_t off = bp + __popc(a1 & lt) + __popc(a2 & lt);
+        if (d.vA) { if ((int64_t)off < A.cap_rl) rp[off] = d.recA; else ++c.drop; ++off; }
+        if (vB) { if ((int64_t)off < A.cap_rl) rp[off] = recB; else ++c.drop; }
+        if (vC) {
+            const uint32_t oa1 = p == 0 ? a1_1 : a1_0, oa2 = p == 0 ? a2_1 : a2_0, oc = p == 0 ? c_1 : c_0;
+            const uint32_t o2 = bo + __popc(oa1) + __popc(oa2) + __popc(oc & lt);
+            if ((int64_t)o2 < A.cap_rl) ro[o2] = recC; else ++c.drop;
         }
-        const int cs = (mine && vS) ? 1 : 0;
-        const uint32_t bs = warp_claim(A.counts + 2 + q, cs, off);
-        if (cs) { if ((int64_t)(bs + off) < A.cap_sl) A.sl[q][bs + off] = recS; else ++c.drop; }
+        if (vS) {
+            const uint32_t o3 = (p == 0 ? b2 : b3) + __popc((p == 0 ? s_0 : s_1) & lt);
+            if ((int64_t)o3 < A.cap_sl) (A.sl[p] + (size_t)seg * A.cap_sl)[o3] = recS; else ++c.drop;
+        }
     }
 }
 

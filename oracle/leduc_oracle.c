@@ -339,14 +339,15 @@ void orc_nfsp_batch_flags(const OrcNfspBatch *b, int g, int out[4]) {
 
 static void nfsp_game_reset(const OrcNfspBatch *b, int gi, int dealer, uint64_t step, uint32_t eta_u32) {
     NfspGame *g = &b->g[gi];
-    uint32_t y[4];
+    uint32_t x[4];
     int ranks[3];
-    game_block(b->seed, b->game0 + (uint64_t)gi, step, 1u, y);
-    deal_from_index(mulhi32(y[0], 120u), ranks);
+    /* generation spec: the step block (stream 0) carries .x action / epsilon, .y deal, .z .w policies */
+    game_block(b->seed, b->game0 + (uint64_t)gi, step, 0u, x);
+    deal_from_index(mulhi32(x[1], 120u), ranks);
     orc_nfsp_reset(&g->env, dealer, ranks[0], ranks[1], ranks[2]);
     /* main.py:38-45: policy 'a' iff random.random() > eta; here 'b' iff u32 draw < eta*2^32 */
-    g->policy[0] = y[1] < eta_u32;
-    g->policy[1] = y[2] < eta_u32;
+    g->policy[0] = x[2] < eta_u32;
+    g->policy[1] = x[3] < eta_u32;
     g->acted_nonzero[0] = g->acted_nonzero[1] = 0;
     g->last_a[0] = g->last_a[1] = 0;
     g->need_reset = 0;
@@ -489,8 +490,10 @@ void orc_nfsp_batch_rollout_act(OrcNfspBatch *b, uint64_t step0, int n_steps, co
             int is_br = g->policy[p];
             if (!is_br) {
                 orc_mlp_avg(&nets[p * 2 + 0], x, vec); /* agent.py:143 */
-            } else if (u[0] < eps_u32) {               /* agent.py:125-128: random score vector */
-                for (int c = 0; c < 3; ++c) vec[c] = (float)(u[1 + c] >> 8) * (1.0f / 16777216.0f);
+            } else if (u[0] < eps_u32) {               /* agent.py:125-128: random score vector, stream 1 */
+                uint32_t y[4];
+                game_block(b->seed, b->game0 + (uint64_t)gi, step, 1u, y);
+                for (int c = 0; c < 3; ++c) vec[c] = (float)(y[c] >> 8) * (1.0f / 16777216.0f);
             } else {
                 orc_mlp_br(&nets[p * 2 + 1], x, vec);
             }
@@ -554,10 +557,10 @@ void orc_legacy_batch_destroy(OrcLegacyBatch *b) {
 const OrcLegacyEnv *orc_legacy_batch_env(const OrcLegacyBatch *b, int g) { return &b->g[g].env; }
 
 static void legacy_game_reset(const OrcLegacyBatch *b, int gi, uint64_t step) {
-    uint32_t y[4];
+    uint32_t x[4];
     int ranks[3];
-    game_block(b->seed, b->game0 + (uint64_t)gi, step, 1u, y);
-    deal_from_index(mulhi32(y[0], 120u), ranks);
+    game_block(b->seed, b->game0 + (uint64_t)gi, step, 0u, x);   /* legacy: .x .y actions, .z deal */
+    deal_from_index(mulhi32(x[2], 120u), ranks);
     orc_legacy_reset(&b->g[gi].env, ranks[0], ranks[1]);
     b->g[gi].hand_count++;
     b->g[gi].need_reset = 0;

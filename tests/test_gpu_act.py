@@ -301,6 +301,24 @@ def test_memories_after_rollout_match_sequential_oracle(nb):
     assert int(sp.counts.sum().item()) == 0
 
 
+def test_segmented_batches_match_dense_order(nb):
+    """A batch staged in segments inserts exactly like the same records staged densely in segment order."""
+    rng = np.random.RandomState(8)
+    n_seg, seg_cap, cap = 8, 40, 97
+    counts = rng.randint(0, seg_cap + 1, n_seg).astype(np.int32)
+    counts[3] = 0
+    stage = rng.randint(0, 1 << 30, (n_seg, seg_cap, 4)).astype(np.int32)
+    dense = np.concatenate([stage[s, : counts[s]] for s in range(n_seg)])
+    for kind in ("ring", "res"):
+        a = nb.DeviceRing(cap, 3) if kind == "ring" else nb.DeviceReservoir(cap, 3)
+        b = nb.DeviceRing(cap, 3) if kind == "ring" else nb.DeviceReservoir(cap, 3)
+        for rep in range(3):
+            a.insert(torch.from_numpy(stage.reshape(-1, 4)).to(a.device), torch.from_numpy(counts.copy()).to(a.device), seg_cap)
+            b.insert(torch.from_numpy(dense).to(b.device), torch.tensor([len(dense)], dtype=torch.int32, device=b.device))
+        assert int(a.total.item()) == int(b.total.item()) == 3 * len(dense)
+        assert torch.equal(a.data, b.data), kind
+
+
 def test_dropin_buffers_reference_shapes(nb, golden_dir):
     """utils.replay_buffer.ReplayBuffer / utils.ReservoirBuffer.ReservoirBuffer: the reference's call
     signatures, return shapes and FIFO / saturation behaviour."""
