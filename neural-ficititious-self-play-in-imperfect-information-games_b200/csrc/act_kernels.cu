@@ -7,6 +7,7 @@
 // 30-bit mask that never leaves registers; because it is binary and sparse (<= 9 bits set) the
 // first layer is a SUM OF WEIGHT ROWS read from shared memory as float4s instead of a dense 30x64
 // product: <= 9 rows for arbitrary masks (act_forward_kernel), 3 precombined rows in the rollout.
+#include "mlp_math.cuh"
 #include "rollout_common.cuh"
 
 namespace nfsp {
@@ -106,27 +107,14 @@ __device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st,
     const float4 *r0 = T + net * 48 + 12 + dealer * 9 + seq_id(both & 63u);
     const float4 *r1 = T + net * 48 + 30 + dealer * 9 + seq_id((both >> 6) & 63u);
     const float4 *w2 = reinterpret_cast<const float4 *>(st + kTabFloats) + net * 3;
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    Layer2Acc acc;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const float4 a = rc[q * kTabRows], b = r0[q * kTabRows], c = r1[q * kTabRows];
-        const float hx = fmaxf((b.x + c.x) + a.x, 0.f), hy = fmaxf((b.y + c.y) + a.y, 0.f);
-        const float hz = fmaxf((b.z + c.z) + a.z, 0.f), hw = fmaxf((b.w + c.w) + a.w, 0.f);
-        const float4 u0 = w2[q * 12], u1 = w2[q * 12 + 1], u2 = w2[q * 12 + 2];
-        z0 = fmaf(hx, u0.x, z0); z0 = fmaf(hy, u0.y, z0); z0 = fmaf(hz, u0.z, z0); z0 = fmaf(hw, u0.w, z0);
-        z1 = fmaf(hx, u1.x, z1); z1 = fmaf(hy, u1.y, z1); z1 = fmaf(hz, u1.z, z1); z1 = fmaf(hw, u1.w, z1);
-        z2 = fmaf(hx, u2.x, z2); z2 = fmaf(hy, u2.y, z2); z2 = fmaf(hz, u2.z, z2); z2 = fmaf(hw, u2.w, z2);
+        acc.quad((b.x + c.x) + a.x, (b.y + c.y) + a.y, (b.z + c.z) + a.z, (b.w + c.w) + a.w, w2[q * 12], w2[q * 12 + 1],
+                 w2[q * 12 + 2]);
     }
-    const float4 b2 = reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net];
-    z0 += b2.x; z1 += b2.y; z2 += b2.z;
-    if (net & 1) {
-        out[0] = fmaxf(z0, 0.f); out[1] = fmaxf(z1, 0.f); out[2] = fmaxf(z2, 0.f);
-    } else {
-        const float m = fmaxf(z0, fmaxf(z1, z2));
-        const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
-        const float inv = 1.0f / (e0 + e1 + e2);
-        out[0] = e0 * inv; out[1] = e1 * inv; out[2] = e2 * inv;
-    }
+    acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1, out[0], out[1], out[2]);
 }
 
 // forward of one net on one observation mask; sw = packed image in shared memory

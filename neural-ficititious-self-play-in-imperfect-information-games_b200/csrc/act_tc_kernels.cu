@@ -13,6 +13,7 @@
 //   B: 3 splits x (64 n x 128 k) = 3 x 16 KB, built once per weight update, brought in by a bulk copy
 #include <cuda_bf16.h>
 
+#include "mlp_math.cuh"
 #include "rollout_common.cuh"
 
 namespace nfsp {
@@ -78,6 +79,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// polling wait with back-off: used by the one warp per group that watches the MMA-done barrier
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -177,26 +192,11 @@ __device__ __forceinline__ void tc_layer1(const TcTile &t, uint32_t phase, float
 
 __device__ __forceinline__ void layer2_head(const float *__restrict__ w2img, const float *h, int net, float out[3]) {
     const float4 *w2 = reinterpret_cast<const float4 *>(w2img) + net * 3;
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    Layer2Acc acc;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float hx = fmaxf(h[4 * q], 0.f), hy = fmaxf(h[4 * q + 1], 0.f);
-        const float hz = fmaxf(h[4 * q + 2], 0.f), hw = fmaxf(h[4 * q + 3], 0.f);
-        const float4 u0 = w2[q * 12], u1 = w2[q * 12 + 1], u2 = w2[q * 12 + 2];
-        z0 = fmaf(hx, u0.x, z0); z0 = fmaf(hy, u0.y, z0); z0 = fmaf(hz, u0.z, z0); z0 = fmaf(hw, u0.w, z0);
-        z1 = fmaf(hx, u1.x, z1); z1 = fmaf(hy, u1.y, z1); z1 = fmaf(hz, u1.z, z1); z1 = fmaf(hw, u1.w, z1);
-        z2 = fmaf(hx, u2.x, z2); z2 = fmaf(hy, u2.y, z2); z2 = fmaf(hz, u2.z, z2); z2 = fmaf(hw, u2.w, z2);
-    }
-    const float4 b2 = reinterpret_cast<const float4 *>(w2img + 16 * 4 * 3 * 4)[net];
-    z0 += b2.x; z1 += b2.y; z2 += b2.z;
-    if (net & 1) {
-        out[0] = fmaxf(z0, 0.f); out[1] = fmaxf(z1, 0.f); out[2] = fmaxf(z2, 0.f);
-    } else {
-        const float m = fmaxf(z0, fmaxf(z1, z2));
-        const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
-        const float inv = 1.0f / (e0 + e1 + e2);
-        out[0] = e0 * inv; out[1] = e1 * inv; out[2] = e2 * inv;
-    }
+    for (int q = 0; q < 16; ++q)
+        acc.quad(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3], w2[q * 12], w2[q * 12 + 1], w2[q * 12 + 2]);
+    acc.head(reinterpret_cast<const float4 *>(w2img + 16 * 4 * 3 * 4)[net], net & 1, out[0], out[1], out[2]);
 }
 
 // writes the thread's operand row: the 4 chunks of `net` hold obs|bias, the 4 chunks of the net the row held
@@ -409,10 +409,13 @@ rollout_tc_kernel(const RolloutArgs A) {
             Decision d;
             if (live) decide_begin(g, A, game, A.step0 + (uint64_t)s, d, c);
             const uint32_t net = live ? (uint32_t)(d.p * 2) + d.pol : 0u;
-            // ---- counting sort of the group's rows by net: packed byte counters, one word per warp
-            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, net == 0), m1 = __ballot_sync(0xFFFFFFFFu, net == 1);
-            const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, net == 2), m3 = ~(m0 | m1 | m2);
-            const uint32_t mine = net == 0 ? m0 : (net == 1 ? m1 : (net == 2 ? m2 : m3));
+            // ---- counting sort of the group's rows by net: packed byte counters, one word per warp.  Sort key
+            // order avg0, br0, br1, avg1 keeps the two small best-response segments adjacent, so fewer warps
+            // straddle a segment boundary.
+            const uint32_t key = net ^ (net >> 1);  // net 0,1,2,3 -> key 0,1,3,2
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, key == 0), m1 = __ballot_sync(0xFFFFFFFFu, key == 1);
+            const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, key == 2), m3 = ~(m0 | m1 | m2);
+            const uint32_t mine = key == 0 ? m0 : (key == 1 ? m1 : (key == 2 ? m2 : m3));
             const uint32_t rank = __popc(mine & ((1u << lane) - 1u));
             if (lane == 0) sCnt[wq] = __popc(m0) | (__popc(m1) << 8) | (__popc(m2) << 16) | (__popc(m3) << 24);
             group_bar(1 + group);
@@ -420,8 +423,8 @@ rollout_tc_kernel(const RolloutArgs A) {
             const uint32_t tot = c0 + c1 + c2 + c3;  // bytes: rows of net 0..3 (<= 128 each, no carry)
             const uint32_t before = (wq > 0 ? c0 : 0u) + (wq > 1 ? c1 : 0u) + (wq > 2 ? c2 : 0u);
             const uint32_t seg1 = tot & 0xFFu, seg2 = seg1 + ((tot >> 8) & 0xFFu), seg3 = seg2 + ((tot >> 16) & 0xFFu);
-            const uint32_t seg_start = net == 0 ? 0u : (net == 1 ? seg1 : (net == 2 ? seg2 : seg3));
-            const uint32_t pos = seg_start + ((before >> (8 * net)) & 0xFFu) + rank;
+            const uint32_t seg_start = key == 0 ? 0u : (key == 1 ? seg1 : (key == 2 ? seg2 : seg3));
+            const uint32_t pos = seg_start + ((before >> (8 * key)) & 0xFFu) + rank;
             {  // operand row `pos`: observation bits + the constant 1 that carries b1
                 uint8_t *row = sA + (pos >> 3) * kWideSBO + (pos & 7u) * 16;
                 const uint32_t x = (d.obs & 0x3FFFFFFFu) | (1u << 30);
@@ -444,47 +447,44 @@ rollout_tc_kernel(const RolloutArgs A) {
                 umma_commit(bar_done);
             }
             ph_hand ^= 1u;
-            if (wq == 0) mbar_wait(bar_done, ph_done);  // one warp polls the mbarrier, the others sleep on the barrier
+            if (wq == 0) mbar_wait_backoff(bar_done, ph_done);  // one warp polls the mbarrier, the others sleep on the barrier
             ph_done ^= 1u;
             group_bar(1 + group);
             tc_fence_after();
             // ---- epilogue of sorted row `gtid`: its net's 64 pre-activations -> layer 2 -> head
             const uint32_t r = gtid;
-            const uint32_t my_net = (r >= seg1) + (r >= seg2) + (r >= seg3);
+            const uint32_t my_key = (r >= seg1) + (r >= seg2) + (r >= seg3);
+            const uint32_t my_net = my_key ^ (my_key >> 1);  // inverse of the key map
             const uint32_t r_lo = wq * 32u, r_hi = r_lo + 31u;
-            const uint32_t n_lo = (r_lo >= seg1) + (r_lo >= seg2) + (r_lo >= seg3);
-            const uint32_t n_hi = (r_hi >= seg1) + (r_hi >= seg2) + (r_hi >= seg3);
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-            for (uint32_t nn = n_lo; nn <= n_hi; ++nn) {  // warp-uniform; two nets only at a segment boundary
-                const float4 *w2 = reinterpret_cast<const float4 *>(sW2) + nn * 3;
-                float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+            const uint32_t k_lo = (r_lo >= seg1) + (r_lo >= seg2) + (r_lo >= seg3);
+            const uint32_t k_hi = (r_hi >= seg1) + (r_hi >= seg2) + (r_hi >= seg3);
+            const float4 *w2 = reinterpret_cast<const float4 *>(sW2) + my_net * 3;
+            Layer2Acc acc;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    float h[16];
-                    tmem_ld16(tmem_acc + nn * 64u + ch * 16u, h);
+            for (int ch = 0; ch < 4; ++ch) {
+                float h[16];
+                if (k_lo == k_hi) {  // the whole warp reads one net's columns (the common case)
+                    tmem_ld16(tmem_acc + my_net * 64u + ch * 16u, h);
+                } else {             // segment boundary inside the warp: one TMEM read per net present, select
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float hx = fmaxf(h[4 * q], 0.f), hy = fmaxf(h[4 * q + 1], 0.f);
-                        const float hz = fmaxf(h[4 * q + 2], 0.f), hw = fmaxf(h[4 * q + 3], 0.f);
-                        const float4 u0 = w2[(ch * 4 + q) * 12], u1 = w2[(ch * 4 + q) * 12 + 1], u2 = w2[(ch * 4 + q) * 12 + 2];
-                        z0 = fmaf(hx, u0.x, z0); z0 = fmaf(hy, u0.y, z0); z0 = fmaf(hz, u0.z, z0); z0 = fmaf(hw, u0.w, z0);
-                        z1 = fmaf(hx, u1.x, z1); z1 = fmaf(hy, u1.y, z1); z1 = fmaf(hz, u1.z, z1); z1 = fmaf(hw, u1.w, z1);
-                        z2 = fmaf(hx, u2.x, z2); z2 = fmaf(hy, u2.y, z2); z2 = fmaf(hz, u2.z, z2); z2 = fmaf(hw, u2.w, z2);
+                    for (int e = 0; e < 16; ++e) h[e] = 0.f;
+                    for (uint32_t kk = k_lo; kk <= k_hi; ++kk) {
+                        const uint32_t nn = kk ^ (kk >> 1);
+                        float t16[16];
+                        tmem_ld16(tmem_acc + nn * 64u + ch * 16u, t16);
+                        if (kk == my_key) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) h[e] = t16[e];
+                        }
                     }
                 }
-                const float4 b2 = reinterpret_cast<const float4 *>(sW2 + 16 * 4 * 3 * 4)[nn];
-                z0 += b2.x; z1 += b2.y; z2 += b2.z;
-                float t0, t1, t2;
-                if (nn & 1u) {
-                    t0 = fmaxf(z0, 0.f); t1 = fmaxf(z1, 0.f); t2 = fmaxf(z2, 0.f);
-                } else {
-                    const float m = fmaxf(z0, fmaxf(z1, z2));
-                    const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
-                    const float inv = 1.0f / (e0 + e1 + e2);
-                    t0 = e0 * inv; t1 = e1 * inv; t2 = e2 * inv;
-                }
-                if (nn == my_net) { o0 = t0; o1 = t1; o2 = t2; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    acc.quad(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3], w2[(ch * 4 + q) * 12],
+                             w2[(ch * 4 + q) * 12 + 1], w2[(ch * 4 + q) * 12 + 2]);
             }
+            float o0, o1, o2;
+            acc.head(reinterpret_cast<const float4 *>(sW2 + 16 * 4 * 3 * 4)[my_net], my_net & 1u, o0, o1, o2);
             sResult[sOwner[r]] = make_float4(o0, o1, o2, 0.f);
             tc_fence_before();
             group_bar(1 + group);                 // all TMEM reads of the slot are done; results are visible
