@@ -8,12 +8,13 @@
 // first layer is a SUM OF WEIGHT ROWS read from shared memory as float4s instead of a dense 30x64
 // product: <= 9 rows for arbitrary masks (act_forward_kernel), 3 precombined rows in the rollout.
 #include "mlp_math.cuh"
-#include "rollout_common.cuh"
+#include "ptx_helpers.cuh"
+#include "rollout_fast.cuh"
 
 namespace nfsp {
 
 constexpr int kActThreads = 128;   // act_forward_kernel (generic observation masks)
-constexpr int kRollThreads = 256;  // rollout_kernel
+constexpr int kRollThreads = 768;  // rollout_kernel: one CTA per SM
 // packed weight image (floats): W1 rows as [16 col-quads][128 rows = net*32 + input][4], where input 30 is
 // the bias b1; then W2 as [64 hidden][4 nets][4 = 3 outputs + pad]; then b2 as [4 nets][4].
 constexpr int kW1Floats = 16 * 128 * 4;
@@ -43,48 +44,67 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
 
 // ---- group-factorised first layer (rollout path) --------------------------------------------------
 // Under main.train's turn order an observation is (cards of the actor, round-0 betting sequence,
-// round-1 betting sequence); each group takes few values, so W1^T x + b1 is the sum of THREE
-// precombined rows: T_cards[c_p][public state] (+ b1), T_r0[dealer][sequence], T_r1[dealer][sequence].
-// The rows are sums of W1 rows only (input independent), rebuilt whenever the weights change.
-//   per net 48 rows: 0-11 cards (c_p*4 + (revealed ? 1+pub : 0)), 12-29 round 0, 30-47 round 1
-//   (dealer*9 + sequence id: 0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC).
-// Image: rows as [16 col-quads][192 rows][4] floats, then W2 as [16 quads][4 nets][3 outputs][4], then b2.
-constexpr int kTabRows = 4 * 48;
-constexpr int kTabFloats = 16 * kTabRows * 4;
-constexpr int kTabW2Floats = 16 * 4 * 3 * 4;
+// round-1 betting sequence); each group takes few values, so W1^T x + b1 is the sum of TWO precombined
+// rows X + Y.  The rows are sums of W1 rows only (input independent), rebuilt whenever the weights change.
+//   per net 111 rows:
+//     X  0-2    round 0: private card c (+ b1)
+//        3-74   round 1: 3 + ((c*3 + pub)*2 + dealer)*4 + f, f = finished round-0 sequence CC, RC, CRC, RRC
+//               = card rows + public card + round-0 history bits (+ b1)
+//     Y  75-92  round 0: 75 + dealer*9 + sequence id so far (0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC)
+//        93-110 round 1: 93 + dealer*9 + sequence id so far
+// Shared-memory layout: a row is 24 float4 "quads": the 16 quads of the 64 hidden units followed by a copy of
+// the first 8, so a thread can read its row starting at quad rot = game & 7 with immediate offsets.  The 8
+// threads of a quarter-warp then hit 8 different 16-byte bank groups whatever rows they gather: the row
+// gathers are bank-conflict free (the straight layout ran at 2.0-2.5x the ideal wavefront count, ncu r01a).
+// W2 uses the same rotated layout, [net][output][24 quads], so a quad of h meets its own weights.
+constexpr int kNetRows = 111, kRowQuads = 24;
+constexpr int kTabRows = 4 * kNetRows;
+constexpr int kTabFloats = kTabRows * kRowQuads * 4;
+constexpr int kTabW2Floats = 4 * 3 * kRowQuads * 4;
 constexpr int kTabImageFloats = kTabFloats + kTabW2Floats + kB2Floats;
 constexpr int kTabImageBytes = kTabImageFloats * 4;
+
+// history bits of betting sequence `id` in round rr when `d` deals (the dealer opens, players alternate)
+__device__ __forceinline__ uint32_t seq_bits(int rr, int d, int id) {
+    const int s0 = id == 0 ? 0 : (id == 1 || id == 3 || id == 4 || id == 7 ? 1 : 2);
+    const int s1 = id < 3 ? 0 : (id == 3 || id == 5 ? 1 : 2);
+    const int s2 = id >= 7 ? 1 : 0;
+    const int sl[3] = {s0, s1, s2};
+    uint32_t bits = 0;
+    for (int k = 0; k < 3; ++k)
+        if (sl[k]) bits |= 1u << (((k & 1) ^ d) * 12 + rr * 6 + k * 2 + (sl[k] - 1));
+    return bits;
+}
 
 __global__ void pack_tables_kernel(const float *__restrict__ w, float *__restrict__ img) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kTabImageFloats; e += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (e < kTabFloats) {
-            const int c = e & 3, row = (e >> 2) % kTabRows, q = (e >> 2) / kTabRows;
-            const int net = row / 48, r = row % 48, j = q * 4 + c;
+            const int x = e & 3, pos = (e >> 2) % kRowQuads, row = (e >> 2) / kRowQuads;
+            const int net = row / kNetRows, r = row % kNetRows, j = (pos & 15) * 4 + x;
             const float *W1 = w + net * NFSP_NET_PARAMS;  // W1[i*64 + j]
             uint32_t bits = 0;                            // observation bits this row stands for
-            if (r < 12) {
-                const int cp = r >> 2, ps = r & 3;
-                if (cp < 3) {
-                    bits = 1u << (24 + cp);
-                    if (ps) bits |= (1u << (27 + cp)) | (1u << (27 + (ps - 1)));
-                }
+            bool bias = false;
+            if (r < 3) {
+                bits = 1u << (24 + r);
+                bias = true;
+            } else if (r < 75) {
+                const int idx = r - 3, f = idx & 3, d = (idx >> 2) & 1, cp = idx >> 3, c = cp / 3, pub = cp % 3;
+                const int fin[4] = {3, 5, 7, 8};
+                bits = (1u << (24 + c)) | (1u << (27 + c)) | (1u << (27 + pub)) | seq_bits(0, d, fin[f]);
+                bias = true;
+            } else if (r < 93) {
+                bits = seq_bits(0, (r - 75) / 9, (r - 75) % 9);
             } else {
-                const int rr = (r - 12) / 18, d = ((r - 12) % 18) / 9, id = (r - 12) % 9;
-                // sequence id -> actions of slots 0..2 (1 = call, 2 = raise, 0 = none)
-                const int s0 = id == 0 ? 0 : (id == 1 || id == 3 || id == 4 || id == 7 ? 1 : 2);
-                const int s1 = id < 3 ? 0 : (id == 3 || id == 5 ? 1 : 2);
-                const int s2 = id >= 7 ? 1 : 0;
-                const int sl[3] = {s0, s1, s2};
-                for (int k = 0; k < 3; ++k)
-                    if (sl[k]) bits |= 1u << (((k & 1) ^ d) * 12 + rr * 6 + k * 2 + (sl[k] - 1));
+                bits = seq_bits(1, (r - 93) / 9, (r - 93) % 9);
             }
             for (int i = 0; i < 30; ++i)
                 if ((bits >> i) & 1u) v += W1[i * 64 + j];
-            if (r < 12 && (r >> 2) < 3) v += W1[1920 + j];  // b1 rides on the card row
+            if (bias) v += W1[1920 + j];
         } else if (e < kTabFloats + kTabW2Floats) {
-            const int f = e - kTabFloats, x = f & 3, c = (f >> 2) % 3, net = ((f >> 2) / 3) & 3, q = (f >> 2) / 12;
-            v = w[net * NFSP_NET_PARAMS + 1984 + (q * 4 + x) * 3 + c];
+            const int f = e - kTabFloats, x = f & 3, pos = (f >> 2) % kRowQuads, c = ((f >> 2) / kRowQuads) % 3;
+            const int net = (f >> 2) / (3 * kRowQuads);
+            v = w[net * NFSP_NET_PARAMS + 1984 + ((pos & 15) * 4 + x) * 3 + c];
         } else {
             const int f = e - kTabFloats - kTabW2Floats, c = f & 3, net = f >> 2;
             if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
@@ -93,28 +113,20 @@ __global__ void pack_tables_kernel(const float *__restrict__ w, float *__restric
     }
 }
 
-__device__ __forceinline__ uint32_t seq_id(uint32_t rnd) {  // 6 slot bits of one round -> sequence id 0..8
-    const uint32_t s0 = rnd & 3u, s1 = (rnd >> 2) & 3u, s2 = (rnd >> 4) & 3u;
-    return s2 ? 6u + s0 : (s1 ? 2u * s0 + s1 : s0);
-}
-
-// one decision of net `net` on the game word: layer 1 as 3 row reads streamed into layer 2
-__device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st, uint32_t hist, uint32_t cp,
-                                                   uint32_t pubstate, uint32_t dealer, int net, float out[3]) {
+// one decision of net `net`: layer 1 as two rotated row reads streamed into layer 2
+__device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st, uint32_t xrow, uint32_t yrow,
+                                                   uint32_t net, uint32_t rot, float &o0, float &o1, float &o2) {
     const float4 *T = reinterpret_cast<const float4 *>(st);
-    const uint32_t both = hist | (hist >> 12);
-    const float4 *rc = T + net * 48 + cp * 4 + pubstate;
-    const float4 *r0 = T + net * 48 + 12 + dealer * 9 + seq_id(both & 63u);
-    const float4 *r1 = T + net * 48 + 30 + dealer * 9 + seq_id((both >> 6) & 63u);
-    const float4 *w2 = reinterpret_cast<const float4 *>(st + kTabFloats) + net * 3;
+    const float4 *xr = T + (net * kNetRows + xrow) * kRowQuads + rot;
+    const float4 *yr = T + (net * kNetRows + yrow) * kRowQuads + rot;
+    const float4 *wr = T + kTabRows * kRowQuads + net * (3 * kRowQuads) + rot;
     Layer2Acc acc;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-        const float4 a = rc[q * kTabRows], b = r0[q * kTabRows], c = r1[q * kTabRows];
-        acc.quad((b.x + c.x) + a.x, (b.y + c.y) + a.y, (b.z + c.z) + a.z, (b.w + c.w) + a.w, w2[q * 12], w2[q * 12 + 1],
-                 w2[q * 12 + 2]);
+        const float4 a = xr[q], b = yr[q];
+        acc.quad(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w, wr[q], wr[kRowQuads + q], wr[2 * kRowQuads + q]);
     }
-    acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1, out[0], out[1], out[2]);
+    acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1u, o0, o1, o2);
 }
 
 // forward of one net on one observation mask; sw = packed image in shared memory
@@ -174,47 +186,65 @@ act_forward_kernel(const float *__restrict__ pack, const uint32_t *__restrict__ 
     }
 }
 
+// One persistent CTA per SM (the table image fills most of its shared memory); a warp owns 32 consecutive
+// games for the launch's steps, the games' state lives in registers in the actor-relative form of
+// nfsp_fast.cuh and goes back to HBM as the packed word.
 template <bool kDebug>
-__global__ void __launch_bounds__(kRollThreads, 3)
+__global__ void __launch_bounds__(kRollThreads, 1)
 rollout_kernel(const RolloutArgs A) {
-    extern __shared__ __align__(16) float sw[];  // table image, kTabImageBytes
+    extern __shared__ __align__(128) float sw[];  // table image, kTabImageBytes
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint8_t s_deal[120];
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(A.pack);
-        float4 *dst = reinterpret_cast<float4 *>(sw);
-        for (int e = threadIdx.x; e < kTabImageFloats / 4; e += blockDim.x) dst[e] = src[e];
-        __syncthreads();
+    fill_deal_lut(s_deal);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
     }
-    Counters c;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the table image comes in as bulk async copies (TMA unit), completion on an mbarrier
+        mbar_expect_tx(bar, kTabImageBytes);
+        constexpr uint32_t kChunk = 32768;
+        for (uint32_t off = 0; off < (uint32_t)kTabImageBytes; off += kChunk) {
+            const uint32_t len = (uint32_t)kTabImageBytes - off < kChunk ? (uint32_t)kTabImageBytes - off : kChunk;
+            bulk_g2s(smem_u32(sw) + off, reinterpret_cast<const uint8_t *>(A.pack) + off, len, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    FastCounters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
-    // all lanes of a warp stay in the loop together (warp collectives in decide_finish)
+    const uint32_t lane = threadIdx.x & 31u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < A.n; base += stride) {
-        const int64_t i = base + (threadIdx.x & 31);
+        const int64_t i = base + lane;
         const bool live = i < A.n;
-        const uint32_t seg = (uint32_t)(base >> 5) & (A.n_seg - 1u);
         const uint64_t game = A.game0 + (uint64_t)i;
-        NfspW g{live ? A.state[i] : 0ull};
+        const uint32_t rot = (uint32_t)game & 7u;
+        WarpStage W;
+        W.init(A, (uint32_t)(base >> 5) & (A.n_seg - 1u));
+        NfspFast g;
+        g.unpack(live ? A.state[i] : 0ull);
         for (int t = 0; t < A.n_steps; ++t) {
-            Decision d;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-            if (live) {
-                decide_begin(g, A, game, A.step0 + (uint64_t)t, d, c);
-                if (d.random) {
-                    v0 = d.v0; v1 = d.v1; v2 = d.v2;
-                } else {
-                    float v[3];
-                    mlp_forward_tables(sw, g.hist(), g.card(d.p), g.round() ? 1u + g.pub() : 0u, g.dealer(),
-                                       d.p * 2 + (int)d.pol, v);
-                    v0 = v[0]; v1 = v[1]; v2 = v[2];
-                }
-            }
-            decide_finish<kDebug>(g, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, seg, c, s_stats);
+            FastDecision d;
+            fast_begin(g, s_deal, A, game, A.step0 + (uint64_t)t, live, d, c);
+            const uint32_t tt = g.tt(), dl = g.dealer(), ca = (g.PA >> 11) & 3u;
+            const bool r1 = tt >= 3u;
+            const uint32_t xrow = r1 ? 3u + ((((ca * 3u + g.pub()) * 2u + dl) << 2) | ((g.sq0() >> 1) - 1u)) : ca;
+            const uint32_t yrow = (r1 ? 93u : 75u) + dl * 9u + g.sq();
+            float v0, v1, v2;
+            mlp_forward_tables(sw, xrow, yrow, g.p() * 2u + (uint32_t)d.pol, rot, v0, v1, v2);
+            if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; }
+            fast_finish<kDebug>(g, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
+            if ((t & 15) == 15) c.spill();
         }
-        if (live) A.state[i] = g.w;
+        if (live) A.state[i] = g.pack();
+        c.wide.trans += live ? A.n_steps : 0;
     }
-    if (A.stats) c.commit(s_stats, A.stats);
+    c.spill();
+    if (A.stats) c.wide.commit(s_stats, A.stats);
 }
 
 }  // namespace nfsp
@@ -283,7 +313,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         h->step += (uint64_t)n_steps;
         return NFSP_OK;
     }
-    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 3);
+    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 1);
     if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     NFSP_LAUNCH_CHECK();
