@@ -123,8 +123,7 @@ __device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st,
     Layer2Acc acc;
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-        const float4 a = xr[q], b = yr[q];
-        acc.quad(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w, wr[q], wr[kRowQuads + q], wr[2 * kRowQuads + q]);
+        acc.quad_sum(xr[q], yr[q], wr[q], wr[kRowQuads + q], wr[2 * kRowQuads + q]);
     }
     acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1u, o0, o1, o2);
 }
@@ -195,7 +194,7 @@ rollout_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) float sw[];  // table image, kTabImageBytes
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint8_t s_deal[120];
+    __shared__ uint32_t s_deal[kDealLutWords];
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
     fill_deal_lut(s_deal);
     const uint32_t bar = smem_u32(&s_bar);
@@ -217,8 +216,15 @@ rollout_kernel(const RolloutArgs A) {
     FastCounters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const uint32_t lane = threadIdx.x & 31u;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < A.n; base += stride) {
+    // blocks of 32 consecutive games are handed out dynamically: one atomic per warp and block keeps the 148 x 24
+    // warps busy to the end (a static split of 2^15 blocks over 3552 warps leaves 8% of the last pass idle)
+    const int64_t n_blocks = (A.n + 31) >> 5;
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(A.work, 1u);
+        blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+        if ((int64_t)blk >= n_blocks) break;
+        const int64_t base = (int64_t)blk << 5;
         const int64_t i = base + lane;
         const bool live = i < A.n;
         const uint64_t game = A.game0 + (uint64_t)i;
@@ -258,6 +264,7 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     if (!h->d_wpack) {
         NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats)));
+        NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
     }
@@ -303,6 +310,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack + kPackFloats;
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
     A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.n_seg = (uint32_t)io->n_segments; A.counts = io->d_counts;
+    A.work = h->d_work;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
     NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 2, "variant must be 0 (default), 1 (CUDA cores) or 2 (tcgen05)");
@@ -313,6 +321,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         h->step += (uint64_t)n_steps;
         return NFSP_OK;
     }
+    NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), (cudaStream_t)stream));
     const int grid = grid_for(h->n, kRollThreads, h->sm_count, 1);
     if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);

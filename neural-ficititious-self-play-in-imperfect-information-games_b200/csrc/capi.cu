@@ -63,6 +63,7 @@ extern "C" int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64
     h->step = 0;
     h->d_state = nullptr;
     h->d_wpack = nullptr;
+    h->d_work = nullptr;
     h->d_wtc = nullptr;
     h->d_wtc_wide = nullptr;
     h->has_weights = false;
@@ -87,6 +88,7 @@ extern "C" int nfsp_env_destroy(nfsp_env_t h) {
     DeviceGuard guard(h->device);
     if (h->d_state) cudaFree(h->d_state);
     if (h->d_wpack) cudaFree(h->d_wpack);
+    if (h->d_work) cudaFree(h->d_work);
     if (h->d_wtc) cudaFree(h->d_wtc);
     if (h->d_wtc_wide) cudaFree(h->d_wtc_wide);
     delete h;

@@ -14,6 +14,9 @@ __device__ __forceinline__ unsigned long long pack2(float a, float b) {
 __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long x, unsigned long long y) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x), "l"(y));
 }
+__device__ __forceinline__ void unpack2(unsigned long long a, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
 __device__ __forceinline__ float hsum2(unsigned long long a) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
@@ -31,6 +34,19 @@ struct Layer2Acc {
         fma2(z0, hxy, pack2(u0.x, u0.y)); fma2(z0, hzw, pack2(u0.z, u0.w));
         fma2(z1, hxy, pack2(u1.x, u1.y)); fma2(z1, hzw, pack2(u1.z, u1.w));
         fma2(z2, hxy, pack2(u2.x, u2.y)); fma2(z2, hzw, pack2(u2.z, u2.w));
+    }
+
+    // same with the pre-activations given as the sum of two table rows (packed adds: x * 1 + y)
+    __device__ __forceinline__ void quad_sum(const float4 &x, const float4 &y, const float4 &u0, const float4 &u1,
+                                             const float4 &u2) {
+        const unsigned long long one = pack2(1.f, 1.f);
+        unsigned long long sxy = pack2(y.x, y.y), szw = pack2(y.z, y.w);
+        fma2(sxy, pack2(x.x, x.y), one);
+        fma2(szw, pack2(x.z, x.w), one);
+        float a, b, c, d;
+        unpack2(sxy, a, b);
+        unpack2(szw, c, d);
+        quad(a, b, c, d, u0, u1, u2);
     }
 
     // + b2, then relu head (best response, agent.py:103) or softmax head (average policy, agent.py:112)

@@ -21,7 +21,7 @@ namespace nfsp {
 
 // per-player word P
 //   0-3  bets in half chips      4 policy ('b' = 1)      5-6 last raw action     7 acted with a non-zero vector
-//   8-10 time of the last step() call (7 = never)        11-12 card rank
+//   8-10 time of the last step() call (7 = never)        11-12 card rank       13-14 public card rank (copy)
 //   24-26 one-hot private card (obs bits 24-26)          27-29 private | public one-hot (obs bits 27-29, shown in round 1)
 constexpr uint32_t kPBets = 0xFu, kPPol = 1u << 4, kPNz = 1u << 7;
 constexpr uint32_t kRound0Cards = 0x07000000u, kRound1Cards = 0x3F000000u;
@@ -37,9 +37,20 @@ __device__ __forceinline__ uint32_t seq_id6(uint32_t rnd) {  // 6 slot bits of o
     return s2 ? 6u + s0 : (s1 ? 2u * s0 + s1 : s0);
 }
 
-// deal index 0..119 -> c0 | c1<<2 | pub<<4 (deck.py:35-50); 120-entry byte table in shared memory
-__device__ __forceinline__ void fill_deal_lut(uint8_t *lut) {
-    for (uint32_t i = threadIdx.x; i < 120u; i += blockDim.x) lut[i] = (uint8_t)deal_ranks(i);
+// Deal table in shared memory: deal index 0..119 (deck.py:35-50: uniform ordered draw of 3 of 6 cards) ->
+// the card part of both players' P words, lut[idx] for player 0 and lut[120 + idx] for player 1:
+//   7 << 8 (never acted) | card << 11 | public card << 13 | one-hot rows (bits 24-29)
+constexpr int kDealLutWords = 240;
+__device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub) {
+    const uint32_t row0 = 1u << c;
+    return (7u << 8) | (c << 11) | (pub << 13) | (row0 << 24) | ((row0 | (1u << pub)) << 27);
+}
+__device__ __forceinline__ void fill_deal_lut(uint32_t *lut) {
+    for (uint32_t i = threadIdx.x; i < 120u; i += blockDim.x) {
+        const uint32_t c = deal_ranks(i);
+        lut[i] = deal_word(c & 3u, (c >> 4) & 3u);
+        lut[120u + i] = deal_word((c >> 2) & 3u, (c >> 4) & 3u);
+    }
 }
 
 struct NfspFast {
@@ -92,18 +103,15 @@ struct NfspFast {
     }
 
     // newenv.py:76-114 + main.py:28-45: the other player deals, fresh cards, per-hand policy draws.
-    // cards = c0 | c1<<2 | pub<<4
-    __device__ __forceinline__ void redeal(uint32_t cards, uint32_t pol0, uint32_t pol1) {
+    // q0 / q1 = deal-table words of players 0 / 1
+    __device__ __forceinline__ void redeal(uint32_t q0, uint32_t q1, uint32_t pol0, uint32_t pol1) {
         const uint32_t d = dealer() ^ 1u;  // the dealer opens: it is the player to act
-        const uint32_t c0 = cards & 3u, c1 = (cards >> 2) & 3u, pb = (cards >> 4) & 3u;
-        const uint32_t ca = d ? c1 : c0, co = d ? c0 : c1, pa = d ? pol1 : pol0, po = d ? pol0 : pol1;
-        const uint32_t pbit = 1u << pb, ra = 1u << ca, ro = 1u << co;
-        PA = 1u | (pa << 4) | (7u << 8) | (ca << 11) | (ra << 24) | ((ra | pbit) << 27);  // small blind 0.5
-        PO = 2u | (po << 4) | (7u << 8) | (co << 11) | (ro << 24) | ((ro | pbit) << 27);  // big blind 1.0
+        PA = (d ? q1 : q0) | 1u | ((d ? pol1 : pol0) << 4);  // small blind 0.5
+        PO = (d ? q0 : q1) | 2u | ((d ? pol0 : pol1) << 4);  // big blind 1.0
         H = 0u;
         SA = 0u;
         SO = 0u;
-        F = (d << 3) | (d << 4) | (pb << 5);
+        F = d * 0x18u | (((q0 >> 13) & 3u) << 5);
         cmask = kRound0Cards;
     }
 
@@ -152,6 +160,14 @@ struct NfspFast {
         const uint32_t a = PA, b = SA;
         PA = PO; PO = a;
         SA = SO; SO = b;
+    }
+
+    // 12-byte trace record, word 3 (layout: DESIGN.md "trace record"), same value as NfspW::trace_misc
+    __device__ __forceinline__ uint32_t trace_misc(int raw, int eff, bool started) const {
+        const uint32_t q = p(), P0 = q ? PO : PA, P1 = q ? PA : PO, r = tt() >= 3u ? 1u : 0u;
+        return (uint32_t)raw | ((uint32_t)eff << 2) | (r << 4) | (dealer() << 5) | (((P0 >> 11) & 3u) << 6) |
+               (((P1 >> 11) & 3u) << 8) | (pub() << 10) | (r << 12) | ((P0 & 15u) << 13) | ((P1 & 15u) << 17) |
+               ((uint32_t)started << 21) | (((P0 >> 4) & 1u) << 22) | (((P1 >> 4) & 1u) << 23);
     }
 
     // rewards in half chips of the actor / the opponent of the terminating step (newenv.py:250-298)

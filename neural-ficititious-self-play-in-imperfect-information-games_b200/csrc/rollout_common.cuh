@@ -30,6 +30,7 @@ struct RolloutArgs {
     int64_t cap_rl, cap_sl;  // per segment
     uint32_t n_seg;          // power of two
     uint32_t *counts;        // [4][n_seg]: rl0, rl1, sl0, sl1
+    uint32_t *work;          // next block of 32 games to hand out (zeroed before the launch)
     unsigned long long *stats;
     uint32_t *trace;
     float *vec;

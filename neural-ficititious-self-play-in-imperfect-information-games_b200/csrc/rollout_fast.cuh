@@ -54,12 +54,13 @@ struct FastDecision {
     float r0, r1, r2;  // the random score vector, valid iff random
 };
 
-__device__ __forceinline__ void fast_begin(NfspFast &g, const uint8_t *deal_lut, const RolloutArgs &A, uint64_t game,
+__device__ __forceinline__ void fast_begin(NfspFast &g, const uint32_t *deal_lut, const RolloutArgs &A, uint64_t game,
                                            uint64_t step, bool live, FastDecision &d, FastCounters &c) {
     const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
     d.started = false;
     if (g.need_reset()) {
-        g.redeal(deal_lut[__umulhi(x.y, 120u)], x.z < A.eta_u32, x.w < A.eta_u32);
+        const uint32_t idx = __umulhi(x.y, 120u);
+        g.redeal(deal_lut[idx], deal_lut[120u + idx], x.z < A.eta_u32, x.w < A.eta_u32);
         d.started = true;
         c.wide.hands += live;
     }
@@ -109,10 +110,9 @@ __device__ __forceinline__ void fast_finish(NfspFast &g, const RolloutArgs &A, c
         recC = make_uint4(g.SO, g.obs_o(), __float_as_uint(0.5f * (float)ro), ((g.PO >> 5) & 3u) | (1u << 8) | ((q ^ 1u) << 16));
     }
     if (kDebug && live && A.trace) {
-        const NfspW w{g.pack()};
         A.trace[at] = (g.terminated() ? g.obs_a() : (q == g.p() ? g.obs_a() : g.obs_o())) | ((uint32_t)g.terminated() << 30) | (q << 31);
         A.trace[plane + at] = __float_as_uint(0.5f * (float)ra);
-        A.trace[2 * plane + at] = w.trace_misc(a, eff, d.started);
+        A.trace[2 * plane + at] = g.trace_misc(a, eff, d.started);
     }
     // ---- append: byte counters rl0 | rl1 << 8 | sl0 << 16 | sl1 << 24, one warp scan, four atomics per warp
     const bool vA = d.vA && live, vS = d.pol && live;
