@@ -50,8 +50,8 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
 //     X  0-2    round 0: private card c (+ b1)
 //        3-74   round 1: 3 + ((c*3 + pub)*2 + dealer)*4 + f, f = finished round-0 sequence CC, RC, CRC, RRC
 //               = card rows + public card + round-0 history bits (+ b1)
-//     Y  75-92  round 0: 75 + dealer*9 + sequence id so far (0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC)
-//        93-110 round 1: 93 + dealer*9 + sequence id so far
+//     Y  75-110 75 + dealer*18 + sigma, sigma = 9*round + sequence id so far in that round
+//               (0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC)
 // Shared-memory layout: a row is 24 float4 "quads": the 16 quads of the 64 hidden units followed by a copy of
 // the first 8, so a thread can read its row starting at quad rot = game & 7 with immediate offsets.  The 8
 // threads of a quarter-warp then hit 8 different 16-byte bank groups whatever rows they gather: the row
@@ -93,10 +93,8 @@ __global__ void pack_tables_kernel(const float *__restrict__ w, float *__restric
                 const int fin[4] = {3, 5, 7, 8};
                 bits = (1u << (24 + c)) | (1u << (27 + c)) | (1u << (27 + pub)) | seq_bits(0, d, fin[f]);
                 bias = true;
-            } else if (r < 93) {
-                bits = seq_bits(0, (r - 75) / 9, (r - 75) % 9);
             } else {
-                bits = seq_bits(1, (r - 93) / 9, (r - 93) % 9);
+                bits = seq_bits(((r - 75) % 18) / 9, (r - 75) / 18, (r - 75) % 9);
             }
             for (int i = 0; i < 30; ++i)
                 if ((bits >> i) & 1u) v += W1[i * 64 + j];
@@ -194,9 +192,9 @@ rollout_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) float sw[];  // table image, kTabImageBytes
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_deal[kDealLutWords];
+    __shared__ FastLuts s_lut;
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
-    fill_deal_lut(s_deal);
+    s_lut.fill();
     const uint32_t bar = smem_u32(&s_bar);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -235,15 +233,14 @@ rollout_kernel(const RolloutArgs A) {
         g.unpack(live ? A.state[i] : 0ull);
         for (int t = 0; t < A.n_steps; ++t) {
             FastDecision d;
-            fast_begin(g, s_deal, A, game, A.step0 + (uint64_t)t, live, d, c);
-            const uint32_t tt = g.tt(), dl = g.dealer(), ca = (g.PA >> 11) & 3u;
-            const bool r1 = tt >= 3u;
-            const uint32_t xrow = r1 ? 3u + ((((ca * 3u + g.pub()) * 2u + dl) << 2) | ((g.sq0() >> 1) - 1u)) : ca;
-            const uint32_t yrow = (r1 ? 93u : 75u) + dl * 9u + g.sq();
+            fast_begin(g, s_lut, A, game, A.step0 + (uint64_t)t, live, d, c);
+            const uint32_t sg = g.sigma(), dl = g.dealer(), ca = (g.PA >> 11) & 3u;
+            const uint32_t xrow = sg >= 9u ? 3u + ((((ca * 3u + g.pub()) * 2u + dl) << 2) | g.fin0()) : ca;
+            const uint32_t yrow = 75u + dl * 18u + sg;
             float v0, v1, v2;
             mlp_forward_tables(sw, xrow, yrow, g.p() * 2u + (uint32_t)d.pol, rot, v0, v1, v2);
             if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; }
-            fast_finish<kDebug>(g, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
+            fast_finish<kDebug>(g, s_lut, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
             if ((t & 15) == 15) c.spill();
         }
         if (live) A.state[i] = g.pack();
@@ -306,6 +303,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     RolloutArgs A;
+    A.keys = philox_keys(h->seed);
     A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
     A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack + kPackFloats;
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }

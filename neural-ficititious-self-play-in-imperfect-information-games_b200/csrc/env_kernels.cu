@@ -87,10 +87,10 @@ nfsp_step_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64_
 // word once per launch and the 12-byte trace record per transition.  Bit-identical to nfsp_step_kernel.
 template <bool kTrace>
 __global__ void __launch_bounds__(kThreads)
-nfsp_step_fast_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64_t game0, uint64_t step0, int n_steps,
+nfsp_step_fast_kernel(uint64_t *__restrict__ state, int64_t n, const PhiloxKeys keys, uint64_t game0, uint64_t step0, int n_steps,
                       uint32_t eta_u32, uint32_t *__restrict__ trace) {
-    __shared__ uint32_t s_deal[kDealLutWords];
-    fill_deal_lut(s_deal);
+    __shared__ FastLuts s_lut;
+    s_lut.fill();
     __syncthreads();
     const int64_t plane = (int64_t)n_steps * n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -98,16 +98,16 @@ nfsp_step_fast_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, ui
         NfspFast g;
         g.unpack(state[i]);
         for (int t = 0; t < n_steps; ++t) {
-            const Philox4 x = game_block(seed, game, step0 + (uint64_t)t, STREAM_STEP);
+            const Philox4 x = game_block(keys, game, step0 + (uint64_t)t, STREAM_STEP);
             bool started = false;
             if (g.need_reset()) {
                 const uint32_t idx = __umulhi(x.y, 120u);
-                g.redeal(s_deal[idx], s_deal[120u + idx], x.z < eta_u32, x.w < eta_u32);
+                g.redeal(s_lut.deal[idx], s_lut.deal[120u + idx], x.z < eta_u32, x.w < eta_u32);
                 started = true;
             }
             const uint32_t q = g.p();
             const int raw = (int)__umulhi(x.x, 3u);
-            const int eff = g.step(raw, true);
+            const int eff = g.step(s_lut.step, raw, true);
             if (kTrace) {
                 const int64_t at = (int64_t)t * n + i;
                 int ra = 0, ro = 0;
@@ -308,10 +308,10 @@ extern "C" int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t
     NFSP_CHECK_ARG(n_steps >= 1, "n_steps must be >= 1");
     if (!d_actions && !d_players && auto_reset) {  // the benchmark configuration has its own lean kernel
         if (d_trace)
-            nfsp_step_fast_kernel<true><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->seed, h->game0, h->step, n_steps,
+            nfsp_step_fast_kernel<true><<<grid, kThreads, 0, st>>>(h->d_state, h->n, philox_keys(h->seed), h->game0, h->step, n_steps,
                                                                    frac_u32(eta), d_trace);
         else
-            nfsp_step_fast_kernel<false><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->seed, h->game0, h->step, n_steps,
+            nfsp_step_fast_kernel<false><<<grid, kThreads, 0, st>>>(h->d_state, h->n, philox_keys(h->seed), h->game0, h->step, n_steps,
                                                                     frac_u32(eta), nullptr);
         NFSP_LAUNCH_CHECK();
         h->step += (uint64_t)n_steps;

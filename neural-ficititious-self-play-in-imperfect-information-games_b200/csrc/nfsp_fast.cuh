@@ -5,14 +5,15 @@
 //
 //   * per-player fields live in two words PA (the player to act) / PO (the other one) that SWAP when the turn
 //     passes, so no field is ever addressed with a variable shift;
-//   * the slot index tt = 3*round + k is kept directly (history bit = 12*player + 2*tt + raise, newenv.py:53);
-//   * the betting sequence of the current round is kept as a sequence id sq (0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC,
-//     6 RR, 7 CRC, 8 RRC): the raise->call coercions (newenv.py:141-145), "previous action was a raise"
-//     (newenv.py:157,169) and "round over" (newenv.py:180-190) are comparisons on sq;
+//   * the betting state is one number sigma = 9*round + sequence id of the current round (0 -, 1 C, 2 R, 3 CC,
+//     4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC), and newenv.Env.do_action / game_or_round_has_terminated
+//     (newenv.py:131-190: raise->call coercions, chips added, history bit, round over) are ONE lookup in a
+//     54-entry shared-memory table indexed by (sigma, raw action) -- the integer pipe is what bounds these
+//     kernels (ncu r01: alu pipe 75% busy), the load/store pipe is idle;
 //   * the snapshots s[p] (newenv.py:200-202) are explicit registers (the observation the player acted on).
 //
-// Semantics are those of NfspW::step / decide_begin / decide_finish; tests run the golden hands and seeded
-// rollouts through both.
+// Semantics are those of NfspW::step / decide_begin / decide_finish; the parity tests run the golden hands
+// and seeded rollouts through both.
 #pragma once
 #include "nfsp_rules.cuh"
 #include "philox.cuh"
@@ -28,17 +29,53 @@ constexpr uint32_t kRound0Cards = 0x07000000u, kRound1Cards = 0x3F000000u;
 
 // flag word F
 //   0-2 tt = 3*round + k (k up to 3 after a showdown)    3 dealer    4 player to act    5-6 public card rank
-//   7 need_reset    8-11 sq (current round)    12-15 sq0 (round 0; == sq while in round 0)
+//   7 need_reset    8-12 sigma    13-14 f = finished round-0 sequence (0 CC, 1 RC, 2 CRC, 3 RRC), set when round 1 starts
 //   16 terminated   17 actor of the terminating step     18-19 outcome   20 anomaly
-constexpr uint32_t kFNeedReset = 1u << 7, kFTerm = 1u << 16;
+constexpr uint32_t kFNeedReset = 1u << 7, kFTerm = 1u << 16, kFStepMask = 0x1F07u;
 
 __device__ __forceinline__ uint32_t seq_id6(uint32_t rnd) {  // 6 slot bits of one round -> sequence id 0..8
     const uint32_t s0 = rnd & 3u, s1 = (rnd >> 2) & 3u, s2 = (rnd >> 4) & 3u;
     return s2 ? 6u + s0 : (s1 ? 2u * s0 + s1 : s0);
 }
 
-// Deal table in shared memory: deal index 0..119 (deck.py:35-50: uniform ordered draw of 3 of 6 cards) ->
-// the card part of both players' P words, lut[idx] for player 0 and lut[120 + idx] for player 1:
+// ---- step table -------------------------------------------------------------------------------------
+// entry(sigma, raw):  0-1 effective action   2-4 half chips added   5 history bit valid (not a fold)
+//   6-9 history bit position 2*t + action - 1 within the actor's 12-bit block   10-11 kind: 0 the turn passes,
+//   1 round 0 over (public card, round 1), 2 showdown, 3 fold   12-14 t of this step
+//   16-31 the new tt / sigma / f fields in F's layout
+constexpr int kStepLutWords = 54;
+enum : uint32_t { KIND_PASS = 0, KIND_ROUND = 1, KIND_SHOWDOWN = 2, KIND_FOLD = 3 };
+
+__device__ __forceinline__ uint32_t step_entry(uint32_t sigma, uint32_t raw) {
+    const uint32_t r = sigma >= 9u ? 1u : 0u, s = sigma - 9u * r;
+    const uint32_t k = s == 0u ? 0u : (s < 3u ? 1u : 2u), t = 3u * r + k;
+    uint32_t av = raw;
+    if (av == A_RAISE && s >= 3u) av = A_CALL;  // newenv.py:141-145: [C,R] and "already raised" both mean s in {4,6}
+    if (av == A_FOLD) return av | (KIND_FOLD << 10) | (t << 12) | ((t | (sigma << 8)) << 16);
+    const bool prev_raise = s != 0u && !(s & 1u);                                           // s in {2,4,6}
+    const uint32_t add = (av == A_RAISE ? 2u : 0u) + (prev_raise ? 2u : 0u) + (t == 0u ? 1u : 0u);  // newenv.py:157-176
+    const uint32_t sn = s < 3u ? 2u * s + av : 5u + (s >> 1);
+    const bool over = s >= 3u || (s != 0u && av == A_CALL);                                 // newenv.py:180-190
+    uint32_t kind, nf;
+    if (!over) {
+        kind = KIND_PASS;
+        nf = (t + 1u) | ((9u * r + sn) << 8);
+    } else if (r == 0u) {
+        kind = KIND_ROUND;  // newenv.py:215-242
+        nf = 3u | (9u << 8) | (((sn >> 1) - 1u) << 13);
+    } else {
+        kind = KIND_SHOWDOWN;  // newenv.py:261-298; k counts the last action too
+        nf = (t + 1u) | ((9u + sn) << 8);
+    }
+    return av | (add << 2) | (1u << 5) | ((2u * t + av - 1u) << 6) | (kind << 10) | (t << 12) | (nf << 16);
+}
+__device__ __forceinline__ void fill_step_lut(uint32_t *lut) {
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kStepLutWords; i += blockDim.x) lut[i] = step_entry(i / 3u, i % 3u);
+}
+
+// ---- deal table -------------------------------------------------------------------------------------
+// deal index 0..119 (deck.py:35-50: uniform ordered draw of 3 of 6 cards) -> the card part of both players'
+// P words, lut[idx] for player 0 and lut[120 + idx] for player 1:
 //   7 << 8 (never acted) | card << 11 | public card << 13 | one-hot rows (bits 24-29)
 constexpr int kDealLutWords = 240;
 __device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub) {
@@ -53,6 +90,16 @@ __device__ __forceinline__ void fill_deal_lut(uint32_t *lut) {
     }
 }
 
+// both tables, one shared array per CTA
+struct FastLuts {
+    uint32_t step[kStepLutWords];
+    uint32_t deal[kDealLutWords];
+    __device__ __forceinline__ void fill() {
+        fill_step_lut(step);
+        fill_deal_lut(deal);
+    }
+};
+
 struct NfspFast {
     uint32_t H, F, PA, PO, SA, SO, cmask;
 
@@ -61,8 +108,8 @@ struct NfspFast {
     __device__ __forceinline__ uint32_t p() const { return (F >> 4) & 1u; }
     __device__ __forceinline__ uint32_t pub() const { return (F >> 5) & 3u; }
     __device__ __forceinline__ bool need_reset() const { return F & kFNeedReset; }
-    __device__ __forceinline__ uint32_t sq() const { return (F >> 8) & 15u; }
-    __device__ __forceinline__ uint32_t sq0() const { return (F >> 12) & 15u; }
+    __device__ __forceinline__ uint32_t sigma() const { return (F >> 8) & 31u; }
+    __device__ __forceinline__ uint32_t fin0() const { return (F >> 13) & 3u; }
     __device__ __forceinline__ bool terminated() const { return F & kFTerm; }
     __device__ __forceinline__ uint32_t obs_a() const { return H | (PA & cmask); }
     __device__ __forceinline__ uint32_t obs_o() const { return H | (PO & cmask); }
@@ -70,7 +117,7 @@ struct NfspFast {
     __device__ __forceinline__ static uint32_t make_p(const NfspW &g, int q) {
         const uint32_t c = g.card(q), row0 = 1u << c, row1 = row0 | (1u << g.pub());
         return g.bets(q) | (g.policy(q) << 4) | (g.last_a(q) << 5) | ((uint32_t)g.acted_nz(q) << 7) | (g.t_snap(q) << 8) |
-               (c << 11) | (row0 << 24) | (row1 << 27);
+               (c << 11) | (g.pub() << 13) | (row0 << 24) | (row1 << 27);
     }
 
     __device__ __forceinline__ void unpack(uint64_t w) {
@@ -80,8 +127,8 @@ struct NfspFast {
         const uint32_t id0 = seq_id6(both & 63u), id1 = seq_id6((both >> 6) & 63u);
         const uint32_t r = g.round(), q = (uint32_t)g.to_act();
         F = (3u * r + g.k()) | (g.dealer() << 3) | (q << 4) | (g.pub() << 5) | ((uint32_t)g.need_reset() << 7) |
-            ((r ? id1 : id0) << 8) | (id0 << 12) | ((uint32_t)g.terminated() << 16) | (g.term_actor() << 17) |
-            (g.outcome() << 18) | ((uint32_t)g.anomaly() << 20);
+            ((r ? 9u + id1 : id0) << 8) | ((r ? (id0 >> 1) - 1u : 0u) << 13) | ((uint32_t)g.terminated() << 16) |
+            (g.term_actor() << 17) | (g.outcome() << 18) | ((uint32_t)g.anomaly() << 20);
         PA = make_p(g, (int)q);
         PO = make_p(g, (int)(q ^ 1u));
         SA = g.snapshot((int)q);
@@ -118,48 +165,25 @@ struct NfspFast {
     // newenv.py:192-349 for the player to act.  raw = np.argmax(action), nz = (np.average(action) != 0).
     // Returns the effective action; on return the turn has passed (PA is the next player to act) unless the
     // hand terminated.  Sets need_reset with terminated (rollout mode, main.py:55-67 ends the hand).
-    __device__ __forceinline__ int step(int raw, bool nz) {
-        const uint32_t t = tt(), s = sq(), q = p();
+    __device__ __forceinline__ int step(const uint32_t *step_lut, int raw, bool nz) {
+        const uint32_t e = step_lut[sigma() * 3u + (uint32_t)raw];
+        const uint32_t q = p(), kind = (e >> 10) & 3u;
         SA = obs_a();
-        PA = (PA & ~0x7E0u) | ((uint32_t)raw << 5) | ((uint32_t)nz << 7) | (t << 8);
-        int av = raw;
-        if (av == A_RAISE && s >= 3u) av = A_CALL;  // newenv.py:141-145: [C,R] and "p already raised" both mean s in {4,6}
-        if (av == A_FOLD) {
-            F |= kFTerm | kFNeedReset | (q << 17);  // outcome 0
-            return av;
+        PA = ((PA & ~0x7E0u) | ((uint32_t)raw << 5) | ((uint32_t)nz << 7) | ((e >> 4) & 0x700u)) + ((e >> 2) & 7u);
+        H |= ((e >> 5) & 1u) << (12u * q + ((e >> 6) & 15u));
+        F = (F & ~kFStepMask) | (e >> 16);
+        if (kind == KIND_ROUND) cmask = kRound1Cards;
+        if (kind >= KIND_SHOWDOWN) {
+            const uint32_t cp = (PA >> 11) & 3u, co = (PO >> 11) & 3u, pb = pub();
+            const uint32_t oc = cp == pb ? 1u : (co == pb ? 2u : (cp < co ? 1u : (cp > co ? 2u : 3u)));
+            F |= kFTerm | kFNeedReset | (q << 17) | (kind == KIND_SHOWDOWN ? oc << 18 : 0u);
+        } else if (kind == KIND_PASS || q != dealer()) {  // round 1 opens with the dealer, otherwise players alternate
+            F ^= 1u << 4;
+            const uint32_t a = PA, b = SA;
+            PA = PO; PO = a;
+            SA = SO; SO = b;
         }
-        const bool prev_raise = s != 0u && !(s & 1u);                                          // s in {2,4,6}
-        PA += (av == A_RAISE ? 2u : 0u) + (prev_raise ? 2u : 0u) + (t == 0u ? 1u : 0u);        // newenv.py:157-176
-        H |= 1u << (12u * q + 2u * t + (uint32_t)av - 1u);
-        const uint32_t sn = s < 3u ? 2u * s + (uint32_t)av : 5u + (s >> 1);
-        const bool over = s >= 3u || (s != 0u && av == A_CALL);                                // newenv.py:180-190
-        if (!over) {  // same round, the turn passes
-            uint32_t f = ((F & ~0xF00u) + 1u) | (sn << 8);
-            if (t < 3u) f = (f & ~0xF000u) | (sn << 12);
-            F = f ^ (1u << 4);
-            swap_players();
-            return av;
-        }
-        if (t < 3u) {  // newenv.py:215-242: the public card is revealed, round 1 starts with the dealer
-            F = (F & ~0xFF07u) | 3u | (sn << 12);
-            cmask = kRound1Cards;
-            if (q != dealer()) {
-                F ^= 1u << 4;
-                swap_players();
-            }
-            return av;
-        }
-        // showdown, newenv.py:261-298
-        const uint32_t cp = (PA >> 11) & 3u, co = (PO >> 11) & 3u, pb = pub();
-        const uint32_t oc = cp == pb ? 1u : (co == pb ? 2u : (cp < co ? 1u : (cp > co ? 2u : 3u)));
-        F = (((F & ~0xF00u) + 1u) | (sn << 8)) | kFTerm | kFNeedReset | (q << 17) | (oc << 18);
-        return av;
-    }
-
-    __device__ __forceinline__ void swap_players() {
-        const uint32_t a = PA, b = SA;
-        PA = PO; PO = a;
-        SA = SO; SO = b;
+        return (int)(e & 3u);
     }
 
     // 12-byte trace record, word 3 (layout: DESIGN.md "trace record"), same value as NfspW::trace_misc

@@ -28,6 +28,36 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// The ten round keys (k0 + r*W0, k1 + r*W1) depend on the seed only: the hot kernels take them precomputed
+// as a by-value kernel argument, so each key is a constant-bank operand of the round's XOR instead of an add.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0;
+        K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return K;
+}
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &K) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ K.k[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+        c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 // purposes (counter word 3), DESIGN.md "Philox streams":
 //   STREAM_STEP   one block per (game, step): .x = uniform action (env-only) / epsilon test (NFSP),
 //                 .y = deal index, .z/.w = per-hand policy draws of players 0/1 (used iff the hand is re-dealt
@@ -38,6 +68,10 @@ enum : uint32_t { STREAM_STEP = 0, STREAM_VECTOR = 1, STREAM_RESERVOIR = 2, STRE
 __device__ __forceinline__ Philox4 game_block(uint64_t seed, uint64_t game, uint64_t step, uint32_t stream) {
     return philox4x32_10((uint32_t)game, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed,
                          (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ Philox4 game_block(const PhiloxKeys &K, uint64_t game, uint64_t step, uint32_t stream) {
+    return philox4x32_10((uint32_t)game, (uint32_t)step, (uint32_t)(step >> 32), stream, K);
 }
 
 __device__ __forceinline__ uint64_t buffer_u64(uint64_t seed, uint64_t idx, uint64_t call, uint32_t stream) {

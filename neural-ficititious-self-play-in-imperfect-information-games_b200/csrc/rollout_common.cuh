@@ -22,6 +22,7 @@ struct RolloutArgs {
     uint64_t *state;
     int64_t n;
     uint64_t seed, game0, step0;
+    PhiloxKeys keys;         // round keys of `seed` (constant-bank operands of the lean kernels)
     int n_steps;
     uint32_t eta_u32, eps_u32;
     const void *pack;  // weight image of the variant

@@ -54,13 +54,13 @@ struct FastDecision {
     float r0, r1, r2;  // the random score vector, valid iff random
 };
 
-__device__ __forceinline__ void fast_begin(NfspFast &g, const uint32_t *deal_lut, const RolloutArgs &A, uint64_t game,
+__device__ __forceinline__ void fast_begin(NfspFast &g, const FastLuts &L, const RolloutArgs &A, uint64_t game,
                                            uint64_t step, bool live, FastDecision &d, FastCounters &c) {
-    const Philox4 x = game_block(A.seed, game, step, STREAM_STEP);
+    const Philox4 x = game_block(A.keys, game, step, STREAM_STEP);
     d.started = false;
     if (g.need_reset()) {
         const uint32_t idx = __umulhi(x.y, 120u);
-        g.redeal(deal_lut[idx], deal_lut[120u + idx], x.z < A.eta_u32, x.w < A.eta_u32);
+        g.redeal(L.deal[idx], L.deal[120u + idx], x.z < A.eta_u32, x.w < A.eta_u32);
         d.started = true;
         c.wide.hands += live;
     }
@@ -71,7 +71,7 @@ __device__ __forceinline__ void fast_begin(NfspFast &g, const uint32_t *deal_lut
     d.pol = (g.PA & kPPol) != 0u;
     d.random = d.pol && x.x < A.eps_u32;
     if (d.random) {  // np.random.rand(1,1,3): rare, so it has its own Philox block
-        const Philox4 y = game_block(A.seed, game, step, STREAM_VECTOR);
+        const Philox4 y = game_block(A.keys, game, step, STREAM_VECTOR);
         d.r0 = (float)(y.x >> 8) * (1.0f / 16777216.0f);
         d.r1 = (float)(y.y >> 8) * (1.0f / 16777216.0f);
         d.r2 = (float)(y.z >> 8) * (1.0f / 16777216.0f);
@@ -81,7 +81,7 @@ __device__ __forceinline__ void fast_begin(NfspFast &g, const uint32_t *deal_lut
 // agent.py:142-156 after the forward + main.py:55-67 terminal observations + the warp-aggregated append.
 // All lanes of the warp call it; `live` masks everything a phantom lane could emit.
 template <bool kDebug>
-__device__ __forceinline__ void fast_finish(NfspFast &g, const RolloutArgs &A, const WarpStage &W, const FastDecision &d,
+__device__ __forceinline__ void fast_finish(NfspFast &g, const FastLuts &L, const RolloutArgs &A, const WarpStage &W, const FastDecision &d,
                                             float v0, float v1, float v2, bool live, int64_t at, int64_t plane,
                                             FastCounters &c) {
     if (kDebug && live) {
@@ -94,7 +94,7 @@ __device__ __forceinline__ void fast_finish(NfspFast &g, const RolloutArgs &A, c
     if (v1 > best) { a = 1; best = v1; }
     if (v2 > best) a = 2;
     const bool nz = (v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f);
-    const int eff = g.step(a, nz);
+    const int eff = g.step(L.step, a, nz);
     c.small += live ? 1u << (5u * (3u * q + (uint32_t)a)) : 0u;
     bool vB = false, vC = false;
     uint4 recB, recC;
