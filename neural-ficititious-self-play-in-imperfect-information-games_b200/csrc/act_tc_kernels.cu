@@ -15,7 +15,7 @@
 
 #include "mlp_math.cuh"
 #include "ptx_helpers.cuh"
-#include "rollout_common.cuh"
+#include "rollout_fast.cuh"
 
 namespace nfsp {
 
@@ -227,17 +227,18 @@ act_forward_tc_kernel(const uint8_t *__restrict__ img, const uint32_t *__restric
 }
 
 // ---- fused rollout, tcgen05 first layer ---------------------------------------------------------------
-// Shape chosen from profiles/r01/umma_microbench.txt (B200): a tcgen05.mma costs ~78 cycles whatever N <= 128
-// and 128 cycles at N = 256, plus ~450 cycles issue->commit latency per chain, so the tile that minimises
+// Shape chosen from profiles/r01/umma_microbench.txt (B200): a tcgen05.mma costs ~90 cycles whatever N <= 128
+// and ~150 cycles at N = 256, plus ~450 cycles issue->commit latency per chain, so the tile that minimises
 // tensor time is the WIDE one: D[128 rows][256 = 4 nets x 64 hidden] = A[128][32] x B[256][32]^T, 2 k-steps
 // x 3 bf16 splits = 6 MMAs per 128 decisions.  A row needs only its own net's 64 columns, so the rows of a
 // tile are SORTED BY NET (counting sort over the group's 128 threads) before they are written as operand rows:
-// warps then read one 64-column block of TMEM (two at a segment boundary).
+// warps then read one 64-column block of TMEM (two at a segment boundary) and their W2 reads are warp-uniform.
 //
-// One persistent CTA per SM, kGroups groups of 128 threads.  A group = 128 games; thread t owns game t
-// (state in registers over the launch's steps) and is the epilogue worker of sorted row t.  The 512 TMEM
-// columns are two accumulator slots that the groups of equal parity use in turn: the issuer of a group waits
-// for the hand-off mbarrier of its predecessor in the ring, the last barrier of the epilogue passes it on.
+// One persistent CTA per SM, kGroups groups of 128 threads.  A group takes tiles of 128 consecutive games from a
+// global counter; thread t owns game t of the tile (actor-relative state in registers over the launch's steps,
+// nfsp_fast.cuh) and is the epilogue worker of sorted row t.  The 512 TMEM columns are two accumulator slots;
+// a group uses slot (group & 1) under a shared-memory lock taken by its MMA issuer and released by the last
+// of its four warps to finish reading the accumulator.
 constexpr int kGroups = 6;
 constexpr int kRtcThreads = 128 * kGroups;
 constexpr int kWideABytes = 128 * 32 * 2;          // 8 KB operand tile per group
@@ -246,13 +247,17 @@ constexpr int kWideBBytes = 3 * kWideBSplitBytes;  // 48 KB
 constexpr int kWideImageBytes = kWideBBytes + kTcW2Floats * 4;
 constexpr uint32_t kWideSBO = 512;                 // 4 k-chunks of 128 B per 8-row group
 constexpr uint32_t kIdescWide = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-// dynamic smem: A tiles | weight image | results float4[kGroups][128] | owner u8[kGroups][128] | counts | barriers
+// dynamic smem: A tiles | weight image | results float4[kGroups][128] | byte -> 8 x bf16 table | owner u8[kGroups][128]
+//               | counts | tile ids | barriers | slot locks
 constexpr int kRtcOffImage = kGroups * kWideABytes;
 constexpr int kRtcOffResult = kRtcOffImage + kWideImageBytes;
-constexpr int kRtcOffOwner = kRtcOffResult + kGroups * 128 * 16;
+constexpr int kRtcOffBits = kRtcOffResult + kGroups * 128 * 16;
+constexpr int kRtcOffOwner = kRtcOffBits + 256 * 16;
 constexpr int kRtcOffCnt = kRtcOffOwner + kGroups * 128;
-constexpr int kRtcOffBars = kRtcOffCnt + kGroups * 4 * 4;
-constexpr int kRtcSmemBytes = kRtcOffBars + 8 * (1 + 2 * kGroups) + 16;
+constexpr int kRtcOffTile = kRtcOffCnt + kGroups * 4 * 4;
+constexpr int kRtcOffBars = kRtcOffTile + kGroups * 4 + 8;
+constexpr int kRtcOffLocks = kRtcOffBars + 8 * (1 + kGroups);
+constexpr int kRtcSmemBytes = kRtcOffLocks + 4 * 4 + 16;
 
 __global__ void pack_tc_wide_kernel(const float *__restrict__ w, uint8_t *__restrict__ img) {
     const int total = 3 * 256 * 32;
@@ -322,29 +327,34 @@ __global__ void __launch_bounds__(kRtcThreads, 1)
 rollout_tc_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
+    __shared__ FastLuts s_lut;
     const uint32_t group = threadIdx.x >> 7, gtid = threadIdx.x & 127u, wq = gtid >> 5, lane = gtid & 31u;
     uint8_t *sA = smem + group * kWideABytes;
     uint8_t *sB = smem + kRtcOffImage;
     const float *sW2 = reinterpret_cast<const float *>(sB + kWideBBytes);
     float4 *sResult = reinterpret_cast<float4 *>(smem + kRtcOffResult) + group * 128;
+    const uint4 *sBits = reinterpret_cast<const uint4 *>(smem + kRtcOffBits);
     uint8_t *sOwner = smem + kRtcOffOwner + group * 128;
     uint32_t *sCnt = reinterpret_cast<uint32_t *>(smem + kRtcOffCnt) + group * 4;
+    volatile uint32_t *sTile = reinterpret_cast<volatile uint32_t *>(smem + kRtcOffTile) + group;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRtcOffBars);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * kGroups);
-    const uint32_t bar_w = smem_u32(bars), bar_done = smem_u32(bars + 1 + group), bar_hand = smem_u32(bars + 1 + kGroups + group);
-    const uint32_t bar_next = smem_u32(bars + 1 + kGroups + (group + 2) % kGroups);
+    uint32_t *locks = reinterpret_cast<uint32_t *>(smem + kRtcOffLocks);  // [0..1] slot busy, [2..3] warps done reading
+    uint32_t *tmem_slot = locks + 4;
+    const uint32_t bar_w = smem_u32(bars), bar_done = smem_u32(bars + 1 + group);
+    uint32_t *slot_busy = locks + (group & 1u), *slot_readers = locks + 2 + (group & 1u);
 
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
+    s_lut.fill();
+    for (uint32_t e = threadIdx.x; e < 256u; e += blockDim.x) reinterpret_cast<uint4 *>(smem + kRtcOffBits)[e] = bits_to_bf16x8(e);
+    if (threadIdx.x < 4) locks[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 1 + 2 * kGroups; ++k) mbar_init(smem_u32(bars + k), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < 1 + kGroups; ++k) mbar_init(smem_u32(bars + k), 1);
+        fence_mbar_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(bar_w, kWideImageBytes);
         bulk_g2s(smem_u32(sB), A.pack, kWideImageBytes, bar_w);
-        mbar_arrive(smem_u32(bars + 1 + kGroups + 0));  // the first user of each accumulator slot starts with the baton
-        mbar_arrive(smem_u32(bars + 1 + kGroups + 1));
     }
     if (threadIdx.x < 32) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
@@ -355,23 +365,26 @@ rollout_tc_kernel(const RolloutArgs A) {
     const uint32_t a_smem = smem_u32(sA), b_smem = smem_u32(sB);
     mbar_wait(bar_w, 0);
 
-    uint32_t ph_done = 0, ph_hand = 0;
-    Counters c;
+    uint32_t ph_done = 0;
+    FastCounters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
-    const int64_t tiles = (A.n + 127) / 128;
-    const int64_t per_round = (int64_t)gridDim.x * kGroups;
-    const int64_t rounds = (tiles + per_round - 1) / per_round;  // every group runs the same number of rounds
-    for (int64_t rd = 0; rd < rounds; ++rd) {
-        const int64_t tile = (rd * gridDim.x + blockIdx.x) * kGroups + group;
+    const int64_t tiles = (A.n + 127) >> 7;
+    for (;;) {
+        if (gtid == 0) *sTile = atomicAdd(A.work, 1u);  // tiles of 128 games are handed out dynamically
+        group_bar(1 + group);
+        const int64_t tile = (int64_t)*sTile;
+        if (tile >= tiles) break;
         const int64_t i = tile * 128 + gtid;
-        const bool live = tile < tiles && i < A.n;
+        const bool live = i < A.n;
         const uint64_t game = A.game0 + (uint64_t)i;
-        const uint32_t seg = (uint32_t)((tile * 4 + wq) & (int64_t)(A.n_seg - 1u));  // = (first game of the warp / 32) % n_seg
-        NfspW g{live ? A.state[i] : 0ull};
+        WarpStage W;
+        W.init(A, (uint32_t)((tile * 4 + wq) & (int64_t)(A.n_seg - 1u)));  // = (first game of the warp / 32) % n_seg
+        NfspFast g;
+        g.unpack(live ? A.state[i] : 0ull);
         for (int s = 0; s < A.n_steps; ++s) {
-            Decision d;
-            if (live) decide_begin(g, A, game, A.step0 + (uint64_t)s, d, c);
-            const uint32_t net = live ? (uint32_t)(d.p * 2) + d.pol : 0u;
+            FastDecision d;
+            fast_begin(g, s_lut, A, game, A.step0 + (uint64_t)s, live, d, c);
+            const uint32_t net = g.p() * 2u + (uint32_t)d.pol;
             // ---- counting sort of the group's rows by net: packed byte counters, one word per warp.  Sort key
             // order avg0, br0, br1, avg1 keeps the two small best-response segments adjacent, so fewer warps
             // straddle a segment boundary.
@@ -383,23 +396,22 @@ rollout_tc_kernel(const RolloutArgs A) {
             if (lane == 0) sCnt[wq] = __popc(m0) | (__popc(m1) << 8) | (__popc(m2) << 16) | (__popc(m3) << 24);
             group_bar(1 + group);
             const uint32_t c0 = sCnt[0], c1 = sCnt[1], c2 = sCnt[2], c3 = sCnt[3];
-            const uint32_t tot = c0 + c1 + c2 + c3;  // bytes: rows of net 0..3 (<= 128 each, no carry)
+            const uint32_t tot = c0 + c1 + c2 + c3;  // bytes: rows of key 0..3 (<= 128 each, no carry)
             const uint32_t before = (wq > 0 ? c0 : 0u) + (wq > 1 ? c1 : 0u) + (wq > 2 ? c2 : 0u);
             const uint32_t seg1 = tot & 0xFFu, seg2 = seg1 + ((tot >> 8) & 0xFFu), seg3 = seg2 + ((tot >> 16) & 0xFFu);
             const uint32_t seg_start = key == 0 ? 0u : (key == 1 ? seg1 : (key == 2 ? seg2 : seg3));
             const uint32_t pos = seg_start + ((before >> (8 * key)) & 0xFFu) + rank;
-            {  // operand row `pos`: observation bits + the constant 1 that carries b1
+            {  // operand row `pos`: observation bits + the constant 1 that carries b1, 8 inputs per table lookup
                 uint8_t *row = sA + (pos >> 3) * kWideSBO + (pos & 7u) * 16;
                 const uint32_t x = (d.obs & 0x3FFFFFFFu) | (1u << 30);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4 *>(row + k * kLBO) = bits_to_bf16x8((x >> (8 * k)) & 0xFFu);
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4 *>(row + k * kLBO) = sBits[(x >> (8 * k)) & 0xFFu];
                 sOwner[pos] = (uint8_t)gtid;
             }
             fence_async_smem();
-            tc_fence_before();
             group_bar(1 + group);
             if (gtid == 0) {
-                mbar_wait(bar_hand, ph_hand);  // the accumulator slot is ours
+                while (atomicCAS(slot_busy, 0u, 1u) != 0u) __nanosleep(32);  // the accumulator slot is ours
                 tc_fence_after();
 #pragma unroll
                 for (int split = 0; split < 3; ++split)
@@ -409,10 +421,8 @@ rollout_tc_kernel(const RolloutArgs A) {
                                       umma_desc_wide(b_smem + split * kWideBSplitBytes + ks * 2 * kLBO), (split | ks) != 0);
                 umma_commit(bar_done);
             }
-            ph_hand ^= 1u;
-            if (wq == 0) mbar_wait_backoff(bar_done, ph_done);  // one warp polls the mbarrier, the others sleep on the barrier
+            mbar_wait_backoff(bar_done, ph_done);
             ph_done ^= 1u;
-            group_bar(1 + group);
             tc_fence_after();
             // ---- epilogue of sorted row `gtid`: its net's 64 pre-activations -> layer 2 -> head
             const uint32_t r = gtid;
@@ -441,6 +451,15 @@ rollout_tc_kernel(const RolloutArgs A) {
                         }
                     }
                 }
+                if (ch == 3) {  // the warp has its last accumulator columns in registers: the 4th warp frees the slot
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0 && atomicAdd(slot_readers, 1u) == 3u) {
+                        *reinterpret_cast<volatile uint32_t *>(slot_readers) = 0u;
+                        __threadfence_block();
+                        atomicExch(slot_busy, 0u);
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     acc.quad(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3], w2[(ch * 4 + q) * 12],
@@ -449,18 +468,19 @@ rollout_tc_kernel(const RolloutArgs A) {
             float o0, o1, o2;
             acc.head(reinterpret_cast<const float4 *>(sW2 + 16 * 4 * 3 * 4)[my_net], my_net & 1u, o0, o1, o2);
             sResult[sOwner[r]] = make_float4(o0, o1, o2, 0.f);
-            tc_fence_before();
-            group_bar(1 + group);                 // all TMEM reads of the slot are done; results are visible
-            if (gtid == 0) mbar_arrive(bar_next);  // pass the accumulator slot on
+            group_bar(1 + group);  // results are visible; A tile, owner map and counters may be rewritten
             float4 v = sResult[gtid];
-            if (d.random) { v.x = d.v0; v.y = d.v1; v.z = d.v2; }
-            decide_finish<kDebug>(g, A, d, v.x, v.y, v.z, live, (int64_t)s * A.n + i, plane, seg, c, s_stats);
+            if (d.random) { v.x = d.r0; v.y = d.r1; v.z = d.r2; }
+            fast_finish<kDebug>(g, s_lut, A, W, d, v.x, v.y, v.z, live, (int64_t)s * A.n + i, plane, c);
+            if ((s & 15) == 15) c.spill();
         }
-        if (live) A.state[i] = g.w;
+        if (live) A.state[i] = g.pack();
+        c.wide.trans += live ? A.n_steps : 0;
     }
+    c.spill();
     tc_fence_before();
     __syncthreads();
-    if (A.stats) c.commit(s_stats, A.stats);
+    if (A.stats) c.wide.commit(s_stats, A.stats);
     if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
@@ -488,6 +508,7 @@ extern "C" int nfsp_act_forward_tc(nfsp_env_t h, const uint32_t *d_obs, const in
 int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A0, bool debug, cudaStream_t st) {
     RolloutArgs A = A0;
     A.pack = h->d_wtc_wide;
+    NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), st));
     const int64_t ctas = (A.n + kRtcThreads - 1) / kRtcThreads;
     const int grid = (int)(ctas < h->sm_count ? ctas : h->sm_count);
     if (debug) rollout_tc_kernel<true><<<grid, kRtcThreads, kRtcSmemBytes, st>>>(A);
