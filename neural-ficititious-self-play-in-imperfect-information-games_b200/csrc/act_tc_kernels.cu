@@ -367,6 +367,14 @@ rollout_tc_kernel(const RolloutArgs A) {
 
     uint32_t ph_done = 0;
     FastCounters c;
+#ifdef NFSP_TC_TIMING
+    long long tm_lock = 0, tm_mma = 0, tm_epi = 0, tm_fin = 0, tm_beg = 0, tm_sort = 0; long long t0, t1;
+#define TC_T0() t0 = clock64()
+#define TC_T1(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+#else
+#define TC_T0()
+#define TC_T1(acc)
+#endif
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const int64_t tiles = (A.n + 127) >> 7;
     for (;;) {
@@ -383,7 +391,9 @@ rollout_tc_kernel(const RolloutArgs A) {
         g.unpack(live ? A.state[i] : 0ull);
         for (int s = 0; s < A.n_steps; ++s) {
             FastDecision d;
+            TC_T0();
             fast_begin(g, s_lut, A, game, A.step0 + (uint64_t)s, live, d, c);
+            TC_T1(tm_beg);
             const uint32_t net = g.p() * 2u + (uint32_t)d.pol;
             // ---- counting sort of the group's rows by net: packed byte counters, one word per warp.  Sort key
             // order avg0, br0, br1, avg1 keeps the two small best-response segments adjacent, so fewer warps
@@ -410,9 +420,11 @@ rollout_tc_kernel(const RolloutArgs A) {
             }
             fence_async_smem();
             group_bar(1 + group);
+            TC_T1(tm_sort);
             if (gtid == 0) {
                 while (atomicCAS(slot_busy, 0u, 1u) != 0u) __nanosleep(32);  // the accumulator slot is ours
                 tc_fence_after();
+                TC_T1(tm_lock);
 #pragma unroll
                 for (int split = 0; split < 3; ++split)
 #pragma unroll
@@ -421,9 +433,10 @@ rollout_tc_kernel(const RolloutArgs A) {
                                       umma_desc_wide(b_smem + split * kWideBSplitBytes + ks * 2 * kLBO), (split | ks) != 0);
                 umma_commit(bar_done);
             }
-            mbar_wait_backoff(bar_done, ph_done);
-            ph_done ^= 1u;
+            mbar_wait_backoff(bar_done, ph_done);  // every thread waits on the mbarrier itself (measured faster than one
+            ph_done ^= 1u;                         // polling warp + a group barrier: 0.67 vs 0.70 ms per launch)
             tc_fence_after();
+            TC_T1(tm_mma);
             // ---- epilogue of sorted row `gtid`: its net's 64 pre-activations -> layer 2 -> head
             const uint32_t r = gtid;
             const uint32_t my_key = (r >= seg1) + (r >= seg2) + (r >= seg3);
@@ -470,13 +483,22 @@ rollout_tc_kernel(const RolloutArgs A) {
             sResult[sOwner[r]] = make_float4(o0, o1, o2, 0.f);
             group_bar(1 + group);  // results are visible; A tile, owner map and counters may be rewritten
             float4 v = sResult[gtid];
+            TC_T1(tm_epi);
             if (d.random) { v.x = d.r0; v.y = d.r1; v.z = d.r2; }
             fast_finish<kDebug>(g, s_lut, A, W, d, v.x, v.y, v.z, live, (int64_t)s * A.n + i, plane, c);
             if ((s & 15) == 15) c.spill();
+            TC_T1(tm_fin);
         }
         if (live) A.state[i] = g.pack();
         c.wide.trans += live ? A.n_steps : 0;
     }
+#ifdef NFSP_TC_TIMING
+    if (gtid == 0 && A.stats) {  // per-phase cycles of the group leaders, summed over groups and CTAs
+        atomicAdd(A.stats + 13, (unsigned long long)(tm_beg + tm_sort));
+        atomicAdd(A.stats + 14, (unsigned long long)(tm_lock) | ((unsigned long long)tm_mma << 32));
+        atomicAdd(A.stats + 15, (unsigned long long)(tm_epi) | ((unsigned long long)tm_fin << 32));
+    }
+#endif
     c.spill();
     tc_fence_before();
     __syncthreads();
