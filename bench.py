@@ -207,6 +207,7 @@ def run_gpu(args):
                             sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
+    stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,11 +230,9 @@ def run_gpu(args):
             sp.rollout(T_PER_CALL, insert=False)
             b.record()
             sp.flush()
-            if e2e:
-                outs = []
-                for p in range(2):
-                    outs += list(sp.rl[p].sample(BATCH)[:5]) + list(sp.sl[p].sample(BATCH)[:2])
-                host = [o.cpu() for o in outs] + [sp.stats.cpu()]
+            if e2e:  # the learner's four minibatches and the counters come back to the host: one slab, one copy each
+                sp.sample_minibatches(BATCH, to_host=True)
+                stats_host.copy_(sp.stats, non_blocking=True)
             c.record()
             c.synchronize()
             tot_ms += a.elapsed_time(c)
@@ -344,7 +343,7 @@ def run_gpu(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": 11 * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "extra": {"env_only": {"kernel": "nfsp_step_kernel", "transitions_per_sec": env_rate,
+            "extra": {"env_only": {"kernel": "nfsp_step_fast_kernel", "transitions_per_sec": env_rate,
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION},

@@ -443,6 +443,56 @@ class SelfPlay:
             self.rl[p].insert(self.stage_rl[p], self.counts[p], self.cap_rl)
             self.sl[p].insert(self.stage_sl[p], self.counts[2 + p], self.cap_sl)
 
+    def sample_minibatches(self, batch=256, to_host=False):
+        """sample_batch(batch) of all four memories (replay_buffer.py:46-59, ReservoirBuffer.py:33-43) into ONE
+        float32 slab: per player RL s[b,30] a[b,3] r[b] s2[b,30] t[b], then SL s[b,30] a[b,3].  Returns
+        (views, slab); with to_host=True the slab lands in a reused pinned host buffer with a single
+        device->host copy (the views then alias the host copy; the caller synchronises the stream)."""
+        b = int(batch)
+        per = b * (65 + 33)
+        key = ("slab", b)
+        cache = self.__dict__.setdefault("_mb_cache", {})
+        if key not in cache:
+            cache[key] = (torch.empty(2 * per, dtype=torch.float32, device=self.device),
+                          torch.empty(2 * per, dtype=torch.float32).pin_memory(),
+                          torch.empty((4, b), dtype=torch.int64, device=self.device),
+                          torch.zeros(4, dtype=torch.int32, device=self.device))
+        slab, host, idx, cnt = cache[key]
+        st = _stream(self.device)
+
+        def cut(base, n, shape):
+            return base + n, (base, n, shape)
+
+        layout = []
+        for p in range(2):
+            o = p * per
+            spec = {}
+            for name, cols in (("s", 30), ("a", 3), ("r", 0), ("s2", 30), ("t", 0)):
+                n = b * max(cols, 1)
+                spec[name] = (o, n, (b, cols) if cols else (b,))
+                o += n
+            for name, cols in (("sl_s", 30), ("sl_a", 3)):
+                n = b * cols
+                spec[name] = (o, n, (b, cols))
+                o += n
+            layout.append(spec)
+            ptr = lambda name: C.c_void_p(slab.data_ptr() + 4 * spec[name][0])  # noqa: E731
+            for k, mem in ((0, self.rl[p]), (1, self.sl[p])):
+                row = 2 * p + k
+                check(lib().nfsp_sample_indices(mem.seed, mem.sample_calls, _ptr(mem.total), mem.capacity, int(mem.is_ring),
+                                                b, C.c_void_p(idx[row].data_ptr()), C.c_void_p(cnt[row:].data_ptr()), st))
+                mem.sample_calls += 1
+            check(lib().nfsp_gather_rl(_ptr(self.rl[p].data), C.c_void_p(idx[2 * p].data_ptr()), b, ptr("s"), ptr("a"),
+                                       ptr("r"), ptr("s2"), ptr("t"), st))
+            check(lib().nfsp_gather_sl(_ptr(self.sl[p].data), C.c_void_p(idx[2 * p + 1].data_ptr()), b, ptr("sl_s"),
+                                       ptr("sl_a"), st))
+        src = slab
+        if to_host:
+            host.copy_(slab, non_blocking=True)
+            src = host
+        views = [{k: src[o:o + n].view(shape) for k, (o, n, shape) in spec.items()} for spec in layout]
+        return views, src
+
     def read_stats(self):
         v = self.stats.cpu().numpy()
         return {k: int(v[i]) for i, k in enumerate(self.STAT_NAMES)}

@@ -14,7 +14,7 @@
 namespace nfsp {
 
 constexpr int kActThreads = 128;   // act_forward_kernel (generic observation masks)
-constexpr int kRollThreads = 768;  // rollout_kernel: one CTA per SM
+constexpr int kRollThreads = 1024;  // rollout_kernel: one CTA per SM
 // packed weight image (floats): W1 rows as [16 col-quads][128 rows = net*32 + input][4], where input 30 is
 // the bias b1; then W2 as [64 hidden][4 nets][4 = 3 outputs + pad]; then b2 as [4 nets][4].
 constexpr int kW1Floats = 16 * 128 * 4;

@@ -301,6 +301,24 @@ def test_memories_after_rollout_match_sequential_oracle(nb):
     assert int(sp.counts.sum().item()) == 0
 
 
+def test_sample_minibatches_slab_equals_per_memory_samples(nb):
+    """The one-slab / one-copy minibatch path returns exactly what sample_batch of each memory returns."""
+    sp = nb.SelfPlay(4000, seed=11, eta=0.3, epsilon=0.1, rl_capacity=3000, sl_capacity=1500, max_steps_per_call=6)
+    sp.rollout(6)
+    calls = [(sp.rl[p].sample_calls, sp.sl[p].sample_calls) for p in range(2)]
+    views, slab = sp.sample_minibatches(64, to_host=True)
+    torch.cuda.synchronize()
+    assert not slab.is_cuda and slab.is_pinned()
+    for p in range(2):
+        sp.rl[p].sample_calls, sp.sl[p].sample_calls = calls[p]
+        s, a, r, s2, t, _, n = sp.rl[p].sample(64)
+        assert int(n.item()) == 64
+        for name, ref in (("s", s), ("a", a), ("r", r), ("s2", s2), ("t", t)):
+            assert torch.equal(views[p][name], ref.cpu()), name
+        s, a, _, n = sp.sl[p].sample(64)
+        assert torch.equal(views[p]["sl_s"], s.cpu()) and torch.equal(views[p]["sl_a"], a.cpu())
+
+
 def test_segmented_batches_match_dense_order(nb):
     """A batch staged in segments inserts exactly like the same records staged densely in segment order."""
     rng = np.random.RandomState(8)
