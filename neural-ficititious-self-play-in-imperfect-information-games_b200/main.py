@@ -1,0 +1,105 @@
+"""Drop-in for the reference's training driver (main.py:21-158), batched.
+
+    python -m nfsp_b200.main [--games N] [--episodes E] [--steps-per-call T] [--config ./config.ini]
+    python -m torch.distributed.run --nproc-per-node G -m nfsp_b200.main ...     # games sharded over G GPUs
+
+The reference plays one hand at a time: `train(env, player1, player2)` alternates the dealer, draws each
+player's per-hand policy with probability eta, lets the agents `play` until both have seen the terminal
+state, calls `update_strategy()` every 128 decisions of an agent and prints the action histogram and the
+exploitability proxy every 100 episodes (main.py:27-75, agent.py:153-154).  All of the per-hand control flow
+lives inside the fused rollout kernel here; this driver is the outer loop only:
+
+    repeat:  rollout(T) for every game  ->  records into M_RL / M_SL  ->  Learner.update()  ->  stats
+
+Same config.ini keys (config.ini:1-40, incl. MRLSize / MSLSize, which the reference defines but never
+reads), same seeds, same printed quantities.  `--human` is accepted and ignored, as in the reference
+(main.py:152-158).
+"""
+from __future__ import annotations
+
+import argparse
+import time
+
+import torch
+
+from . import sharding
+from .batched import SelfPlay
+from .config import load_config
+from .exploitability import exploitability
+from .learner import Learner
+
+
+def sampled_actions(stats, player):
+    """agent.Agent.sampled_actions (agent.py:196-204): share of fold / call / raise among `player`'s actions."""
+    a = [stats["a%d_%s" % (player, k)] for k in ("fold", "call", "raise")]
+    tot = max(sum(a), 1)
+    return [x / tot for x in a]
+
+
+def train(sp: SelfPlay, learner: Learner, episodes: int, steps_per_call: int = 8, report_every: int = 100,
+          world: int = 1, log=print, true_exploitability: bool = True):
+    """main.train (main.py:21-124).  Plays until `episodes` hands have finished over all games and ranks.
+    Returns the list of reported rows (the reference's `plotter`, main.py:75, plus what it prints)."""
+    rows, calls, t0 = [], 0, time.time()
+    while True:
+        sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
+        st = learner.update()                 # agent.py:153-154 -> 192-194 -> 209-264
+        calls += 1
+        if calls % report_every and calls != 1:
+            continue
+        tot = sharding.allreduce_stats(sp.stats).tolist()
+        stats = dict(zip(sp.STAT_NAMES, (int(v) for v in tot)))
+        row = {"calls": calls, "hands": stats["hands"], "transitions": stats["transitions"],
+               "exploitability_proxy": st.get("exploitability"),   # agent.py:234-238 summed over players, main.py:73
+               "actions": [sampled_actions(stats, p) for p in range(2)],
+               "transitions_per_sec": stats["transitions"] / max(time.time() - t0, 1e-9)}
+        if true_exploitability:
+            row["exploitability"] = exploitability(sp)  # exact best response to the average policies
+        rows.append(row)
+        log("================ Stats ==================")
+        for p in range(2):
+            f, c, r = row["actions"][p]
+            log("Player%d: fold %.3f call %.3f raise %.3f" % (p, f, c, r))
+        log("Exploitability: {}".format(row["exploitability_proxy"]))
+        if true_exploitability:
+            log("Exact exploitability of the average policies: %.4f chips/hand" % row["exploitability"]["value"])
+        log("hands %d  transitions %d  (%.3e transitions/s)" % (row["hands"], row["transitions"], row["transitions_per_sec"]))
+        if stats["hands"] >= episodes:
+            return rows
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="NFSP self-play on Leduc Hold'em, B200-native")
+    ap.add_argument("--human", action="store_true", help="accepted and ignored, as in the reference (main.py:152-158)")
+    ap.add_argument("--config", default="./config.ini")
+    ap.add_argument("--games", type=int, default=1 << 16, help="parallel games over all GPUs")
+    ap.add_argument("--episodes", type=int, default=None, help="hands to play (default: Common.Episodes)")
+    ap.add_argument("--steps-per-call", type=int, default=8)
+    ap.add_argument("--report-every", type=int, default=100)
+    ap.add_argument("--no-true-exploitability", action="store_true")
+    args = ap.parse_args(argv)
+    cfg = load_config(args.config)
+    rank, world, local = sharding.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    seed = cfg.getint("Utils", "Seed")              # main.py:132-133
+    game0, n = sharding.shard_games(args.games, rank, world)
+    sp = SelfPlay(n, seed=seed, game0=game0, device=dev, eta=cfg.getfloat("Agent", "Eta"),
+                  epsilon=cfg.getfloat("Agent", "Epsilon"), rl_capacity=cfg.getint("Agent", "MRLSize"),
+                  sl_capacity=cfg.getint("Agent", "MSLSize"), max_steps_per_call=args.steps_per_call)
+    learner = Learner(sp, cfg=cfg)
+    episodes = args.episodes if args.episodes is not None else cfg.getint("Common", "Episodes")
+    rows = train(sp, learner, episodes, args.steps_per_call, args.report_every, world,
+                 log=print if rank == 0 else (lambda *a, **k: None),
+                 true_exploitability=not args.no_true_exploitability)
+    if world > 1:
+        dist.destroy_process_group()
+    return rows
+
+
+if __name__ == "__main__":
+    main()
