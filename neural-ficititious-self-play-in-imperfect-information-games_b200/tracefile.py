@@ -17,7 +17,7 @@ shares one global `random` stream between deck, policies and buffers, SURVEY 8 a
 every hand that started and finished inside the window.  `check` replays the file through the GENERAL env
 kernel (explicit deck via set_hands, explicit action codes, no auto re-deal) and compares every transition
 word for word: the two kernels share no game logic beyond the packed word, so this is an independent
-end-to-end check that needs no oracle; the tests additionally replay the same file on the CPU oracle.
+end-to-end check that needs nothing but the GPU; the parity tests additionally replay the same file on the CPU.
 """
 from __future__ import annotations
 
