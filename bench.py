@@ -133,7 +133,7 @@ def run_reference(args):
     sample = "%d threads x %d games x %d decisions per step (oracle port of Agent.play + newenv + memories adds)" % (
         threads, gpt, T_PER_CALL)
     line = {"impl": "reference", "metric": "leduc_transitions_per_sec", "value": value, "unit": "transitions/s",
-            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(),
             "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port", "sample": sample},

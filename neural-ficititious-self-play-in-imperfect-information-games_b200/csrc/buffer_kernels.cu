@@ -139,7 +139,21 @@ sample_kernel(uint64_t seed, uint64_t call_idx, const uint64_t *__restrict__ tot
     for (int m = threadIdx.x; m < b; m += blockDim.x)
         draw[m] = mulhi64(buffer_u64(seed, (uint64_t)m, call_idx, STREAM_SAMPLE), lo + (uint64_t)m + 1u);
     __syncthreads();
-    if (threadIdx.x < 32) {
+    // Fast path: if the draws are pairwise distinct, "already taken" never fires and pick == draw (the memories
+    // hold millions of records, so this is the normal case); checked with b*b/2 parallel compares.  Otherwise
+    // the sequential scan below resolves the collisions exactly as Floyd's algorithm does.
+    __shared__ int s_collision;
+    if (threadIdx.x == 0) s_collision = 0;
+    __syncthreads();
+    for (int m = threadIdx.x; m < b; m += blockDim.x) {
+        const uint64_t t = draw[m];
+        bool dup = false;
+        for (int k = 0; k < m; ++k) dup |= (draw[k] == t);
+        if (dup) s_collision = 1;
+        pick[m] = t;
+    }
+    __syncthreads();
+    if (s_collision && threadIdx.x < 32) {
         for (int m = 0; m < b; ++m) {
             const uint64_t t = draw[m];
             bool dup = false;
