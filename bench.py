@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 GAMES_PER_GPU = 1 << 20
 T_PER_CALL = 8
+ENV_T_PER_CALL = 32  # env-only K1 beside the headline: transitions per game and launch (trace planes: 402 MB)
 ETA, EPS, SEED = 0.1, 0.06, 1234
 RL_CAP, SL_CAP = 1 << 25, 1 << 23  # records per player (16 B each): one step's records never wrap the ring
 BATCH = 256
@@ -277,11 +278,11 @@ def run_gpu(args):
     # env-only K1 (BASELINE configs[1]) beside it, same games count, trace planes written
     env = nfsp_b200.BatchedNfspEnv(n, seed=SEED, game0=game0, device=dev)
     env.reset()
-    tr = torch.empty((3, T_PER_CALL, n), dtype=torch.int32, device=dev)
+    tr = torch.empty((3, ENV_T_PER_CALL, n), dtype=torch.int32, device=dev)
     from nfsp_b200.batched import _ptr, _stream, check, lib
 
     def env_step():
-        check(lib().nfsp_env_step(env._h, None, None, T_PER_CALL, 1, ETA, _ptr(tr), _stream(dev)))
+        check(lib().nfsp_env_step(env._h, None, None, ENV_T_PER_CALL, 1, ETA, _ptr(tr), _stream(dev)))
 
     for _ in range(3):
         env_step()
@@ -294,7 +295,7 @@ def run_gpu(args):
         b.record()
         b.synchronize()
         env_ms += a.elapsed_time(b)
-    env_rate = n * T_PER_CALL * args.steps / (env_ms * 1e-3)
+    env_rate = n * ENV_T_PER_CALL * args.steps / (env_ms * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -346,7 +347,8 @@ def run_gpu(args):
             "extra": {"env_only": {"kernel": "nfsp_step_fast_kernel", "transitions_per_sec": env_rate,
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
-                                   "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION},
+                                   "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
+                                   "transitions_per_launch": n * ENV_T_PER_CALL},
                       "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
                                                                  "kernel_ms_per_launch": other_ms / args.steps},
                       "buffers": buffers,

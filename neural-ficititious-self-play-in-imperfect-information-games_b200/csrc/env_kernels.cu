@@ -97,25 +97,33 @@ nfsp_step_fast_kernel(uint64_t *__restrict__ state, int64_t n, const PhiloxKeys 
         const uint64_t game = game0 + (uint64_t)i;
         NfspFast g;
         g.unpack(state[i]);
+        // the slow-changing part of the trace record's word 3 is kept assembled: dealer, cards, policies, round and
+        // both players' bets change only at a re-deal / by the chips an action adds
+        uint32_t misc = g.trace_misc(0, 0, false);
         for (int t = 0; t < n_steps; ++t) {
             const Philox4 x = game_block(keys, game, step0 + (uint64_t)t, STREAM_STEP);
-            bool started = false;
+            uint32_t started = 0u;
             if (g.need_reset()) {
                 const uint32_t idx = __umulhi(x.y, 120u);
-                g.redeal(s_lut.deal[idx], s_lut.deal[120u + idx], x.z < eta_u32, x.w < eta_u32);
-                started = true;
+                const uint32_t pol0 = x.z < eta_u32, pol1 = x.w < eta_u32;
+                g.redeal(s_lut.deal[idx], s_lut.deal[120u + idx], pol0, pol1);
+                const uint32_t d = g.dealer();
+                misc = s_lut.deal[240u + idx] | (d << 5) | (pol0 << 22) | (pol1 << 23) | (d ? (2u << 13) | (1u << 17) : (1u << 13) | (2u << 17));
+                started = 1u << 21;
             }
             const uint32_t q = g.p();
-            const int raw = (int)__umulhi(x.x, 3u);
-            const int eff = g.step(s_lut.step, raw, true);
+            const uint32_t raw = __umulhi(x.x, 3u);
+            const uint32_t e = g.step(s_lut.step, (int)raw, true);
             if (kTrace) {
                 const int64_t at = (int64_t)t * n + i;
                 int ra = 0, ro = 0;
                 if (g.terminated()) g.rewards(ra, ro);
                 const uint32_t obs = (g.terminated() || q == g.p()) ? g.obs_a() : g.obs_o();
+                misc += ((e >> 2) & 7u) << (13u + 4u * q);
+                if (g.tt() >= 3u) misc |= 0x1010u;
                 trace[at] = obs | ((uint32_t)g.terminated() << 30) | (q << 31);
                 trace[plane + at] = __float_as_uint(0.5f * (float)ra);
-                trace[2 * plane + at] = g.trace_misc(raw, eff, started);
+                trace[2 * plane + at] = misc | raw | ((e & 3u) << 2) | started;
             }
         }
         state[i] = g.pack();

@@ -23,6 +23,7 @@ namespace nfsp {
 // per-player word P
 //   0-3  bets in half chips      4 policy ('b' = 1)      5-6 last raw action     7 acted with a non-zero vector
 //   8-10 time of the last step() call (7 = never)        11-12 card rank       13-14 public card rank (copy)
+//   15-16 who wins a showdown of this deal: 0 player 0, 1 player 1, 2 nobody, 3 the actor (newenv.py:261-298)
 //   24-26 one-hot private card (obs bits 24-26)          27-29 private | public one-hot (obs bits 27-29, shown in round 1)
 constexpr uint32_t kPBets = 0xFu, kPPol = 1u << 4, kPNz = 1u << 7;
 constexpr uint32_t kRound0Cards = 0x07000000u, kRound1Cards = 0x3F000000u;
@@ -77,16 +78,25 @@ __device__ __forceinline__ void fill_step_lut(uint32_t *lut) {
 // deal index 0..119 (deck.py:35-50: uniform ordered draw of 3 of 6 cards) -> the card part of both players'
 // P words, lut[idx] for player 0 and lut[120 + idx] for player 1:
 //   7 << 8 (never acted) | card << 11 | public card << 13 | one-hot rows (bits 24-29)
-constexpr int kDealLutWords = 240;
-__device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub) {
+constexpr int kDealLutWords = 360;  // + [240 + idx]: the cards as the trace record's word 3 holds them (c0<<6 | c1<<8 | pub<<10)
+__device__ __forceinline__ uint32_t showdown_winner(uint32_t c0, uint32_t c1, uint32_t pub) {
+    // newenv.py:261-298: the actor pairing the board wins, else the opponent pairing it, else the lower rank index
+    // (0 = Ace).  3 = both pair the board: the actor wins whoever it is (cannot be dealt from two cards per rank,
+    // but set_hands accepts it and the reference's order of tests decides)
+    if (c0 == pub && c1 == pub) return 3u;
+    return c0 == pub ? 0u : (c1 == pub ? 1u : (c0 < c1 ? 0u : (c0 > c1 ? 1u : 2u)));
+}
+__device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub, uint32_t winner) {
     const uint32_t row0 = 1u << c;
-    return (7u << 8) | (c << 11) | (pub << 13) | (row0 << 24) | ((row0 | (1u << pub)) << 27);
+    return (7u << 8) | (c << 11) | (pub << 13) | (winner << 15) | (row0 << 24) | ((row0 | (1u << pub)) << 27);
 }
 __device__ __forceinline__ void fill_deal_lut(uint32_t *lut) {
     for (uint32_t i = threadIdx.x; i < 120u; i += blockDim.x) {
         const uint32_t c = deal_ranks(i);
-        lut[i] = deal_word(c & 3u, (c >> 4) & 3u);
-        lut[120u + i] = deal_word((c >> 2) & 3u, (c >> 4) & 3u);
+        const uint32_t w = showdown_winner(c & 3u, (c >> 2) & 3u, (c >> 4) & 3u);
+        lut[i] = deal_word(c & 3u, (c >> 4) & 3u, w);
+        lut[120u + i] = deal_word((c >> 2) & 3u, (c >> 4) & 3u, w);
+        lut[240u + i] = ((c & 3u) << 6) | (((c >> 2) & 3u) << 8) | (((c >> 4) & 3u) << 10);
     }
 }
 
@@ -117,7 +127,7 @@ struct NfspFast {
     __device__ __forceinline__ static uint32_t make_p(const NfspW &g, int q) {
         const uint32_t c = g.card(q), row0 = 1u << c, row1 = row0 | (1u << g.pub());
         return g.bets(q) | (g.policy(q) << 4) | (g.last_a(q) << 5) | ((uint32_t)g.acted_nz(q) << 7) | (g.t_snap(q) << 8) |
-               (c << 11) | (g.pub() << 13) | (row0 << 24) | (row1 << 27);
+               (c << 11) | (g.pub() << 13) | (showdown_winner(g.card(0), g.card(1), g.pub()) << 15) | (row0 << 24) | (row1 << 27);
     }
 
     __device__ __forceinline__ void unpack(uint64_t w) {
@@ -163,9 +173,10 @@ struct NfspFast {
     }
 
     // newenv.py:192-349 for the player to act.  raw = np.argmax(action), nz = (np.average(action) != 0).
-    // Returns the effective action; on return the turn has passed (PA is the next player to act) unless the
-    // hand terminated.  Sets need_reset with terminated (rollout mode, main.py:55-67 ends the hand).
-    __device__ __forceinline__ int step(const uint32_t *step_lut, int raw, bool nz) {
+    // Returns the step-table entry (bits 0-1 the effective action, bits 2-4 the half chips added); on return the
+    // turn has passed (PA is the next player to act) unless the hand terminated.  Sets need_reset with terminated
+    // (rollout mode, main.py:55-67 ends the hand).
+    __device__ __forceinline__ uint32_t step(const uint32_t *step_lut, int raw, bool nz) {
         const uint32_t e = step_lut[sigma() * 3u + (uint32_t)raw];
         const uint32_t q = p(), kind = (e >> 10) & 3u;
         SA = obs_a();
@@ -174,8 +185,8 @@ struct NfspFast {
         F = (F & ~kFStepMask) | (e >> 16);
         if (kind == KIND_ROUND) cmask = kRound1Cards;
         if (kind >= KIND_SHOWDOWN) {
-            const uint32_t cp = (PA >> 11) & 3u, co = (PO >> 11) & 3u, pb = pub();
-            const uint32_t oc = cp == pb ? 1u : (co == pb ? 2u : (cp < co ? 1u : (cp > co ? 2u : 3u)));
+            const uint32_t win = (PA >> 15) & 3u;  // outcome: 1 the actor wins, 2 the opponent wins, 3 draw
+            const uint32_t oc = win == 2u ? 3u : ((win == q || win == 3u) ? 1u : 2u);
             F |= kFTerm | kFNeedReset | (q << 17) | (kind == KIND_SHOWDOWN ? oc << 18 : 0u);
         } else if (kind == KIND_PASS || q != dealer()) {  // round 1 opens with the dealer, otherwise players alternate
             F ^= 1u << 4;
@@ -183,7 +194,7 @@ struct NfspFast {
             PA = PO; PO = a;
             SA = SO; SO = b;
         }
-        return (int)(e & 3u);
+        return e;
     }
 
     // 12-byte trace record, word 3 (layout: DESIGN.md "trace record"), same value as NfspW::trace_misc

@@ -94,7 +94,7 @@ __device__ __forceinline__ void fast_finish(NfspFast &g, const FastLuts &L, cons
     if (v1 > best) { a = 1; best = v1; }
     if (v2 > best) a = 2;
     const bool nz = (v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f);
-    const int eff = g.step(L.step, a, nz);
+    const int eff = (int)(g.step(L.step, a, nz) & 3u);
     c.small += live ? 1u << (5u * (3u * q + (uint32_t)a)) : 0u;
     bool vB = false, vC = false;
     uint4 recB, recC;
