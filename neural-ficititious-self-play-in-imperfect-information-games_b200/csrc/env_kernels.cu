@@ -116,8 +116,7 @@ nfsp_step_fast_kernel(uint64_t *__restrict__ state, int64_t n, const PhiloxKeys 
             const uint32_t e = g.step(s_lut.step, (int)raw, true);
             if (kTrace) {
                 const int64_t at = (int64_t)t * n + i;
-                int ra = 0, ro = 0;
-                if (g.terminated()) g.rewards(ra, ro);
+                const int ra = g.reward_actor();
                 const uint32_t obs = (g.terminated() || q == g.p()) ? g.obs_a() : g.obs_o();
                 misc += ((e >> 2) & 7u) << (13u + 4u * q);
                 if (g.tt() >= 3u) misc |= 0x1010u;

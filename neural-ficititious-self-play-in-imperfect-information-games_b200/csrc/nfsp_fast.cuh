@@ -183,17 +183,18 @@ struct NfspFast {
         PA = ((PA & ~0x7E0u) | ((uint32_t)raw << 5) | ((uint32_t)nz << 7) | ((e >> 4) & 0x700u)) + ((e >> 2) & 7u);
         H |= ((e >> 5) & 1u) << (12u * q + ((e >> 6) & 15u));
         F = (F & ~kFStepMask) | (e >> 16);
-        if (kind == KIND_ROUND) cmask = kRound1Cards;
-        if (kind >= KIND_SHOWDOWN) {
-            const uint32_t win = (PA >> 15) & 3u;  // outcome: 1 the actor wins, 2 the opponent wins, 3 draw
-            const uint32_t oc = win == 2u ? 3u : ((win == q || win == 3u) ? 1u : 2u);
-            F |= kFTerm | kFNeedReset | (q << 17) | (kind == KIND_SHOWDOWN ? oc << 18 : 0u);
-        } else if (kind == KIND_PASS || q != dealer()) {  // round 1 opens with the dealer, otherwise players alternate
-            F ^= 1u << 4;
-            const uint32_t a = PA, b = SA;
-            PA = PO; PO = a;
-            SA = SO; SO = b;
-        }
+        // branch-free tail: a warp's 32 games are in different phases, so branches would run every side anyway
+        cmask = kind == KIND_ROUND ? kRound1Cards : cmask;
+        const bool term = kind >= KIND_SHOWDOWN;
+        const uint32_t win = (PA >> 15) & 3u;  // outcome: 1 the actor wins, 2 the opponent wins, 3 draw; 0 = fold
+        const uint32_t oc = kind != KIND_SHOWDOWN ? 0u : (win == 2u ? 3u : ((win == q || win == 3u) ? 1u : 2u));
+        F |= term ? (kFTerm | kFNeedReset | (q << 17) | (oc << 18)) : 0u;
+        // round 1 opens with the dealer, otherwise players alternate; nobody moves after the end of the hand
+        const bool pass = !term && (kind == KIND_PASS || q != dealer());
+        F ^= pass ? 1u << 4 : 0u;
+        const uint32_t a = PA, b = SA;
+        PA = pass ? PO : a; PO = pass ? a : PO;
+        SA = pass ? SO : b; SO = pass ? b : SO;
         return e;
     }
 
@@ -211,6 +212,13 @@ struct NfspFast {
         const uint32_t oc = (F >> 18) & 3u;
         ra = oc == 0u ? -ba : (oc == 1u ? bo : (oc == 2u ? -bo : 0));
         ro = oc == 0u ? ba : (oc == 1u ? -ba : (oc == 2u ? ba : 0));
+    }
+    // reward of the actor only, 0 while the hand is live (newenv.py:125-129); branch-free
+    __device__ __forceinline__ int reward_actor() const {
+        const int ba = (int)(PA & 15u), bo = (int)(PO & 15u);
+        const uint32_t oc = (F >> 18) & 3u;
+        const int mag = oc == 0u ? ba : bo, v = oc == 1u ? mag : -mag;
+        return (terminated() && oc != 3u) ? v : 0;
     }
 };
 
