@@ -278,6 +278,34 @@ def test_rollout_variants_agree_without_debug(nb):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("variant", ["cuda", "tcgen05"])
+@pytest.mark.parametrize("n", [1, 31, 129, 1000])
+def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
+    """One launch of 19 steps == 19 launches of one step (game words, counters, record multisets), for sizes that
+    leave phantom lanes in the last warp / tile; 19 > 16 also crosses the small-counter spill."""
+    steps = 19
+    res = []
+    for chunks in ([steps], [1] * steps, [7, 12]):
+        sp = nb.SelfPlay(n, seed=31, eta=0.25, epsilon=0.2, rl_capacity=1 << 12, sl_capacity=1 << 12,
+                         max_steps_per_call=steps, variant=variant)
+        rl = [[], []]
+        sl = [[], []]
+        for c in chunks:
+            sp.rollout(c, insert=False)
+            r, s_ = sp.staged()
+            for p in range(2):
+                rl[p].append(r[p])
+                sl[p].append(s_[p])
+            sp.counts.zero_()
+        res.append((sp.env.state_words().cpu().numpy(), sp.read_stats(),
+                    [canon(np.concatenate(x)) for x in rl], [canon(np.concatenate(x)) for x in sl]))
+    for other in res[1:]:
+        assert np.array_equal(res[0][0], other[0]) and res[0][1] == other[1]
+        for a, b in zip(res[0][2] + res[0][3], other[2] + other[3]):
+            assert np.array_equal(a, b)
+    assert res[0][1]["transitions"] == n * steps and res[0][1]["dropped"] == 0
+
+
 def test_memories_after_rollout_match_sequential_oracle(nb):
     """rollout -> flush: ring / reservoir contents equal the oracle fed with the staged records in ticket order."""
     n, steps, seed = 3000, 6, 8
