@@ -45,18 +45,44 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML every 2 ms, nvidia-smi
+    (one query per ~0.1 s) if NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons")
+                else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        bits = (0x8, 0x40, 0x20, 0x4)  # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        return [mhz, self.max_mhz] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self._nvml_row())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
@@ -70,10 +96,9 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return None
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(str(r[2 + i]).lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 def cpu_rollout_rate(threads, games_per_thread, t_steps, reps):
@@ -316,6 +341,20 @@ def run_gpu(args):
         if k >= 3:
             other_ms += a.elapsed_time(b)
     other_rate = n * T_PER_CALL * args.steps / (other_ms * 1e-3)
+    # BASELINE configs[2] as stated: 64k parallel games (latency-bound: 2 048 blocks of 32 games for 4 736 warps)
+    sp64 = nfsp_b200.SelfPlay(1 << 16, seed=SEED, device=dev, eta=ETA, epsilon=EPS, rl_capacity=200000,
+                              sl_capacity=2000000, max_steps_per_call=T_PER_CALL)
+    ms64 = 0.0
+    for k in range(3 + args.steps):
+        a, b = ev(), ev()
+        a.record()
+        sp64.rollout(T_PER_CALL)
+        b.record()
+        b.synchronize()
+        if k >= 3:
+            ms64 += a.elapsed_time(b)
+    rate64 = (1 << 16) * T_PER_CALL * args.steps / (ms64 * 1e-3)
+    del sp64
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
@@ -351,6 +390,8 @@ def run_gpu(args):
                                    "transitions_per_launch": n * ENV_T_PER_CALL},
                       "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
                                                                  "kernel_ms_per_launch": other_ms / args.steps},
+                      "rollout_64k_games": {"config": "BASELINE configs[2]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts",
+                                            "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps},
                       "buffers": buffers,
                       "learner": {"update_ms": learner_ms, "sgd_steps_per_update": 8, "allreduce_floats": 4 * 2179 + 8,
                                   "exploitability_proxy": lstats.get("exploitability"), "trained_mask": lstats.get("trained")},
