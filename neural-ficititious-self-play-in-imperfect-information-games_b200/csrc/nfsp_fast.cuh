@@ -12,8 +12,8 @@
 //     kernels (ncu r01: alu pipe 75% busy), the load/store pipe is idle;
 //   * the snapshots s[p] (newenv.py:200-202) are explicit registers (the observation the player acted on).
 //
-// Semantics are those of NfspW::step / decide_begin / decide_finish; the parity tests run the golden hands
-// and seeded rollouts through both.
+// Semantics are those of NfspW::step (nfsp_rules.cuh, the packed-word implementation the general env kernel
+// runs); the parity tests run the golden hands and seeded rollouts through both.
 #pragma once
 #include "nfsp_rules.cuh"
 #include "philox.cuh"

@@ -1,7 +1,8 @@
 // Lean decision logic of the fused rollout on the actor-relative register state of nfsp_fast.cuh:
 // everything of Agent.play (agent.py:130-156) and of main.train's inner loop (main.py:28-67) around the
-// network forward.  Same Philox words, same records, same counters as decide_begin/decide_finish in
-// rollout_common.cuh (which the tcgen05 variant still uses); the parity tests run both.
+// network forward, shared by both first-layer variants.  The rules it applies are those of NfspW::step
+// (nfsp_rules.cuh), which the general env kernel still runs on the packed word: two implementations of the same
+// game that the parity tests and `tracefile check` hold against each other.
 #pragma once
 #include "nfsp_fast.cuh"
 #include "rollout_common.cuh"
