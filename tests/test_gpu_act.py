@@ -306,6 +306,52 @@ def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
     assert res[0][1]["transitions"] == n * steps and res[0][1]["dropped"] == 0
 
 
+@pytest.mark.parametrize("variant", ["cuda", "tcgen05"])
+def test_staging_overflow_drops_and_never_writes_past_a_segment(nb, variant):
+    """compute-sanitizer is closed on this pool, so the bounds are checked by hand: staging segments far too small
+    for the rollout, canary words behind every segment.  Records that do not fit are counted as dropped, the
+    canaries survive, and everything that was staged is a record the full-size run staged too."""
+    import ctypes as C
+
+    from nfsp_b200 import _lib
+    from nfsp_b200.batched import check, lib, _stream
+
+    n, steps, seed, n_seg, cap, guard = 3000, 8, 5, 8, 40, 8
+    full = nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps,
+                       variant=variant)
+    full.rollout(steps, insert=False)
+    rl_full, sl_full = full.staged()
+    sp = nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps,
+                     variant=variant)
+    dev = sp.device
+    # the kernel addresses segment s at s * cap: a dense [n_seg * cap] array followed by one canary block; inside a
+    # segment every slot beyond the claimed count must keep the fill value as well
+    dense = [torch.full((n_seg * cap + guard, 4), -7, dtype=torch.int32, device=dev) for _ in range(4)]
+    counts = torch.zeros((4, n_seg), dtype=torch.int32, device=dev)
+    io = _lib.RolloutIO()
+    io.d_rl[0], io.d_rl[1], io.d_sl[0], io.d_sl[1] = (t.data_ptr() for t in dense)
+    io.cap_rl, io.cap_sl, io.n_segments = cap, cap, n_seg
+    io.d_counts, io.d_stats = counts.data_ptr(), sp.stats.data_ptr()
+    io.variant = sp.VARIANTS[variant]
+    check(lib().nfsp_rollout(sp.env._h, steps, sp.eta, sp.epsilon, C.byref(io), _stream(dev)))
+    torch.cuda.synchronize()
+    st = sp.read_stats()
+    cnt = counts.cpu().numpy()
+    assert st["dropped"] > 0 and st["dropped"] == int(np.maximum(cnt - cap, 0).sum())
+    for k, t in enumerate(dense):
+        a = t.cpu().numpy()
+        assert (a[n_seg * cap:] == -7).all(), "canary behind the last segment overwritten"
+        ref = canon(np.concatenate([rl_full[0], rl_full[1]]) if k < 2 else np.concatenate([sl_full[0], sl_full[1]]))
+        ref_set = set(map(bytes, ref.view(np.uint8).reshape(len(ref), 16)))
+        for s_ in range(n_seg):
+            kept = min(int(cnt[k, s_]), cap)
+            seg = a[s_ * cap:(s_ + 1) * cap]
+            assert (seg[kept:] == -7).all(), "slot beyond the claimed count written"
+            for row in seg[:kept]:
+                assert row.astype(np.int32).tobytes() in ref_set
+    assert np.array_equal(sp.env.state_words().cpu().numpy(), full.env.state_words().cpu().numpy())
+
+
 def test_memories_after_rollout_match_sequential_oracle(nb):
     """rollout -> flush: ring / reservoir contents equal the oracle fed with the staged records in ticket order."""
     n, steps, seed = 3000, 6, 8
