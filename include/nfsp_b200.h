@@ -81,7 +81,10 @@ int nfsp_env_set_hands(nfsp_env_t h, const int8_t *d_dealer, const int8_t *d_car
  *   d_players int8[n_steps][n] or NULL: NULL => main.train's turn order (main.py:55-65).
  *   auto_reset: re-deal a finished hand at its next step (dealer alternates, main.py:28-31).
  *   d_trace   uint32[3][n_steps][n] or NULL: planes obs|terminal<<30|player<<31, reward (float
- *             bits), misc (DESIGN.md "trace record"). */
+ *             bits), misc (DESIGN.md "trace record").
+ * With d_actions = d_players = NULL and auto_reset (the throughput configuration) the call runs the lean kernel
+ * (game in actor-relative registers, table-driven betting step); every other combination runs the general
+ * kernel on the packed word.  Both produce identical words and traces. */
 int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int n_steps, int auto_reset,
                   double eta, uint32_t *d_trace, void *stream);
 /* newenv.Env.get_state(p) (newenv.py:116-129), packed: player < 0 => per-game d_players.
@@ -144,8 +147,9 @@ typedef struct {
     uint32_t *d_trace;    /* as nfsp_env_step, or NULL                                          */
     float *d_vec;         /* float[n_steps][n][3] score vectors actually used, or NULL          */
     const float *d_forced_vec; /* float[n_steps][n][3] or NULL: use these instead of the nets   */
-    int32_t variant;      /* first layer on: 1 = CUDA cores (group-factorised row sums),
-                             2 = tensor cores (tcgen05.mma, TMEM accumulator), 0 = library default */
+    int32_t variant;      /* first layer on: 1 = CUDA cores (sum of two precombined weight rows, bank-conflict-free
+                             shared-memory gathers), 2 = tensor cores (tcgen05.mma, TMEM accumulator),
+                             0 = library default */
 } nfsp_rollout_io;
 #define NFSP_ROLLOUT_DEFAULT_VARIANT 1
 

@@ -77,11 +77,14 @@ class Learner:
         lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
         check(lib().nfsp_sgd_apply(_ptr(sp.weights), _ptr(self.flat), C.byref(lr), 1.0 / world, _stream(self.device)))
 
-    def update(self):
-        """update_strategy() of both agents.  Returns a dict of statistics (host floats)."""
+    def _ready_mask(self):
+        """agent.py:215,259: a net trains only once its memory holds more than a minibatch.  Memories never shrink,
+        so once all four are ready the (host-synchronising) size reads stop."""
+        if getattr(self, "_all_ready", False):
+            return 15
         sp = self.sp
         mask = 0
-        for p in range(2):  # agent.py:215,259: train only once the memory holds more than a minibatch
+        for p in range(2):
             if sp.sl[p].size() > self.minibatch:
                 mask |= 1 << (2 * p)
             if sp.rl[p].size() > self.minibatch:
@@ -90,6 +93,14 @@ class Learner:
             m = torch.tensor([(mask >> k) & 1 for k in range(4)], dtype=torch.int32, device=self.device)
             dist.all_reduce(m, op=dist.ReduceOp.MIN)
             mask = sum(int(v) << k for k, v in enumerate(m.tolist()))
+        self._all_ready = mask == 15
+        return mask
+
+    def update(self, sync=True):
+        """update_strategy() of both agents.  Returns a dict of statistics; with sync=False nothing is read back
+        from the device (the loss / exploitability-proxy entries are then the previous synchronised values)."""
+        sp = self.sp
+        mask = self._ready_mask()
         if mask == 0:
             return {"trained": 0}
         for p in range(2):
@@ -103,10 +114,13 @@ class Learner:
                 self._step(idx_rl, idx_sl, row0, min(self.fit_batch, self.minibatch - row0), mask)
                 if stats is None:                # exploitability proxy of the sampled batch, first pass
                     stats = self.flat[GRAD:].clone()
-        s = stats.cpu().tolist()
+        if sync:
+            self._loss = stats.cpu().tolist()
+        s = getattr(self, "_loss", [0.0] * N_STATS)
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:
-                self.exploitability[p] = s[p] / max(s[2 + p], 1.0)   # agent.py:234-238 (mean over ranks too)
+                if sync:
+                    self.exploitability[p] = s[p] / max(s[2 + p], 1.0)   # agent.py:234-238 (mean over ranks too)
                 self.iteration[p] += 1                               # agent.py:245
                 it = self.iteration[p]
                 self.temp[p] = (1 + 0.02 * math.sqrt(it)) ** (-1)    # agent.py:247

@@ -42,10 +42,11 @@ def train(sp: SelfPlay, learner: Learner, episodes: int, steps_per_call: int = 8
     Returns the list of reported rows (the reference's `plotter`, main.py:75, plus what it prints)."""
     rows, calls, t0 = [], 0, time.time()
     while True:
-        sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
-        st = learner.update()                 # agent.py:153-154 -> 192-194 -> 209-264
         calls += 1
-        if calls % report_every and calls != 1:
+        report = calls % report_every == 0 or calls == 1
+        sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
+        st = learner.update(sync=report)      # agent.py:153-154 -> 192-194 -> 209-264; host reads only when reporting
+        if not report:
             continue
         tot = sharding.allreduce_stats(sp.stats).tolist()
         stats = dict(zip(sp.STAT_NAMES, (int(v) for v in tot)))
