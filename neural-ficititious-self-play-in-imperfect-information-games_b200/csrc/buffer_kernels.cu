@@ -86,6 +86,11 @@ __device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket
     return j < cap ? (int64_t)j : -1;
 }
 
+// Both passes are random 8/16-byte accesses whose latency (not bandwidth) is the bound with one access in flight
+// per thread, so each thread handles kResUnroll records per iteration: the slot draws are independent and the
+// atomics / loads of an iteration are all issued before the first result is needed.
+constexpr int kResUnroll = 4;
+
 // pass 1: every accepted record stamps its slot with ticket+1; atomicMax keeps the latest
 __global__ void __launch_bounds__(kBufThreads)
 reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, const uint64_t *__restrict__ total_p,
@@ -96,10 +101,17 @@ reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, con
     const uint64_t total = *total_p;
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t ticket = total + before + i;
-        const int64_t slot = reservoir_slot(seed, ticket, cap, mode);
-        if (slot >= 0) atomicMax(stamp + slot, (unsigned long long)(ticket + 1u));
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kResUnroll) {
+        int64_t slot[kResUnroll];
+#pragma unroll
+        for (int u = 0; u < kResUnroll; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            slot[u] = i < cnt ? reservoir_slot(seed, total + before + i, cap, mode) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kResUnroll; ++u)
+            if (slot[u] >= 0) atomicMax(stamp + slot[u], (unsigned long long)(total + before + i0 + (uint64_t)u * stride + 1u));
     }
 }
 
@@ -114,10 +126,22 @@ reservoir_write_kernel(uint4 *__restrict__ res, const unsigned long long *__rest
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t ticket = total + before + i;
-        const int64_t slot = reservoir_slot(seed, ticket, cap, mode);
-        if (slot >= 0 && stamp[slot] == (unsigned long long)(ticket + 1u)) res[slot] = src[i];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kResUnroll) {
+        int64_t slot[kResUnroll];
+        unsigned long long owner[kResUnroll];
+#pragma unroll
+        for (int u = 0; u < kResUnroll; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            slot[u] = i < cnt ? reservoir_slot(seed, total + before + i, cap, mode) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kResUnroll; ++u) owner[u] = slot[u] >= 0 ? stamp[slot[u]] : 0ull;
+#pragma unroll
+        for (int u = 0; u < kResUnroll; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            if (slot[u] >= 0 && owner[u] == (unsigned long long)(total + before + i + 1u)) res[slot[u]] = src[i];
+        }
     }
 }
 
