@@ -15,10 +15,13 @@ namespace nfsp {
 
 constexpr int kActThreads = 128;   // act_forward_kernel (generic observation masks)
 constexpr int kRollThreads = 1024;  // rollout_kernel: one CTA per SM
-// packed weight image (floats): W1 rows as [16 col-quads][128 rows = net*32 + input][4], where input 30 is
-// the bias b1; then W2 as [64 hidden][4 nets][4 = 3 outputs + pad]; then b2 as [4 nets][4].
-constexpr int kW1Floats = 16 * 128 * 4;
-constexpr int kW2Floats = 64 * 4 * 4;
+// packed weight image (floats) of the generic forward: W1 rows as [128 rows = net*32 + input][24 quads][4], where
+// input 30 is the bias b1 and a row is its 16 quads of hidden units followed by a copy of the first 8 (so a thread can
+// read from quad rot = index & 7 with immediate offsets and the 8 threads of a quarter-warp never share a bank
+// group, see the rollout tables below); then W2 as [4 nets][3 outputs][24 quads][4]; then b2 as [4 nets][4].
+constexpr int kFwdRowQuads = 24;
+constexpr int kW1Floats = 128 * kFwdRowQuads * 4;
+constexpr int kW2Floats = 4 * 3 * kFwdRowQuads * 4;
 constexpr int kB2Floats = 4 * 4;
 constexpr int kPackFloats = kW1Floats + kW2Floats + kB2Floats;
 
@@ -26,14 +29,15 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats; e += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (e < kW1Floats) {
-            const int c = e & 3, row = (e >> 2) & 127, q = e >> 9;
-            const int net = row >> 5, i = row & 31, j = q * 4 + c;
+            const int c = e & 3, pos = (e >> 2) % kFwdRowQuads, row = (e >> 2) / kFwdRowQuads;
+            const int net = row >> 5, i = row & 31, j = (pos & 15) * 4 + c;
             const float *wn = w + net * NFSP_NET_PARAMS;
             if (i < 30) v = wn[i * 64 + j];
             else if (i == 30) v = wn[1920 + j];
         } else if (e < kW1Floats + kW2Floats) {
-            const int f = e - kW1Floats, c = f & 3, net = (f >> 2) & 3, j = f >> 4;
-            if (c < 3) v = w[net * NFSP_NET_PARAMS + 1984 + j * 3 + c];
+            const int f = e - kW1Floats, x = f & 3, pos = (f >> 2) % kFwdRowQuads, c = ((f >> 2) / kFwdRowQuads) % 3;
+            const int net = (f >> 2) / (3 * kFwdRowQuads);
+            v = w[net * NFSP_NET_PARAMS + 1984 + ((pos & 15) * 4 + x) * 3 + c];
         } else {
             const int f = e - kW1Floats - kW2Floats, c = f & 3, net = f >> 2;
             if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
@@ -126,42 +130,30 @@ __device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st,
     acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1u, o0, o1, o2);
 }
 
-// forward of one net on one observation mask; sw = packed image in shared memory
-__device__ __forceinline__ void mlp_forward(const float *__restrict__ sw, uint32_t obs, int net, float out[3]) {
-    const float4 *w1 = reinterpret_cast<const float4 *>(sw);
-    const int row0 = net * 32;
-    float h[64];
+// forward of one net on one observation mask; sw = packed image in shared memory.  The first layer is the sum of the
+// <= 10 weight rows of the set input bits (+ the bias row), accumulated in the thread's ROTATED quad order.
+__device__ __forceinline__ void mlp_forward(const float *__restrict__ sw, uint32_t obs, int net, uint32_t rot, float out[3]) {
+    const float4 *w1 = reinterpret_cast<const float4 *>(sw) + rot;
+    float4 h[16];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) h[j] = 0.f;
+    for (int q = 0; q < 16; ++q) h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t bits = (obs & 0x3FFFFFFFu) | (1u << 30);  // input 30 = constant 1 -> adds the bias row last
     while (bits) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1u;
-        const float4 *r = w1 + row0 + i;
+        const float4 *r = w1 + (net * 32 + i) * kFwdRowQuads;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const float4 v = r[q * 128];
-            h[4 * q + 0] += v.x; h[4 * q + 1] += v.y; h[4 * q + 2] += v.z; h[4 * q + 3] += v.w;
+            const float4 v = r[q];
+            h[q].x += v.x; h[q].y += v.y; h[q].z += v.z; h[q].w += v.w;
         }
     }
-    const float4 *w2 = reinterpret_cast<const float4 *>(sw + kW1Floats) + net;
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    const float4 *w2 = reinterpret_cast<const float4 *>(sw + kW1Floats) + net * (3 * kFwdRowQuads) + rot;
+    Layer2Acc acc;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        const float hj = fmaxf(h[j], 0.f);  // Dense(64, relu), agent.py:102,111
-        const float4 v = w2[j * 4];
-        z0 = fmaf(hj, v.x, z0); z1 = fmaf(hj, v.y, z1); z2 = fmaf(hj, v.z, z2);
-    }
-    const float4 b2 = reinterpret_cast<const float4 *>(sw + kW1Floats + kW2Floats)[net];
-    z0 += b2.x; z1 += b2.y; z2 += b2.z;
-    if (net & 1) {  // best-response net: Dense(3, relu), agent.py:103
-        out[0] = fmaxf(z0, 0.f); out[1] = fmaxf(z1, 0.f); out[2] = fmaxf(z2, 0.f);
-    } else {        // average-policy net: Dense(3, softmax), agent.py:112
-        const float m = fmaxf(z0, fmaxf(z1, z2));
-        const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
-        const float inv = 1.0f / (e0 + e1 + e2);
-        out[0] = e0 * inv; out[1] = e1 * inv; out[2] = e2 * inv;
-    }
+    for (int q = 0; q < 16; ++q)  // Dense(64, relu) then Dense(3), agent.py:102-103,111-112
+        acc.quad(h[q].x, h[q].y, h[q].z, h[q].w, w2[q], w2[kFwdRowQuads + q], w2[2 * kFwdRowQuads + q]);
+    acc.head(reinterpret_cast<const float4 *>(sw + kW1Floats + kW2Floats)[net], net & 1, out[0], out[1], out[2]);
 }
 
 __device__ __forceinline__ void load_pack(float *sw, const float *__restrict__ pack) {
@@ -174,11 +166,11 @@ __device__ __forceinline__ void load_pack(float *sw, const float *__restrict__ p
 __global__ void __launch_bounds__(kActThreads)
 act_forward_kernel(const float *__restrict__ pack, const uint32_t *__restrict__ obs, const int8_t *__restrict__ net,
                    int64_t n, float *__restrict__ out) {
-    __shared__ __align__(16) float sw[kPackFloats];
+    extern __shared__ __align__(16) float sw[];  // kPackFloats
     load_pack(sw, pack);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float v[3];
-        mlp_forward(sw, obs[i], (int)(net[i] & 3), v);
+        mlp_forward(sw, obs[i], (int)(net[i] & 3), (uint32_t)i & 7u, v);
         out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
     }
 }
@@ -262,6 +254,7 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     if (!h->d_wpack) {
         NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats)));
         NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
+        NFSP_CUDA(cudaFuncSetAttribute(act_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackFloats * sizeof(float))));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
     }
@@ -284,7 +277,7 @@ extern "C" int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     const int grid = grid_for(n, kActThreads, h->sm_count, 4);
-    act_forward_kernel<<<grid, kActThreads, 0, (cudaStream_t)stream>>>(h->d_wpack, d_obs, d_net, n, d_out);
+    act_forward_kernel<<<grid, kActThreads, kPackFloats * sizeof(float), (cudaStream_t)stream>>>(h->d_wpack, d_obs, d_net, n, d_out);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

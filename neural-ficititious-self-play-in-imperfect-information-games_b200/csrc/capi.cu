@@ -64,7 +64,6 @@ extern "C" int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64
     h->d_state = nullptr;
     h->d_wpack = nullptr;
     h->d_work = nullptr;
-    h->d_wtc = nullptr;
     h->d_wtc_wide = nullptr;
     h->has_weights = false;
     cudaError_t e = cudaMalloc(&h->d_state, sizeof(uint64_t) * (size_t)n_games);
@@ -89,7 +88,6 @@ extern "C" int nfsp_env_destroy(nfsp_env_t h) {
     if (h->d_state) cudaFree(h->d_state);
     if (h->d_wpack) cudaFree(h->d_wpack);
     if (h->d_work) cudaFree(h->d_work);
-    if (h->d_wtc) cudaFree(h->d_wtc);
     if (h->d_wtc_wide) cudaFree(h->d_wtc_wide);
     delete h;
     return NFSP_OK;

@@ -17,8 +17,7 @@ struct nfsp_env_s {
     uint64_t *d_state;   // n packed words
     float *d_wpack;      // acting nets repacked for the kernels (act_kernels.cu), or nullptr
     uint32_t *d_work;    // dynamic work counter of the fused rollout
-    void *d_wtc;         // tensor-core operand image of layer 1, nets stacked along K (act_tc_kernels.cu)
-    void *d_wtc_wide;    // same, nets side by side along N (fused rollout)
+    void *d_wtc_wide;    // tensor-core operand image of layer 1, the four nets side by side along N (act_tc_kernels.cu)
     bool has_weights;
 };
 

@@ -34,15 +34,24 @@ b = sp.forward(torch.from_numpy(o_all), torch.from_numpy(k_all), tensor_cores=Tr
 print("rows", len(o_all), "cuda-core max err", np.abs(a - ref).max(), "tcgen05 max err", np.abs(b - ref).max())
 n = 1 << 23
 oo = torch.from_numpy(o_all).cuda()[torch.randint(0, len(o_all), (n,), device="cuda")]
-kk = torch.randint(0, 4, (n,), device="cuda", dtype=torch.int8)
-for name, tc in (("cuda-core", False), ("tcgen05", True)):
-    for _ in range(3):
-        sp.forward(oo, kk, tensor_cores=tc)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        sp.forward(oo, kk, tensor_cores=tc)
-    e1.record()
-    e1.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    print("%-10s %.3f ms for %d rows -> %.3e rows/s" % (name, ms, n, n / ms * 1e3))
+mixes = {
+    "uniform-random nets": torch.randint(0, 4, (n,), device="cuda", dtype=torch.int8),
+    "NFSP mix 45/5/5/45": torch.tensor([0, 1, 3, 2], device="cuda", dtype=torch.int8)[
+        torch.bucketize(torch.rand(n, device="cuda"), torch.tensor([0.45, 0.50, 0.55], device="cuda"))],
+    "one net (Model.predict)": torch.zeros(n, device="cuda", dtype=torch.int8),
+}
+only = sys.argv[1] if len(sys.argv) > 1 else None
+for mix, kk in mixes.items():
+    if only and only not in mix:
+        continue
+    for name, tc in (("cuda-core", False), ("tcgen05", True)):
+        for _ in range(3):
+            sp.forward(oo, kk, tensor_cores=tc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            sp.forward(oo, kk, tensor_cores=tc)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("%-24s %-10s %.3f ms for %d rows -> %.3e rows/s" % (mix, name, ms, n, n / ms * 1e3))

@@ -11,4 +11,5 @@ a.record(); sp.rollout(T, insert=False); b.record(); b.synchronize()
 st = sp.stats.cpu().numpy().astype("uint64")
 steps = n * T / 128
 print("ms", a.elapsed_time(b))
-print("per group-step cycles: begin+sort %.0f lock %.0f mma %.0f epi %.0f fin %.0f" % (int(st[13]) / steps, (int(st[14]) & 0xFFFFFFFF) / steps, (int(st[14]) >> 32) / steps, (int(st[15]) & 0xFFFFFFFF) / steps, (int(st[15]) >> 32) / steps))
+print("per group-step cycles: begin %.0f  sort+lock+mma+epilogue %.0f  result exchange %.0f  finish %.0f" % (
+    int(st[13]) / steps, int(st[14]) / steps, (int(st[15]) & 0xFFFFFFFF) / steps, (int(st[15]) >> 32) / steps))
