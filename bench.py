@@ -340,6 +340,28 @@ def run_gpu(args):
         env_ms += a.elapsed_time(b)
     env_rate = n * ENV_T_PER_CALL * args.steps / (env_ms * 1e-3)
 
+    # the README's env (leduc/env.py, ENV_LEGACY) beside it: README iterations of 2 transitions, records written
+    leg = nfsp_b200.BatchedLegacyEnv(n, seed=SEED, game0=game0, device=dev)
+    leg.reset()
+    rec = torch.empty((3, T_PER_CALL, n, 2), dtype=torch.int32, device=dev)
+
+    def legacy_step():
+        check(lib().nfsp_legacy_rollout(leg._h, None, T_PER_CALL, _ptr(rec), _stream(dev)))
+
+    for _ in range(3):
+        legacy_step()
+    leg_ms = 0.0
+    for _ in range(args.steps):
+        flush_buf.zero_()
+        a, b = ev(), ev()
+        a.record()
+        legacy_step()
+        b.record()
+        b.synchronize()
+        leg_ms += a.elapsed_time(b)
+    legacy_rate = 2 * n * T_PER_CALL * args.steps / (leg_ms * 1e-3)
+    del rec, leg
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -406,6 +428,9 @@ def run_gpu(args):
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
                                    "transitions_per_launch": n * ENV_T_PER_CALL},
+                      "env_only_legacy": {"kernel": "legacy_rollout_kernel", "transitions_per_sec": legacy_rate,
+                                          "achieved_gbs": legacy_rate * 20.0 / 1e9, "frac_of_hbm_peak": legacy_rate * 20.0 / 1e9 / hbm,
+                                          "algorithmic_bytes_per_transition": 20.0},
                       "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
                                                                  "kernel_ms_per_launch": other_ms / args.steps},
                       "rollout_64k_games": {"config": "BASELINE configs[2]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts",

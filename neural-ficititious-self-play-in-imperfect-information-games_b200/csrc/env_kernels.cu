@@ -58,7 +58,7 @@ nfsp_step_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64_
             const int64_t at = (int64_t)t * n + i;
             int code = actions ? (int)actions[at] : -1;
             bool started = false;
-            const bool redeal = auto_reset && g.need_reset();
+            const bool redeal = auto_reset && (g.need_reset() || g.terminated());  // also hands finished with auto_reset = 0
             if (redeal || code < 0) {  // one Philox block serves the re-deal and the random action
                 const Philox4 x = game_block(seed, game, step, STREAM_STEP);
                 if (redeal) {

@@ -136,7 +136,9 @@ struct NfspFast {
         const uint32_t both = H | (H >> 12);
         const uint32_t id0 = seq_id6(both & 63u), id1 = seq_id6((both >> 6) & 63u);
         const uint32_t r = g.round(), q = (uint32_t)g.to_act();
-        F = (3u * r + g.k()) | (g.dealer() << 3) | (q << 4) | (g.pub() << 5) | ((uint32_t)g.need_reset() << 7) |
+        // a hand that finished without the re-deal flag (stepped with auto_reset = 0 before) is re-dealt all the same:
+        // the kernels that use this representation always run with auto re-deal
+        F = (3u * r + g.k()) | (g.dealer() << 3) | (q << 4) | (g.pub() << 5) | ((uint32_t)(g.need_reset() || g.terminated()) << 7) |
             ((r ? 9u + id1 : id0) << 8) | ((r ? (id0 >> 1) - 1u : 0u) << 13) | ((uint32_t)g.terminated() << 16) |
             (g.term_actor() << 17) | (g.outcome() << 18) | ((uint32_t)g.anomaly() << 20);
         PA = make_p(g, (int)q);

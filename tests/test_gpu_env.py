@@ -275,3 +275,25 @@ def test_dropin_legacy_env_readme_flow(nb, golden_dir):
                 assert info == ""
     env.reset()  # Philox deal path
     assert env.init_state(1).shape == (1, 3)
+
+
+def test_lean_and_general_kernels_agree_after_manual_hands(nb):
+    """Hands played to the end WITHOUT auto re-deal, then handed to the auto re-deal paths: the lean kernel
+    (Philox actions) and the general kernel (the same actions passed explicitly) re-deal them and stay word for
+    word identical, traces included."""
+    n, steps = 5000, 10
+    rng = np.random.RandomState(4)
+    envs = [nb.BatchedNfspEnv(n, seed=77) for _ in range(2)]
+    dealer = rng.randint(0, 2, n).astype(np.int8)
+    cards = np.stack([rng.randint(0, 3, n), rng.randint(0, 3, n), rng.randint(0, 3, n)], 1).astype(np.int8)
+    manual = rng.randint(0, 3, (6, n)).astype(np.int8)
+    for e in envs:
+        e.set_hands(dealer, cards)
+        for k in range(6):   # some games finish early and then refuse further steps (anomaly flag), as in the reference
+            e.step(manual[k:k + 1], n_steps=1, auto_reset=False)
+        e.step_counter = 100
+    lean = envs[0].step(n_steps=steps, trace=True)
+    acts = lean["action"].to(torch.int8)
+    gen = envs[1].step(actions=acts, n_steps=steps, auto_reset=True, trace=True)
+    assert torch.equal(lean["raw"], gen["raw"])
+    assert torch.equal(envs[0].state_words(), envs[1].state_words())
