@@ -7,13 +7,16 @@
 //     taken action against r + gamma * (1 - t) * max_a' Q_target(s2), mean over the 3 outputs and the rows;
 //   average policy (agent.py:109-116, 255-264): softmax head, categorical cross-entropy against the stored
 //     score vector a (Keras semantics: the target is used as is, not renormalised).
-// One CTA per net, one thread per hidden unit: the thread keeps its column of W1, its row of W2 and the
-// matching gradient accumulators in registers; the 64-wide reductions of layer 2 go through shuffles.
+// One CTA per net, kRowGroups groups of 64 threads, one thread per hidden unit and group: the thread keeps its column
+// of W1, its row of W2 and the matching gradient accumulators in registers; the 64-wide reductions of layer 2 go
+// through shuffles and a 64-thread named barrier.  The groups take the minibatch rows round-robin (the kernel is
+// latency-bound: three dependent reductions per row) and their partial gradients are summed in a fixed order.
 #include "common.cuh"
 
 namespace nfsp {
 
-constexpr int kLearnThreads = 64;
+constexpr int kRowGroups = 4;
+constexpr int kLearnThreads = 64 * kRowGroups;
 constexpr int kGradFloats = 4 * NFSP_NET_PARAMS;
 
 struct LearnerArgs {
@@ -48,17 +51,18 @@ struct NetRegs {
     }
 };
 
-// sum over the 64 threads of the CTA (2 warps); every thread gets the 3 totals
-__device__ __forceinline__ void cta_sum3(float &a, float &b, float &c, float (*red)[2][4], int slot) {
+// sum over the 64 threads of a group (2 warps); every thread of the group gets the 3 totals
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 64;" ::"r"(1 + group) : "memory"); }
+__device__ __forceinline__ void cta_sum3(float &a, float &b, float &c, float (*red)[2][4], int slot, int group) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
         b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
         c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     }
-    const int warp = threadIdx.x >> 5;
+    const int warp = (threadIdx.x >> 5) & 1;
     if ((threadIdx.x & 31) == 0) { red[slot][warp][0] = a; red[slot][warp][1] = b; red[slot][warp][2] = c; }
-    __syncthreads();
+    group_sync(group);
     a = red[slot][0][0] + red[slot][1][0];
     b = red[slot][0][1] + red[slot][1][1];
     c = red[slot][0][2] + red[slot][1][2];
@@ -66,11 +70,13 @@ __device__ __forceinline__ void cta_sum3(float &a, float &b, float &c, float (*r
 
 __global__ void __launch_bounds__(kLearnThreads)
 learner_grad_kernel(const LearnerArgs A) {
-    __shared__ float red[4][2][4];
-    const int net = blockIdx.x, player = net >> 1, is_br = net & 1, j = threadIdx.x;
+    __shared__ float red_all[kRowGroups][4][2][4];
+    __shared__ float part[kRowGroups][40][64];  // per group: gw1[30], gb1, gw2[3] per hidden unit; row 34: gb2, loss, expl
+    const int net = blockIdx.x, player = net >> 1, is_br = net & 1, group = threadIdx.x >> 6, j = threadIdx.x & 63;
+    float (*red)[2][4] = red_all[group];
     float *g = A.grad + net * NFSP_NET_PARAMS;
     if (!((A.net_mask >> net) & 1)) {
-        for (int e = j; e < NFSP_NET_PARAMS; e += kLearnThreads) g[e] = 0.f;
+        for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) g[e] = 0.f;
         return;
     }
     NetRegs W, T;
@@ -88,7 +94,7 @@ learner_grad_kernel(const LearnerArgs A) {
     for (int i = 0; i < 30; ++i) gw1[i] = 0.f;
     float loss = 0.f, expl = 0.f;
     const float inv_rows = 1.0f / (float)A.rows;
-    for (int r = 0; r < A.rows; ++r) {
+    for (int r = group; r < A.rows; r += kRowGroups) {
         const int row = A.row0 + r;
         uint32_t s;
         float dz0, dz1, dz2;
@@ -100,13 +106,13 @@ learner_grad_kernel(const LearnerArgs A) {
             // online Q(s), target Q(s2), target Q(s) (exploitability proxy, agent.py:234-238)
             const float h = W.hidden(s);
             float z0 = h * W.w2[0], z1 = h * W.w2[1], z2 = h * W.w2[2];
-            cta_sum3(z0, z1, z2, red, 0);
+            cta_sum3(z0, z1, z2, red, 0, group);
             const float ht = T.hidden(rec.y);
             float y0 = ht * T.w2[0], y1 = ht * T.w2[1], y2 = ht * T.w2[2];
-            cta_sum3(y0, y1, y2, red, 1);
+            cta_sum3(y0, y1, y2, red, 1, group);
             const float hs = T.hidden(s);
             float e0 = hs * T.w2[0], e1 = hs * T.w2[1], e2 = hs * T.w2[2];
-            cta_sum3(e0, e1, e2, red, 2);
+            cta_sum3(e0, e1, e2, red, 2, group);
             expl += fmaxf(fmaxf(fmaxf(e0 + t2_0, 0.f), fmaxf(e1 + t2_1, 0.f)), fmaxf(e2 + t2_2, 0.f));
             const float qn = fmaxf(fmaxf(fmaxf(y0 + t2_0, 0.f), fmaxf(y1 + t2_1, 0.f)), fmaxf(y2 + t2_2, 0.f));
             const float target = rew + ((term && !A.terminal_bootstraps) ? 0.f : A.gamma * qn);
@@ -117,7 +123,7 @@ learner_grad_kernel(const LearnerArgs A) {
             loss += (ae > 1.f ? ae - 0.5f : 0.5f * err * err) * (1.0f / 3.0f);
             const float dq = -(ae > 1.f ? copysignf(1.f, err) : err) * (1.0f / 3.0f) * (za > 0.f ? 1.f : 0.f);
             dz0 = a == 0 ? dq : 0.f; dz1 = a == 1 ? dq : 0.f; dz2 = a == 2 ? dq : 0.f;
-            __syncthreads();  // red[] slots are reused by the next row
+            group_sync(group);  // red[] slots are reused by the next row
             const float dh = (h > 0.f) ? (W.w2[0] * dz0 + W.w2[1] * dz1 + W.w2[2] * dz2) : 0.f;
             gw2[0] += h * dz0; gw2[1] += h * dz1; gw2[2] += h * dz2;
             gb1 += dh;
@@ -129,7 +135,7 @@ learner_grad_kernel(const LearnerArgs A) {
             const float ya = __uint_as_float(rec.y), yb = __uint_as_float(rec.z), yc = __uint_as_float(rec.w);
             const float h = W.hidden(s);
             float z0 = h * W.w2[0], z1 = h * W.w2[1], z2 = h * W.w2[2];
-            cta_sum3(z0, z1, z2, red, 0);
+            cta_sum3(z0, z1, z2, red, 0, group);
             z0 += b2_0; z1 += b2_1; z2 += b2_2;
             const float m = fmaxf(z0, fmaxf(z1, z2));
             const float x0 = expf(z0 - m), x1 = expf(z1 - m), x2 = expf(z2 - m);
@@ -138,7 +144,7 @@ learner_grad_kernel(const LearnerArgs A) {
             const float ysum = ya + yb + yc;
             loss += -(ya * logf(fmaxf(p0, 1e-7f)) + yb * logf(fmaxf(p1, 1e-7f)) + yc * logf(fmaxf(p2, 1e-7f)));
             dz0 = p0 * ysum - ya; dz1 = p1 * ysum - yb; dz2 = p2 * ysum - yc;
-            __syncthreads();
+            group_sync(group);
             const float dh = (h > 0.f) ? (W.w2[0] * dz0 + W.w2[1] * dz1 + W.w2[2] * dz2) : 0.f;
             gw2[0] += h * dz0; gw2[1] += h * dz1; gw2[2] += h * dz2;
             gb1 += dh;
@@ -147,17 +153,41 @@ learner_grad_kernel(const LearnerArgs A) {
         }
         gb2[0] += dz0; gb2[1] += dz1; gb2[2] += dz2;
     }
+    // the groups' partial sums meet in shared memory and are added in group order (deterministic)
 #pragma unroll
-    for (int i = 0; i < 30; ++i) g[i * 64 + j] = gw1[i] * inv_rows;
-    g[1920 + j] = gb1 * inv_rows;
+    for (int i = 0; i < 30; ++i) part[group][i][j] = gw1[i];
+    part[group][30][j] = gb1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) g[1984 + j * 3 + c] = gw2[c] * inv_rows;
+    for (int c = 0; c < 3; ++c) part[group][31 + c][j] = gw2[c];
     if (j == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g[2176 + c] = gb2[c] * inv_rows;
+        for (int c = 0; c < 3; ++c) part[group][34][c] = gb2[c];
+        part[group][34][3] = loss;
+        part[group][34][4] = expl;
+    }
+    __syncthreads();
+    if (group != 0) return;
+    float tot[34];
+#pragma unroll
+    for (int i = 0; i < 34; ++i) {
+        float v = part[0][i][j];
+#pragma unroll
+        for (int k = 1; k < kRowGroups; ++k) v += part[k][i][j];
+        tot[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 30; ++i) g[i * 64 + j] = tot[i] * inv_rows;
+    g[1920 + j] = tot[30] * inv_rows;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[1984 + j * 3 + c] = tot[31 + c] * inv_rows;
+    if (j < 5) {
+        float v = part[0][34][j];
+#pragma unroll
+        for (int k = 1; k < kRowGroups; ++k) v += part[k][34][j];
+        if (j < 3) g[2176 + j] = v * inv_rows;
         // stats: [0,1] exploitability-proxy sums of the BR nets, [2,3] their row counts, [4..7] loss sums per net
-        if (is_br) { A.stats[player] = expl; A.stats[2 + player] = (float)A.rows; }
-        A.stats[4 + net] = loss;
+        if (j == 3) A.stats[4 + net] = v;
+        if (j == 4 && is_br) { A.stats[player] = v; A.stats[2 + player] = (float)A.rows; }
     }
 }
 
