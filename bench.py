@@ -423,7 +423,7 @@ def run_gpu(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": 11 * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "extra": {"env_only": {"kernel": "nfsp_step_fast_kernel", "transitions_per_sec": env_rate,
+            "extra": {"env_only": {"kernel": "nfsp_step_fsm_kernel", "transitions_per_sec": env_rate,
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,

@@ -82,11 +82,15 @@ int nfsp_env_set_hands(nfsp_env_t h, const int8_t *d_dealer, const int8_t *d_car
  *   auto_reset: re-deal a finished hand at its next step (dealer alternates, main.py:28-31).
  *   d_trace   uint32[3][n_steps][n] or NULL: planes obs|terminal<<30|player<<31, reward (float
  *             bits), misc (DESIGN.md "trace record").
- * With d_actions = d_players = NULL and auto_reset (the throughput configuration) the call runs the lean kernel
- * (game in actor-relative registers, table-driven betting step); every other combination runs the general
- * kernel on the packed word.  Both produce identical words and traces. */
+ * With d_actions = d_players = NULL and auto_reset (the throughput configuration) the call runs the state-machine
+ * kernel (one table entry per (dealer, betting sequence, action), csrc/nfsp_fsm.cuh); every other combination runs
+ * the general kernel on the packed word.  Both produce identical words and traces. */
 int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int n_steps, int auto_reset,
                   double eta, uint32_t *d_trace, void *stream);
+/* Host only, no device needed: copies the table image of the state-machine step kernel (rows of newenv.Env.step /
+ * main.train's turn order, the deal and reward tables; layout in csrc/nfsp_fsm.cuh) into out if capacity_words is
+ * large enough.  Returns the image size in 32-bit words. */
+int nfsp_fsm_image(uint32_t *out, int capacity_words);
 /* newenv.Env.get_state(p) (newenv.py:116-129), packed: player < 0 => per-game d_players.
  * Outputs (any may be NULL): d_s snapshot mask, d_s2 current observation mask, d_reward,
  * d_term, d_last_a (argmax of last_action[p], 3 if it was never set / all-zero). */

@@ -62,6 +62,7 @@ extern "C" int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64
     h->game0 = game0;
     h->step = 0;
     h->d_state = nullptr;
+    h->d_fsm = nullptr;
     h->d_wpack = nullptr;
     h->d_work = nullptr;
     h->d_wtc_wide = nullptr;
@@ -78,6 +79,14 @@ extern "C" int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64
         delete h;
         return set_error(NFSP_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     }
+    if (rules == NFSP_RULES_NFSP) {
+        const int rc = nfsp_fsm_upload(h);
+        if (rc != NFSP_OK) {
+            cudaFree(h->d_state);
+            delete h;
+            return rc;
+        }
+    }
     *out = h;
     return NFSP_OK;
 }
@@ -86,6 +95,7 @@ extern "C" int nfsp_env_destroy(nfsp_env_t h) {
     if (!h) return NFSP_OK;
     DeviceGuard guard(h->device);
     if (h->d_state) cudaFree(h->d_state);
+    if (h->d_fsm) cudaFree(h->d_fsm);
     if (h->d_wpack) cudaFree(h->d_wpack);
     if (h->d_work) cudaFree(h->d_work);
     if (h->d_wtc_wide) cudaFree(h->d_wtc_wide);

@@ -15,11 +15,15 @@ struct nfsp_env_s {
     int64_t n;
     uint64_t seed, game0, step;
     uint64_t *d_state;   // n packed words
+    uint32_t *d_fsm;     // ENV_NFSP: table image of the state-machine step kernel (nfsp_fsm.cuh), built at create
     float *d_wpack;      // acting nets repacked for the kernels (act_kernels.cu), or nullptr
     uint32_t *d_work;    // dynamic work counter of the fused rollout
     void *d_wtc_wide;    // tensor-core operand image of layer 1, the four nets side by side along N (act_tc_kernels.cu)
     bool has_weights;
 };
+
+// builds and uploads the table image of nfsp_step_fsm_kernel (env_kernels.cu); the handle's device is current
+int nfsp_fsm_upload(nfsp_env_t h);
 
 // builds the tensor-core operand image of the acting nets (act_tc_kernels.cu)
 int nfsp_pack_tc_image(nfsp_env_t h, const float *d_weights, cudaStream_t st);

@@ -13,7 +13,7 @@ shares one global `random` stream between deck, policies and buffers, SURVEY 8 a
     python -m nfsp_b200.tracefile record --games 4096 --steps 32 --out hands.npz
     python -m nfsp_b200.tracefile check hands.npz
 
-`record` plays Philox-dealt uniform-random hands with the lean env kernel (nfsp_step_fast_kernel) and writes
+`record` plays Philox-dealt uniform-random hands with the state-machine env kernel (nfsp_step_fsm_kernel) and writes
 every hand that started and finished inside the window.  `check` replays the file through the GENERAL env
 kernel (explicit deck via set_hands, explicit action codes, no auto re-deal) and compares every transition
 word for word: the two kernels share no game logic beyond the packed word, so this is an independent
