@@ -343,10 +343,11 @@ def run_gpu(args):
     # the README's env (leduc/env.py, ENV_LEGACY) beside it: README iterations of 2 transitions, records written
     leg = nfsp_b200.BatchedLegacyEnv(n, seed=SEED, game0=game0, device=dev)
     leg.reset()
-    rec = torch.empty((3, T_PER_CALL, n, 2), dtype=torch.int32, device=dev)
+    leg_iters = ENV_T_PER_CALL // 2  # as many transitions per game and launch as the NFSP env kernel above
+    rec = torch.empty((3, leg_iters, n, 2), dtype=torch.int32, device=dev)
 
     def legacy_step():
-        check(lib().nfsp_legacy_rollout(leg._h, None, T_PER_CALL, _ptr(rec), _stream(dev)))
+        check(lib().nfsp_legacy_rollout(leg._h, None, leg_iters, _ptr(rec), _stream(dev)))
 
     for _ in range(3):
         legacy_step()
@@ -359,7 +360,7 @@ def run_gpu(args):
         b.record()
         b.synchronize()
         leg_ms += a.elapsed_time(b)
-    legacy_rate = 2 * n * T_PER_CALL * args.steps / (leg_ms * 1e-3)
+    legacy_rate = 2 * n * leg_iters * args.steps / (leg_ms * 1e-3)
     del rec, leg
 
     if rank != 0:
@@ -427,10 +428,18 @@ def run_gpu(args):
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
-                                   "transitions_per_launch": n * ENV_T_PER_CALL},
+                                   "transitions_per_launch": n * ENV_T_PER_CALL,
+                                   # what the kernel really moves: the 16-byte state word once per launch, 12 bytes of trace per transition
+                                   "moved_bytes_per_transition": 12.0 + 16.0 / ENV_T_PER_CALL,
+                                   "moved_gbs": env_rate * (12.0 + 16.0 / ENV_T_PER_CALL) / 1e9,
+                                   "moved_frac_of_hbm_peak": env_rate * (12.0 + 16.0 / ENV_T_PER_CALL) / 1e9 / hbm},
                       "env_only_legacy": {"kernel": "legacy_rollout_kernel", "transitions_per_sec": legacy_rate,
                                           "achieved_gbs": legacy_rate * 20.0 / 1e9, "frac_of_hbm_peak": legacy_rate * 20.0 / 1e9 / hbm,
-                                          "algorithmic_bytes_per_transition": 20.0},
+                                          "algorithmic_bytes_per_transition": 20.0,
+                                          "transitions_per_launch": 2 * n * leg_iters,
+                                          "moved_bytes_per_transition": 12.0 + 8.0 / leg_iters,
+                                          "moved_gbs": legacy_rate * (12.0 + 8.0 / leg_iters) / 1e9,
+                                          "moved_frac_of_hbm_peak": legacy_rate * (12.0 + 8.0 / leg_iters) / 1e9 / hbm},
                       "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
                                                                  "kernel_ms_per_launch": other_ms / args.steps},
                       "rollout_64k_games": {"config": "BASELINE configs[2]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts",

@@ -91,6 +91,9 @@ int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players
  * main.train's turn order, the deal and reward tables; layout in csrc/nfsp_fsm.cuh) into out if capacity_words is
  * large enough.  Returns the image size in 32-bit words. */
 int nfsp_fsm_image(uint32_t *out, int capacity_words);
+/* The same for the legacy rules (leduc/env.py README iteration; layout in csrc/legacy_fsm.cuh); *n_rows receives the
+ * number of states a rollout can reach. */
+int nfsp_legacy_fsm_image(uint32_t *out, int capacity_words, int *n_rows);
 /* newenv.Env.get_state(p) (newenv.py:116-129), packed: player < 0 => per-game d_players.
  * Outputs (any may be NULL): d_s snapshot mask, d_s2 current observation mask, d_reward,
  * d_term, d_last_a (argmax of last_action[p], 3 if it was never set / all-zero). */

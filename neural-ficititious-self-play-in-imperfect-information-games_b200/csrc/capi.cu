@@ -79,7 +79,7 @@ extern "C" int nfsp_env_create(int rules, int64_t n_games, uint64_t seed, uint64
         delete h;
         return set_error(NFSP_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     }
-    if (rules == NFSP_RULES_NFSP) {
+    {
         const int rc = nfsp_fsm_upload(h);
         if (rc != NFSP_OK) {
             cudaFree(h->d_state);

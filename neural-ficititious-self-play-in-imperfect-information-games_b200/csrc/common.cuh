@@ -15,7 +15,7 @@ struct nfsp_env_s {
     int64_t n;
     uint64_t seed, game0, step;
     uint64_t *d_state;   // n packed words
-    uint32_t *d_fsm;     // ENV_NFSP: table image of the state-machine step kernel (nfsp_fsm.cuh), built at create
+    uint32_t *d_fsm;     // table image of the rule set's state-machine kernel (nfsp_fsm.cuh / legacy_fsm.cuh), built at create
     float *d_wpack;      // acting nets repacked for the kernels (act_kernels.cu), or nullptr
     uint32_t *d_work;    // dynamic work counter of the fused rollout
     void *d_wtc_wide;    // tensor-core operand image of layer 1, the four nets side by side along N (act_tc_kernels.cu)

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "legacy_rules.cuh"
 #include "nfsp_fast.cuh"
+#include "legacy_fsm.cuh"
 #include "nfsp_fsm.cuh"
 #include "nfsp_rules.cuh"
 #include "philox.cuh"
@@ -224,50 +225,118 @@ legacy_gns_kernel(uint64_t *__restrict__ state, int64_t n, const int8_t *__restr
     }
 }
 
+// One game through n_iters README iterations on the packed word: the rules as written in legacy_rules.cuh.  The rollout
+// kernel plays a game this way only when its word is not a state a rollout can produce (see legacy_fsm.cuh).
+template <bool kTrace>
+__device__ __noinline__ uint64_t legacy_generic_game(uint64_t w, const PhiloxKeys &keys, uint64_t game, uint64_t step0, int n_iters,
+                                                      const int8_t *__restrict__ actions, uint32_t *__restrict__ rec, int64_t n,
+                                                      int64_t i) {
+    const int64_t plane = (int64_t)n_iters * n * 2;
+    LegacyW g{w};
+    for (int t = 0; t < n_iters; ++t) {
+        bool started = false;
+        const int64_t at = ((int64_t)t * n + i) * 2;
+        int a0 = actions ? (int)actions[at] : -1, a1 = actions ? (int)actions[at + 1] : -1;
+        if (g.need_reset() || a0 < 0 || a1 < 0) {
+            const Philox4 x = game_block(keys, game, step0 + (uint64_t)t, STREAM_STEP);
+            if (g.need_reset()) {
+                legacy_redeal(g, x);
+                started = true;
+            }
+            if (a0 < 0) a0 = (int)__umulhi(x.x, 3u);
+            if (a1 < 0) a1 = (int)__umulhi(x.y, 3u);
+        }
+        // README.md:15-38: both players step, then both read the new state
+        g.step(a0, 0, kPenalty);
+        g.step(a1, 1, kPenalty);
+        g.get_new_state(0);
+        const int t0 = g.terminal(0), r0 = g.reward(0), sp0 = g.st_pot(0);
+        g.get_new_state(1);
+        if (kTrace) {
+            uint2 w0, w1, w2;
+            w0.x = (uint32_t)g.card(0) | (0xFFu << 8) | ((uint32_t)sp0 << 16) | ((uint32_t)t0 << 24);
+            w0.y = (uint32_t)g.card(1) | (0xFFu << 8) | ((uint32_t)g.st_pot(1) << 16) | ((uint32_t)g.terminal(1) << 24);
+            *reinterpret_cast<uint2 *>(rec + at) = w0;
+            w1.x = (uint32_t)r0;
+            w1.y = (uint32_t)g.reward(1);
+            *reinterpret_cast<uint2 *>(rec + plane + at) = w1;
+            w2.x = (uint32_t)a0 | ((uint32_t)(g.left(0) + 1) << 2) | ((uint32_t)g.pot(0) << 5) | ((uint32_t)started << 8);
+            w2.y = (uint32_t)a1 | ((uint32_t)(g.left(1) + 1) << 2) | ((uint32_t)g.pot(1) << 5) | ((uint32_t)started << 8);
+            *reinterpret_cast<uint2 *>(rec + 2 * plane + at) = w2;
+        }
+        if (t0 | g.terminal(1)) g.w |= 1ull << 30;
+    }
+    return g.w;
+}
+
+// The README iteration for every game, n_iters times, with auto re-deal: one table entry per (state, a0, a1)
+// (legacy_fsm.cuh).  `image` is the table image built on the host at nfsp_env_create.
 template <bool kTrace>
 __global__ void __launch_bounds__(kThreads)
-legacy_rollout_kernel(uint64_t *__restrict__ state, int64_t n, uint64_t seed, uint64_t game0, uint64_t step0,
-                      int n_iters, const int8_t *__restrict__ actions, uint32_t *__restrict__ rec) {
-    const int64_t plane = (int64_t)n_iters * n * 2;
+legacy_rollout_kernel(uint64_t *__restrict__ state, int64_t n, const uint32_t *__restrict__ image, const PhiloxKeys keys,
+                      uint64_t game0, uint64_t step0, int n_iters, const int8_t *__restrict__ actions,
+                      uint32_t *__restrict__ rec) {
+    __shared__ __align__(16) uint32_t s_tab[lfsm::kImageWords];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_tab);
+    for (int w = threadIdx.x; w < lfsm::kImageWords; w += blockDim.x) s_tab[w] = image[w] + (lfsm::is_address(w) ? base : 0u);
+    __syncthreads();
+    const uint8_t *s_keys = reinterpret_cast<const uint8_t *>(s_tab) + lfsm::kKeyOff;
+    const uint32_t deal_base = base + (uint32_t)lfsm::kDealOff;
+    const int64_t plane = (int64_t)n_iters * n;  // in uint2 records
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t game = game0 + (uint64_t)i;
-        LegacyW g{state[i]};
+        const LegacyW g{state[i]};
+        // a hand that is over is re-dealt before anything is looked up: any row will do
+        const int key = g.need_reset() ? -1 : lfsm::state_key(g, kPenalty);
+        const uint32_t row = g.need_reset() ? 0u : (key >= 0 ? (uint32_t)s_keys[key] : 0xFFu);
+        if (row == 0xFFu) {
+            state[i] = legacy_generic_game<kTrace>(g.w, keys, game, step0, n_iters, actions, rec, n, i);
+            continue;
+        }
+        uint32_t six = base + (uint32_t)lfsm::kRowsOff + row * (uint32_t)lfsm::kRowBytes, ea = six;
+        uint32_t c0 = (uint32_t)g.card(0), c1 = (uint32_t)g.card(1);
+        int G = c0 > c1, L = c0 < c1, r0 = 0, r1 = 0;
+        uint32_t need = g.need_reset() ? lfsm::kTermBit : 0u;
+        uint2 *p0 = reinterpret_cast<uint2 *>(rec) + i, *p1 = p0 + plane, *p2 = p1 + plane;
         for (int t = 0; t < n_iters; ++t) {
-            const uint64_t step = step0 + (uint64_t)t;
-            bool started = false;
-            const int64_t at = ((int64_t)t * n + i) * 2;
-            int a0 = actions ? (int)actions[at] : -1, a1 = actions ? (int)actions[at + 1] : -1;
-            if (g.need_reset() || a0 < 0 || a1 < 0) {
-                const Philox4 x = game_block(seed, game, step, STREAM_STEP);
-                if (g.need_reset()) {
-                    legacy_redeal(g, x);
-                    started = true;
+            int a0 = -1, a1 = -1;
+            if (actions) {  // values above 2 act as a raise (env.py:130: the else branch)
+                const int64_t at = ((int64_t)t * n + i) * 2;
+                a0 = min((int)actions[at], 2);
+                a1 = min((int)actions[at + 1], 2);
+            }
+            uint32_t started = 0u;
+            if (need | (uint32_t)((a0 | a1) < 0)) {
+                const Philox4 x = game_block(keys, game, step0 + (uint64_t)t, STREAM_STEP);
+                if (need) {  // env.py:46-72
+                    const uint4 D = fsm::lds128(deal_base + __umulhi(x.z, 120u) * 16u);
+                    c0 = D.x; c1 = D.y; G = (int)D.z; L = (int)D.w;
+                    six = base + (uint32_t)lfsm::kRowsOff;
+                    started = 1u << 8;
                 }
                 if (a0 < 0) a0 = (int)__umulhi(x.x, 3u);
                 if (a1 < 0) a1 = (int)__umulhi(x.y, 3u);
             }
-            // README.md:15-38: both players step, then both read the new state
-            g.step(a0, 0, kPenalty);
-            g.step(a1, 1, kPenalty);
-            g.get_new_state(0);
-            const int t0 = g.terminal(0), r0 = g.reward(0), sp0 = g.st_pot(0);
-            g.get_new_state(1);
+            ea = six + (uint32_t)(a0 * 3 + a1) * (uint32_t)lfsm::kEntryBytes;
+            const uint4 A = fsm::lds128(ea);  // nx, w0, rb0, rb1
+            const uint4 B = fsm::lds128(ea + 16u);  // w2x, w2y, p0t, p1t
+            const int u = L * (int)B.w - G * (int)B.z;  // env.py:184-199 for both players
+            r0 = (int)A.z + u;
+            r1 = (int)A.w - u;
             if (kTrace) {
-                uint2 w0, w1;
-                w0.x = (uint32_t)g.card(0) | (0xFFu << 8) | ((uint32_t)sp0 << 16) | ((uint32_t)t0 << 24);
-                w0.y = (uint32_t)g.card(1) | (0xFFu << 8) | ((uint32_t)g.st_pot(1) << 16) | ((uint32_t)g.terminal(1) << 24);
-                *reinterpret_cast<uint2 *>(rec + at) = w0;
-                w1.x = (uint32_t)r0;
-                w1.y = (uint32_t)g.reward(1);
-                *reinterpret_cast<uint2 *>(rec + plane + at) = w1;
-                uint2 w2;
-                w2.x = (uint32_t)a0 | ((uint32_t)(g.left(0) + 1) << 2) | ((uint32_t)g.pot(0) << 5) | ((uint32_t)started << 8);
-                w2.y = (uint32_t)a1 | ((uint32_t)(g.left(1) + 1) << 2) | ((uint32_t)g.pot(1) << 5) | ((uint32_t)started << 8);
-                *reinterpret_cast<uint2 *>(rec + 2 * plane + at) = w2;
+                *p0 = make_uint2(A.y | c0, A.y | c1);
+                *p1 = make_uint2((uint32_t)r0, (uint32_t)r1);
+                *p2 = make_uint2(B.x | started, B.y | started);
+                p0 += n;
+                p1 += n;
+                p2 += n;
             }
-            if (t0 | g.terminal(1)) g.w |= 1ull << 30;
+            need = A.y & lfsm::kTermBit;
+            six = A.x;
         }
-        state[i] = g.w;
+        const uint32_t lo = fsm::lds32(ea + 32u) | c0 | (c1 << 2);
+        const uint32_t hi = ((uint32_t)r0 & 0xFFFFu) | ((uint32_t)r1 << 16);
+        state[i] = (uint64_t)lo | ((uint64_t)hi << 32);
     }
 }
 
@@ -297,6 +366,17 @@ expand_obs_kernel(const uint32_t *__restrict__ masks, int64_t n, float *__restri
 
 using namespace nfsp;
 
+// grid of a table-driven kernel: exactly the CTAs that are resident at once (each copies the table image into its
+// shared memory once and then strides over the games), never more than the games need
+template <class Kernel>
+static int resident_grid(Kernel kernel, int64_t n, int sm_count) {
+    static const int per_sm = [kernel] {
+        int v = 0;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) == cudaSuccess && v >= 1 ? v : 4;
+    }();
+    return grid_for(n, kThreads, sm_count, per_sm);
+}
+
 #define ENV_PROLOGUE(h, want_rules)                                                              \
     NFSP_CHECK_ARG(h != nullptr, "null handle");                                                 \
     NFSP_CHECK_ARG(h->rules == (want_rules), "handle has rules %d, call needs %d", h->rules, (want_rules)); \
@@ -307,18 +387,27 @@ using namespace nfsp;
     (void)grid
 
 int nfsp_fsm_upload(nfsp_env_t h) {
-    static uint32_t image[fsm::kImageWords];
-    static const bool built = (fsm::build_image(image), true);
-    (void)built;
-    NFSP_CUDA(cudaMalloc(&h->d_fsm, sizeof(image)));
-    NFSP_CUDA(cudaMemcpy(h->d_fsm, image, sizeof(image), cudaMemcpyHostToDevice));
+    static uint32_t image[fsm::kImageWords], legacy_image[lfsm::kImageWords];
+    static const int legacy_rows = (fsm::build_image(image), lfsm::build_image(legacy_image, kPenalty));
+    if (legacy_rows < 0) return set_error(NFSP_E_ARG, "legacy state machine does not fit its image");
+    const bool legacy = h->rules == NFSP_RULES_LEGACY;
+    const size_t bytes = legacy ? sizeof(legacy_image) : sizeof(image);
+    NFSP_CUDA(cudaMalloc(&h->d_fsm, bytes));
+    NFSP_CUDA(cudaMemcpy(h->d_fsm, legacy ? legacy_image : image, bytes, cudaMemcpyHostToDevice));
     return NFSP_OK;
 }
 
-// the table image of the state-machine step kernel, for inspection on the host (no device needed)
+// the table images of the state-machine kernels, for inspection on the host (no device needed)
 extern "C" int nfsp_fsm_image(uint32_t *out, int capacity_words) {
     if (out && capacity_words >= fsm::kImageWords) fsm::build_image(out);
     return fsm::kImageWords;
+}
+extern "C" int nfsp_legacy_fsm_image(uint32_t *out, int capacity_words, int *n_rows) {
+    if (out && capacity_words >= lfsm::kImageWords) {
+        const int rows = lfsm::build_image(out, kPenalty);
+        if (n_rows) *n_rows = rows;
+    }
+    return lfsm::kImageWords;
 }
 
 extern "C" int nfsp_env_reset(nfsp_env_t h, const int8_t *d_dealer, double eta, void *stream) {
@@ -345,11 +434,11 @@ extern "C" int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t
     NFSP_CHECK_ARG(n_steps >= 1, "n_steps must be >= 1");
     if (!d_actions && !d_players && auto_reset) {  // the benchmark configuration has its own lean kernel
         if (d_trace)
-            nfsp_step_fsm_kernel<true><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0,
-                                                                  h->step, n_steps, frac_u32(eta), d_trace);
+            nfsp_step_fsm_kernel<true><<<resident_grid(nfsp_step_fsm_kernel<true>, h->n, h->sm_count), kThreads, 0, st>>>(
+                h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0, h->step, n_steps, frac_u32(eta), d_trace);
         else
-            nfsp_step_fsm_kernel<false><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0,
-                                                                   h->step, n_steps, frac_u32(eta), nullptr);
+            nfsp_step_fsm_kernel<false><<<resident_grid(nfsp_step_fsm_kernel<false>, h->n, h->sm_count), kThreads, 0, st>>>(
+                h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0, h->step, n_steps, frac_u32(eta), nullptr);
         NFSP_LAUNCH_CHECK();
         h->step += (uint64_t)n_steps;
         return NFSP_OK;
@@ -423,11 +512,11 @@ extern "C" int nfsp_legacy_rollout(nfsp_env_t h, const int8_t *d_actions, int n_
     ENV_PROLOGUE(h, NFSP_RULES_LEGACY);
     NFSP_CHECK_ARG(n_iters >= 1, "n_iters must be >= 1");
     if (d_rec)
-        legacy_rollout_kernel<true><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->seed, h->game0, h->step, n_iters,
-                                                               d_actions, d_rec);
+        legacy_rollout_kernel<true><<<resident_grid(legacy_rollout_kernel<true>, h->n, h->sm_count), kThreads, 0, st>>>(
+            h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0, h->step, n_iters, d_actions, d_rec);
     else
-        legacy_rollout_kernel<false><<<grid, kThreads, 0, st>>>(h->d_state, h->n, h->seed, h->game0, h->step,
-                                                                n_iters, d_actions, nullptr);
+        legacy_rollout_kernel<false><<<resident_grid(legacy_rollout_kernel<false>, h->n, h->sm_count), kThreads, 0, st>>>(
+            h->d_state, h->n, h->d_fsm, philox_keys(h->seed), h->game0, h->step, n_iters, d_actions, nullptr);
     NFSP_LAUNCH_CHECK();
     h->step += (uint64_t)n_iters;
     return NFSP_OK;

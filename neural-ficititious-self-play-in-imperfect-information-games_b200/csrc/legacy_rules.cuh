@@ -21,25 +21,25 @@ namespace nfsp {
 struct LegacyW {
     uint64_t w;
 
-    __device__ __forceinline__ int card(int p) const { return (int)((w >> (2 * p)) & 3u); }
-    __device__ __forceinline__ int left(int p) const { return (int)((w >> (4 + 3 * p)) & 7u) - 1; }
-    __device__ __forceinline__ int pot(int p) const { return (int)((w >> (10 + 3 * p)) & 7u); }
-    __device__ __forceinline__ int terminal(int p) const { return (int)((w >> (16 + p)) & 1u); }
-    __device__ __forceinline__ int st_pot(int p) const { return (int)((w >> (18 + 4 * p)) & 15u); }
-    __device__ __forceinline__ int st_action(int p) const { return (int)((w >> (26 + 2 * p)) & 3u); }
-    __device__ __forceinline__ bool need_reset() const { return (w >> 30) & 1u; }
-    __device__ __forceinline__ int reward(int p) const { return (int)(int16_t)(uint16_t)(w >> (32 + 16 * p)); }
+    __host__ __device__ __forceinline__ int card(int p) const { return (int)((w >> (2 * p)) & 3u); }
+    __host__ __device__ __forceinline__ int left(int p) const { return (int)((w >> (4 + 3 * p)) & 7u) - 1; }
+    __host__ __device__ __forceinline__ int pot(int p) const { return (int)((w >> (10 + 3 * p)) & 7u); }
+    __host__ __device__ __forceinline__ int terminal(int p) const { return (int)((w >> (16 + p)) & 1u); }
+    __host__ __device__ __forceinline__ int st_pot(int p) const { return (int)((w >> (18 + 4 * p)) & 15u); }
+    __host__ __device__ __forceinline__ int st_action(int p) const { return (int)((w >> (26 + 2 * p)) & 3u); }
+    __host__ __device__ __forceinline__ bool need_reset() const { return (w >> 30) & 1u; }
+    __host__ __device__ __forceinline__ int reward(int p) const { return (int)(int16_t)(uint16_t)(w >> (32 + 16 * p)); }
 
-    __device__ __forceinline__ void set_left(int p, int v) {
+    __host__ __device__ __forceinline__ void set_left(int p, int v) {
         w = (w & ~(7ull << (4 + 3 * p))) | ((uint64_t)(uint32_t)(v + 1) << (4 + 3 * p));
     }
-    __device__ __forceinline__ void set_terminal(int p, int v) {
+    __host__ __device__ __forceinline__ void set_terminal(int p, int v) {
         w = (w & ~(1ull << (16 + p))) | ((uint64_t)v << (16 + p));
     }
-    __device__ __forceinline__ void set_st_pot(int p, int v) {
+    __host__ __device__ __forceinline__ void set_st_pot(int p, int v) {
         w = (w & ~(15ull << (18 + 4 * p))) | ((uint64_t)v << (18 + 4 * p));
     }
-    __device__ __forceinline__ void set_reward(int p, int v) {
+    __host__ __device__ __forceinline__ void set_reward(int p, int v) {
         if (v > 32767 || v < -32768) {
             w |= 1ull << 31;
             v = v > 0 ? 32767 : -32768;
@@ -48,12 +48,12 @@ struct LegacyW {
     }
 
     // env.py:46-72: Choices = 4 (config.ini:22), pots 0, rewards 0, stored action "3" (env.py:66)
-    __device__ __forceinline__ void reset(uint32_t c0, uint32_t c1) {
+    __host__ __device__ __forceinline__ void reset(uint32_t c0, uint32_t c1) {
         w = (uint64_t)c0 | ((uint64_t)c1 << 2) | (5ull << 4) | (5ull << 7) | (3ull << 26) | (3ull << 28);
     }
 
     // env.py:84-158; av = np.argmax(action); penalty = config.ini Agent.Penalty
-    __device__ __forceinline__ void step(int av, int p, int penalty) {
+    __host__ __device__ __forceinline__ void step(int av, int p, int penalty) {
         const int o = p ^ 1;
         int lp = left(p), term = 0;
         if (lp > 0) {
@@ -80,7 +80,7 @@ struct LegacyW {
     }
 
     // env.py:160-205
-    __device__ __forceinline__ void get_new_state(int p) {
+    __host__ __device__ __forceinline__ void get_new_state(int p) {
         const int o = p ^ 1;
         set_st_pot(p, pot(0) + pot(1));
         const int t = terminal(o);

@@ -45,14 +45,16 @@ enum : uint32_t { KIND_PASS = 0, KIND_ROUND = 1, KIND_SHOWDOWN = 2, KIND_FOLD = 
 
 // image layout, byte offsets (all 16-byte aligned)
 constexpr int kLiveRows = 36, kTermRows = 16, kRows = kLiveRows + kTermRows;
-constexpr int kRowBytes = 128, kEntryBytes = 32, kInfoOff = 96;
+// a row is 3 entries + the info word = 112 bytes = 7 bank groups of 16 bytes: 7 is coprime with the 8 bank groups an
+// LDS.128 quarter-warp spans, so different rows with the same action do not collide (they did with 128-byte rows)
+constexpr int kRowBytes = 112, kEntryBytes = 32, kInfoOff = 96;
 constexpr int kFsmOff = 0;
-constexpr int kDealOff = kFsmOff + kRows * kRowBytes;           // 6656
+constexpr int kDealOff = kFsmOff + kRows * kRowBytes;           // 5824
 constexpr int kDealEntries = 120, kPolOff = kDealEntries * 16;  // the 4 policy entries follow a dealer's 120 deals
 constexpr int kDealHalf = kPolOff + 4 * 16;                     // 1984
-constexpr int kRewardOff = kDealOff + 2 * kDealHalf;            // 10624
+constexpr int kRewardOff = kDealOff + 2 * kDealHalf;            // 9792
 constexpr int kRewardWords = 1024;
-constexpr int kImageBytes = kRewardOff + 4 * kRewardWords;      // 14720
+constexpr int kImageBytes = kRewardOff + 4 * kRewardWords;      // 13888
 constexpr int kImageWords = kImageBytes / 4;
 
 __host__ __device__ inline uint32_t seq_actions(uint32_t s) { return s == 0u ? 0u : (s < 3u ? 1u : 2u); }
@@ -160,7 +162,7 @@ inline void build_image(uint32_t *img) {
 }
 // word w of the image holds a byte offset that becomes a shared-memory address
 __host__ __device__ inline bool is_address(int w) {
-    if (w < kDealOff / 4) return (w & 31) < 24 && (w & 7) == 3;
+    if (w < kDealOff / 4) return (w % (kRowBytes / 4)) < 24 && ((w % (kRowBytes / 4)) & 7) == 3;
     if (w >= kRewardOff / 4) return false;
     const int v = (w - kDealOff / 4) % (kDealHalf / 4);
     return v >= kPolOff / 4 && (v & 3) == 3;

@@ -1,4 +1,5 @@
-"""Short driver for ncu: a few passes of the hot path at bench size (1M games, 8 decisions per launch).
+"""Short driver for ncu: a few passes of the hot path at bench size (1M games; 8 decisions per launch for the
+fused rollout, 32 transitions per game and launch for the env-only kernels, as in bench.py).
 
     python profiles/run_hot_path.py [rollout|env|legacy|all] [passes]
 """
@@ -23,13 +24,13 @@ if what in ("env", "all"):
     env = nfsp_b200.BatchedNfspEnv(n, seed=1234)
     env.reset()
     for _ in range(passes):
-        env.step(n_steps=T, trace=True)
+        env.step(n_steps=32, trace=True)
     torch.cuda.synchronize()
     print("env ok")
 if what in ("legacy", "all"):
     leg = nfsp_b200.BatchedLegacyEnv(n, seed=1234)
     leg.reset()
     for _ in range(passes):
-        leg.rollout(T, trace=True)
+        leg.rollout(16, trace=True)
     torch.cuda.synchronize()
     print("legacy ok")

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "neural-ficititious-self-play-in-imperfect-information-games_b200")
 
 # layout constants of csrc/nfsp_fsm.cuh
-ROW, ENTRY, INFO = 128, 32, 96
+ROW, ENTRY, INFO = 112, 32, 96
 LIVE_ROWS, ROWS = 36, 52
 DEAL_OFF = ROWS * ROW
 POL_OFF = 120 * 16
@@ -140,3 +140,62 @@ def test_image_structure(image):
     rewards = image[REWARD_OFF // 4:].view(np.float32)
     assert rewards[0] == 0.0 and not np.signbit(rewards[0])
     assert set(np.unique(np.abs(rewards))) <= {0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.5, 7.0, 7.5}
+
+
+# ------------------------------------------------------------------------------------------- legacy rules
+L_ENTRY, L_ROW, L_MAXROWS = 48, 9 * 48, 72
+L_KEY_OFF = L_MAXROWS * L_ROW
+L_DEAL_OFF = L_KEY_OFF + 4096
+L_TERM = 1 << 24
+
+
+@pytest.fixture(scope="module")
+def legacy_image(image):
+    import nfsp_b200
+
+    L = nfsp_b200.lib()
+    n = L.nfsp_legacy_fsm_image(None, 0, None)
+    assert n * 4 == L_DEAL_OFF + 120 * 16
+    buf = np.zeros(n, np.uint32)
+    rows = ctypes.c_int(0)
+    assert L.nfsp_legacy_fsm_image(buf.ctypes.data_as(ctypes.c_void_p), n, ctypes.byref(rows)) == n
+    return buf, rows.value
+
+
+def s32(v):
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def test_walking_the_legacy_image_reproduces_the_oracle_records(legacy_image):
+    """legacy_rollout_kernel's per-iteration recipe on the host against the restated leduc/env.py README loop."""
+    img, rows = legacy_image
+    assert rows == 70  # the states reachable from a fresh hand (left, pots, carried penalties)
+    n, iters, seed = 200, 40, 4321
+    b = orc.LegacyBatch(n, seed)
+    b.reset(0)
+    ref = b.rollout(1, iters)
+    key = (seed & M32, seed >> 32)
+    ended = 0
+    for g in range(n):
+        x = [int(v) for v in orc.philox((g, 0, 0, 0), key)]
+        c0, c1, G, L = words(img, L_DEAL_OFF + ((x[2] * 120) >> 32) * 16, 4)
+        six, need = 0, 0
+        for t in range(iters):
+            x = [int(v) for v in orc.philox((g, 1 + t, 0, 0), key)]
+            started = 0
+            if need:
+                c0, c1, G, L = words(img, L_DEAL_OFF + ((x[2] * 120) >> 32) * 16, 4)
+                six, started = 0, 1 << 8
+            a0, a1 = (x[0] * 3) >> 32, (x[1] * 3) >> 32
+            nx, w0, rb0, rb1, w2x, w2y, p0t, p1t, lo = words(img, six + (a0 * 3 + a1) * L_ENTRY, 9)
+            u = L * p1t - G * p0t
+            r = (s32(rb0) + u, s32(rb1) - u)
+            for p, (c, w2) in enumerate(((c0, w2x), (c1, w2y))):
+                rec, where = ref[t, g, p], "game %d iteration %d player %d" % (g, t, p)
+                assert (c, -1, (w0 >> 16) & 0xFF, (w0 >> 24) & 1) == (rec["card"], rec["pub"], rec["pot"], rec["terminal"]), where
+                assert r[p] == rec["reward"] and (w2 | started) == int(rec["misc"]), where
+            need = w0 & L_TERM
+            ended += 1 if need else 0
+            assert need or nx % L_ROW == 0 and nx // L_ROW < rows
+            six = nx
+    assert ended > n * iters // 8

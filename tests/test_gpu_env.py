@@ -224,6 +224,73 @@ def test_legacy_seeded_rollout_vs_oracle(nb, n, iters):
         assert [e["left0"][gi], e["left1"][gi], e["pot0"][gi], e["pot1"][gi]] == [o.left[0], o.left[1], o.pot[0], o.pot[1]]
 
 
+def _deal_ranks(idx):  # deck.py:35-50: ordered draw of 3 of the 6 cards -> ranks
+    i0, r = divmod(idx, 20)
+    j1, j2 = r >> 2, r & 3
+    i1 = j1 + (j1 >= i0)
+    lo, hi = min(i0, i1), max(i0, i1)
+    i2 = j2 + (j2 >= lo)
+    i2 += i2 >= hi
+    return i0 >> 1, i1 >> 1, i2 >> 1
+
+
+def test_legacy_rollout_from_hand_stepped_states(nb, golden_dir):
+    """Hands stepped by hand in the fuzz fixture's call orders (terminal flags and accumulated rewards a rollout can
+    never produce), THEN handed to the rollout kernel: such words are played by its packed-word path, ordinary ones by
+    the table path, and every record must equal the reference rules driven call by call on the same Philox stream."""
+    g = load(golden_dir, "fuzz_legacy_calls.npz")
+    N, K = g["op"].shape
+    seed, iters, step0 = 99, 10, 5
+    env = nb.BatchedLegacyEnv(N, seed=seed)
+    env.set_hands(g["cards"])
+    for c in range(K):
+        is_step = g["op"][:, c] == 0
+        pl = g["player"][:, c].astype(np.int8)
+        env.step(np.where(is_step, g["action"][:, c], 4).astype(np.int8), pl)
+        env.get_new_state(np.where(is_step, 2, pl).astype(np.int8), want_out=False)
+    before = _np(env.export())
+    env.step_counter = step0
+    rec = env.rollout(iters, trace=True)["raw"].cpu().numpy()
+    after = _np(env.export())
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    odd = 0
+    for gi in range(0, N, 3):
+        e = orc.LegacySingle()
+        e.reset(int(g["cards"][gi, 0]), int(g["cards"][gi, 1]))
+        for c in range(K):
+            if g["op"][gi, c] == 0:
+                e.step(int(g["action"][gi, c]), int(g["player"][gi, c]))
+            else:
+                e.get_new_state(int(g["player"][gi, c]))
+        odd += int(before["term0"][gi] | before["term1"][gi] | (before["rew0"][gi] not in (0, -1)) | (before["rew1"][gi] not in (0, -1)))
+        need = False
+        for t in range(iters):
+            x = [int(v) for v in orc.philox((gi, step0 + t, 0, 0), key)]
+            started = 0
+            if need:
+                c0, c1, _ = _deal_ranks((x[2] * 120) >> 32)
+                e.reset(c0, c1)
+                started = 1 << 8
+            a = ((x[0] * 3) >> 32, (x[1] * 3) >> 32)
+            e.step(a[0], 0)
+            e.step(a[1], 1)
+            out = [e.get_new_state(0)]
+            left0, pot0 = e.e.left[0], e.e.pot[0]
+            out.append(e.get_new_state(1))
+            for p in (0, 1):
+                w, where = int(rec[0, t, gi, p]) & 0xFFFFFFFF, "game %d iteration %d player %d" % (gi, t, p)
+                card, pub, pot, reward, term = out[p]
+                assert (w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFF, (w >> 24) & 0xFF) == (card, pub & 0xFF, pot, term), where
+                assert int(rec[1, t, gi, p]) == reward, where
+                misc = a[p] | ((e.e.left[p] + 1) << 2) | (e.e.pot[p] << 5) | started
+                assert int(rec[2, t, gi, p]) & 0xFFFFFFFF == misc, where
+            assert (left0, pot0) == (e.e.left[0], e.e.pot[0])
+            need = bool(out[0][4] | out[1][4])
+        assert [after["left0"][gi], after["left1"][gi], after["pot0"][gi], after["pot1"][gi]] == [e.e.left[0], e.e.left[1], e.e.pot[0], e.e.pot[1]]
+        assert [after["rew0"][gi], after["rew1"][gi]] == [e.e.st_reward[0], e.e.st_reward[1]]
+    assert odd > 20  # the packed-word path was exercised
+
+
 # ------------------------------------------------------------------------------- drop-in classes
 def test_dropin_newenv_single_game(nb, golden_dir):
     """leduc.newenv.Env with the reference's shapes, replaying a slice of the golden hands."""
