@@ -272,23 +272,27 @@ __device__ __noinline__ uint64_t legacy_generic_game(uint64_t w, const PhiloxKey
 // The README iteration for every game, n_iters times, with auto re-deal: one table entry per (state, a0, a1)
 // (legacy_fsm.cuh).  `image` is the table image built on the host at nfsp_env_create.
 template <bool kTrace>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 legacy_rollout_kernel(uint64_t *__restrict__ state, int64_t n, const uint32_t *__restrict__ image, const PhiloxKeys keys,
                       uint64_t game0, uint64_t step0, int n_iters, const int8_t *__restrict__ actions,
                       uint32_t *__restrict__ rec) {
-    __shared__ __align__(16) uint32_t s_tab[lfsm::kImageWords];
+    // rows and deals in shared memory; the state-key table is read once per game and launch and stays in global memory
+    __shared__ __align__(16) uint32_t s_tab[lfsm::kSharedWords];
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_tab);
-    for (int w = threadIdx.x; w < lfsm::kImageWords; w += blockDim.x) s_tab[w] = image[w] + (lfsm::is_address(w) ? base : 0u);
+    for (int w = threadIdx.x; w < lfsm::kSharedWords; w += blockDim.x) {
+        const int src = w < lfsm::kKeyOff / 4 ? w : w + lfsm::kKeys / 4;
+        s_tab[w] = image[src] + (lfsm::is_address(src) ? base : 0u);
+    }
     __syncthreads();
-    const uint8_t *s_keys = reinterpret_cast<const uint8_t *>(s_tab) + lfsm::kKeyOff;
-    const uint32_t deal_base = base + (uint32_t)lfsm::kDealOff;
+    const uint8_t *g_keys = reinterpret_cast<const uint8_t *>(image) + lfsm::kKeyOff;
+    const uint32_t deal_base = base + (uint32_t)lfsm::kKeyOff;
     const int64_t plane = (int64_t)n_iters * n;  // in uint2 records
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t game = game0 + (uint64_t)i;
         const LegacyW g{state[i]};
         // a hand that is over is re-dealt before anything is looked up: any row will do
         const int key = g.need_reset() ? -1 : lfsm::state_key(g, kPenalty);
-        const uint32_t row = g.need_reset() ? 0u : (key >= 0 ? (uint32_t)s_keys[key] : 0xFFu);
+        const uint32_t row = g.need_reset() ? 0u : (key >= 0 ? (uint32_t)__ldg(g_keys + key) : 0xFFu);
         if (row == 0xFFu) {
             state[i] = legacy_generic_game<kTrace>(g.w, keys, game, step0, n_iters, actions, rec, n, i);
             continue;

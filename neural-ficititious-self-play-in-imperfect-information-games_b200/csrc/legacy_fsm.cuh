@@ -33,6 +33,7 @@ constexpr int kKeys = 4096;
 constexpr int kDealOff = kKeyOff + kKeys;                 // 35200: deal index -> c0, c1, G, L
 constexpr int kImageBytes = kDealOff + 120 * 16;          // 37120
 constexpr int kImageWords = kImageBytes / 4;
+constexpr int kSharedWords = (kImageBytes - kKeys) / 4;   // what a CTA keeps in shared memory: rows, then deals
 constexpr uint32_t kTermBit = 1u << 24;
 constexpr uint32_t kLoMask = 0x7FFFFFF0u;  // everything of the low word but the cards and the overflow flag
 
