@@ -188,6 +188,23 @@ int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t 
  * deque positions (oldest first) mapped to ring slots. */
 int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_total, int64_t cap, int is_ring,
                         int batch, int64_t *d_idx, uint32_t *d_n_out, void *stream);
+/* sample_batch(batch) of up to NFSP_MAX_SAMPLE_REQS memories in one launch (Agent.update_strategy draws from the RL and
+ * the SL memory of a player back to back, agent.py:212-262): request m draws its positions exactly as
+ * nfsp_sample_indices(seed, call_idx, ...) does and expands the rows as nfsp_gather_rl / nfsp_gather_sl do into d_out,
+ * one contiguous block: ring (RL)  s[batch][30] a[batch][3] r[batch] s2[batch][30] t[batch]  = 65 * batch floats,
+ * reservoir (SL)  s[batch][30] a[batch][3]  = 33 * batch floats.  d_idx int64[n_reqs][batch] (storage slots, -1 beyond
+ * the records held) and d_n_out uint32[n_reqs] (rows sampled) may be NULL. */
+#define NFSP_MAX_SAMPLE_REQS 8
+typedef struct {
+    const void *d_mem;        /* ring / reservoir storage, 16-byte records */
+    const uint64_t *d_total;  /* records ever inserted (device) */
+    int64_t cap;
+    uint64_t seed, call_idx;
+    int32_t is_ring;
+    float *d_out;
+} nfsp_sample_req;
+int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, int batch, int64_t *d_idx, uint32_t *d_n_out,
+                            void *stream);
 /* gather + expand to the dense float32 batches the learner consumes (replay_buffer.py:53-59):
  * s [b][30], a [b][3] (one-hot of the stored argmax), r [b], s2 [b][30], t [b] */
 int nfsp_gather_rl(const void *d_ring, const int64_t *d_idx, int batch, float *d_s, float *d_a, float *d_r,

@@ -381,7 +381,15 @@ class SelfPlay:
         self.env.reset()
 
     def set_weights(self, weights):
-        self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
+        """The four acting nets, float32 [4, 2179] (avg0, br0, avg1, br1).  A host tensor (pinned for an asynchronous
+        copy) is copied into the device tensor this object already holds: no allocation on the step path."""
+        on_host = not (isinstance(weights, torch.Tensor) and weights.is_cuda)
+        if on_host and getattr(self, "_own_weights", False) and isinstance(weights, torch.Tensor) \
+                and weights.dtype == torch.float32 and tuple(weights.shape) == tuple(self.weights.shape):
+            self.weights.copy_(weights, non_blocking=True)
+        else:
+            self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
+            self._own_weights = on_host  # a device tensor handed in stays the caller's: never written through
         check(lib().nfsp_act_set_weights(self.env._h, _ptr(self.weights), _stream(self.device)))
 
     def forward(self, obs_masks, net_idx, tensor_cores=False):
@@ -489,16 +497,16 @@ class SelfPlay:
                 spec[name] = (o, n, (b, cols))
                 o += n
             layout.append(spec)
-            ptr = lambda name: C.c_void_p(slab.data_ptr() + 4 * spec[name][0])  # noqa: E731
+        # one launch: CTA m draws the positions of memory m and expands its rows into its block of the slab
+        reqs = (_lib.SampleReq * 4)()
+        for p in range(2):
             for k, mem in ((0, self.rl[p]), (1, self.sl[p])):
-                row = 2 * p + k
-                check(lib().nfsp_sample_indices(mem.seed, mem.sample_calls, _ptr(mem.total), mem.capacity, int(mem.is_ring),
-                                                b, C.c_void_p(idx[row].data_ptr()), C.c_void_p(cnt[row:].data_ptr()), st))
+                r = reqs[2 * p + k]
+                r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
+                r.seed, r.call_idx, r.is_ring = mem.seed, mem.sample_calls, int(mem.is_ring)
+                r.d_out = slab.data_ptr() + 4 * (p * per + k * 65 * b)
                 mem.sample_calls += 1
-            check(lib().nfsp_gather_rl(_ptr(self.rl[p].data), C.c_void_p(idx[2 * p].data_ptr()), b, ptr("s"), ptr("a"),
-                                       ptr("r"), ptr("s2"), ptr("t"), st))
-            check(lib().nfsp_gather_sl(_ptr(self.sl[p].data), C.c_void_p(idx[2 * p + 1].data_ptr()), b, ptr("sl_s"),
-                                       ptr("sl_a"), st))
+        check(lib().nfsp_sample_minibatches(reqs, 4, b, _ptr(idx), _ptr(cnt), st))
         src = slab
         if to_host:
             host.copy_(slab, non_blocking=True)

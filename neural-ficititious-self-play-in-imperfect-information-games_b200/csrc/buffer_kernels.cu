@@ -151,24 +151,22 @@ reservoir_write_kernel(uint4 *__restrict__ res, const unsigned long long *__rest
 // parallel, the "already taken" scan is a warp-parallel compare over the prefix.
 constexpr int kMaxBatch = 1024;
 
-__global__ void __launch_bounds__(kBufThreads)
-sample_kernel(uint64_t seed, uint64_t call_idx, const uint64_t *__restrict__ total_p, uint64_t cap, int is_ring,
-              int batch, int64_t *__restrict__ idx_out, uint32_t *__restrict__ n_out) {
-    __shared__ uint64_t draw[kMaxBatch];
-    __shared__ uint64_t pick[kMaxBatch];
-    const uint64_t total = *total_p;
+// draw / pick: kMaxBatch words of shared memory each; slot_out[m] (shared or global) = storage slot of sample m, -1
+// beyond the records held.  Returns the number of samples (min(count, batch)).  All threads of the CTA call it.
+template <class SlotT>
+__device__ __forceinline__ int floyd_sample(uint64_t seed, uint64_t call_idx, uint64_t total, uint64_t cap, int is_ring,
+                                            int batch, uint64_t *draw, uint64_t *pick, SlotT *slot_out) {
+    __shared__ int s_collision;
     const uint64_t count = total < cap ? total : cap;
     const int b = (uint64_t)batch < count ? batch : (int)count;
     const uint64_t lo = count - (uint64_t)b;
+    if (threadIdx.x == 0) s_collision = 0;
     for (int m = threadIdx.x; m < b; m += blockDim.x)
         draw[m] = mulhi64(buffer_u64(seed, (uint64_t)m, call_idx, STREAM_SAMPLE), lo + (uint64_t)m + 1u);
     __syncthreads();
     // Fast path: if the draws are pairwise distinct, "already taken" never fires and pick == draw (the memories
     // hold millions of records, so this is the normal case); checked with b*b/2 parallel compares.  Otherwise
     // the sequential scan below resolves the collisions exactly as Floyd's algorithm does.
-    __shared__ int s_collision;
-    if (threadIdx.x == 0) s_collision = 0;
-    __syncthreads();
     for (int m = threadIdx.x; m < b; m += blockDim.x) {
         const uint64_t t = draw[m];
         bool dup = false;
@@ -193,9 +191,78 @@ sample_kernel(uint64_t seed, uint64_t call_idx, const uint64_t *__restrict__ tot
     for (int m = threadIdx.x; m < batch; m += blockDim.x) {
         int64_t slot = -1;
         if (m < b) slot = is_ring ? (int64_t)((head + pick[m]) % cap) : (int64_t)pick[m];
-        idx_out[m] = slot;
+        slot_out[m] = (SlotT)slot;
     }
+    return b;
+}
+
+__global__ void __launch_bounds__(kBufThreads)
+sample_kernel(uint64_t seed, uint64_t call_idx, const uint64_t *__restrict__ total_p, uint64_t cap, int is_ring,
+              int batch, int64_t *__restrict__ idx_out, uint32_t *__restrict__ n_out) {
+    __shared__ uint64_t draw[kMaxBatch];
+    __shared__ uint64_t pick[kMaxBatch];
+    const int b = floyd_sample(seed, call_idx, *total_p, cap, is_ring, batch, draw, pick, idx_out);
     if (threadIdx.x == 0 && n_out) *n_out = (uint32_t)b;
+}
+
+// one output element of a sampled RL / SL row (the dense views of replay_buffer.py:46-59 / ReservoirBuffer.py:33-43)
+__device__ __forceinline__ void expand_rl(const uint4 rec, int row, int col, float *__restrict__ s, float *__restrict__ a,
+                                          float *__restrict__ r, float *__restrict__ s2, float *__restrict__ t) {
+    if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
+    else if (col < 60) s2[row * 30 + (col - 30)] = (float)((rec.y >> (col - 30)) & 1u);
+    else if (col < 63) a[row * 3 + (col - 60)] = ((rec.w & 0xFFu) == (uint32_t)(col - 60)) ? 1.f : 0.f;
+    else if (col == 63) r[row] = __uint_as_float(rec.z);
+    else t[row] = (float)((rec.w >> 8) & 0xFFu);
+}
+__device__ __forceinline__ void expand_sl(const uint4 rec, int row, int col, float *__restrict__ s, float *__restrict__ a) {
+    if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
+    else a[row * 3 + (col - 30)] = __uint_as_float(col == 30 ? rec.y : (col == 31 ? rec.z : rec.w));
+}
+
+// sample_batch of several memories in ONE launch: blockIdx.x = memory.  A CTA draws the positions of its memory, fetches
+// its share of the sampled records once (one random 16-byte read per row, all in flight together) and expands them
+// into out[m] -- an RL block is s[b][30] a[b][3] r[b] s2[b][30] t[b], an SL block s[b][30] a[b][3] (b = batch).  The
+// rows of a memory are split over gridDim.y CTAs; each repeats the (cheap) draw.
+struct SampleReqs {
+    const uint4 *mem[NFSP_MAX_SAMPLE_REQS];
+    const uint64_t *total[NFSP_MAX_SAMPLE_REQS];
+    uint64_t cap[NFSP_MAX_SAMPLE_REQS], seed[NFSP_MAX_SAMPLE_REQS], call_idx[NFSP_MAX_SAMPLE_REQS];
+    float *out[NFSP_MAX_SAMPLE_REQS];
+    int is_ring[NFSP_MAX_SAMPLE_REQS];
+};
+__global__ void __launch_bounds__(kBufThreads)
+sample_gather_kernel(const SampleReqs R, int batch, int64_t *__restrict__ idx_out, uint32_t *__restrict__ n_out) {
+    __shared__ uint64_t draw[kMaxBatch];
+    __shared__ uint64_t pick[kMaxBatch];
+    __shared__ int64_t slot[kMaxBatch];
+    __shared__ uint4 s_rec[kMaxBatch];
+    const int m = blockIdx.x;
+    const int b = floyd_sample(R.seed[m], R.call_idx[m], *R.total[m], R.cap[m], R.is_ring[m], batch, draw, pick, slot);
+    __syncthreads();
+    const int per = (batch + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int row0 = (int)blockIdx.y * per, row1 = min(batch, row0 + per);
+    if (threadIdx.x == 0 && blockIdx.y == 0 && n_out) n_out[m] = (uint32_t)b;
+    const uint4 *mem = R.mem[m];
+    for (int k = row0 + threadIdx.x; k < row1; k += blockDim.x) {
+        if (idx_out) idx_out[(int64_t)m * batch + k] = slot[k];
+        s_rec[k] = slot[k] >= 0 ? mem[slot[k]] : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    float *o = R.out[m];
+    const int rows = max(row1 - row0, 0);
+    if (R.is_ring[m]) {
+        float *s = o, *a = s + 30 * batch, *r = a + 3 * batch, *s2 = r + batch, *t = s2 + 30 * batch;
+        for (int e = threadIdx.x; e < rows * 65; e += blockDim.x) {
+            const int row = row0 + e / 65, col = e % 65;
+            expand_rl(s_rec[row], row, col, s, a, r, s2, t);
+        }
+    } else {
+        float *s = o, *a = s + 30 * batch;
+        for (int e = threadIdx.x; e < rows * 33; e += blockDim.x) {
+            const int row = row0 + e / 33, col = e % 33;
+            expand_sl(s_rec[row], row, col, s, a);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kBufThreads)
@@ -206,12 +273,7 @@ gather_rl_kernel(const uint4 *__restrict__ ring, const int64_t *__restrict__ idx
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int row = e / 65, col = e - row * 65;
         const int64_t slot = idx[row];
-        const uint4 rec = slot >= 0 ? ring[slot] : make_uint4(0, 0, 0, 0);
-        if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
-        else if (col < 60) s2[row * 30 + (col - 30)] = (float)((rec.y >> (col - 30)) & 1u);
-        else if (col < 63) a[row * 3 + (col - 60)] = ((rec.w & 0xFFu) == (uint32_t)(col - 60)) ? 1.f : 0.f;
-        else if (col == 63) r[row] = __uint_as_float(rec.z);
-        else t[row] = (float)((rec.w >> 8) & 0xFFu);
+        expand_rl(slot >= 0 ? ring[slot] : make_uint4(0, 0, 0, 0), row, col, s, a, r, s2, t);
     }
 }
 
@@ -222,9 +284,7 @@ gather_sl_kernel(const uint4 *__restrict__ res, const int64_t *__restrict__ idx,
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int row = e / 33, col = e - row * 33;
         const int64_t slot = idx[row];
-        const uint4 rec = slot >= 0 ? res[slot] : make_uint4(0, 0, 0, 0);
-        if (col < 30) s[row * 30 + col] = (float)((rec.x >> col) & 1u);
-        else a[row * 3 + (col - 30)] = __uint_as_float(col == 30 ? rec.y : (col == 31 ? rec.z : rec.w));
+        expand_sl(slot >= 0 ? res[slot] : make_uint4(0, 0, 0, 0), row, col, s, a);
     }
 }
 
@@ -288,6 +348,26 @@ extern "C" int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint6
     NFSP_CHECK_ARG(batch >= 1 && batch <= kMaxBatch, "batch must be in [1,%d]", kMaxBatch);
     sample_kernel<<<1, kBufThreads, 0, (cudaStream_t)stream>>>(seed, call_idx, d_total, (uint64_t)cap, is_ring, batch,
                                                                d_idx, d_n_out);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, int batch, int64_t *d_idx, uint32_t *d_n_out,
+                                       void *stream) {
+    NFSP_CHECK_ARG(reqs && n_reqs >= 1 && n_reqs <= NFSP_MAX_SAMPLE_REQS, "1..%d requests", NFSP_MAX_SAMPLE_REQS);
+    NFSP_CHECK_ARG(batch >= 1 && batch <= kMaxBatch, "batch must be in [1,%d]", kMaxBatch);
+    SampleReqs R;
+    for (int m = 0; m < n_reqs; ++m) {
+        NFSP_CHECK_ARG(reqs[m].d_mem && reqs[m].d_total && reqs[m].d_out && reqs[m].cap > 0, "bad request %d", m);
+        R.mem[m] = (const uint4 *)reqs[m].d_mem;
+        R.total[m] = reqs[m].d_total;
+        R.cap[m] = (uint64_t)reqs[m].cap;
+        R.seed[m] = reqs[m].seed;
+        R.call_idx[m] = reqs[m].call_idx;
+        R.out[m] = reqs[m].d_out;
+        R.is_ring[m] = reqs[m].is_ring;
+    }
+    sample_gather_kernel<<<dim3((unsigned)n_reqs, 8u, 1u), kBufThreads, 0, (cudaStream_t)stream>>>(R, batch, d_idx, d_n_out);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

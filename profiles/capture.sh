@@ -10,6 +10,6 @@ python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_plain.json 2> $out/${ta
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_under_ncu.log 2>&1
 python profiles/run_hot_path.py all 2 > $out/${tag}_hot_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "$K" -c 24 -f -o $out/${tag}_prof \
+ncu --set full --clock-control none --import-source on -k "$K" -c 40 -f -o $out/${tag}_prof \
     python profiles/run_hot_path.py all 2 > $out/${tag}_hot_under_ncu.log 2>&1
 tail -n 2 $out/${tag}_hot_plain.log; tail -n 2 $out/${tag}_hot_under_ncu.log

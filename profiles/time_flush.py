@@ -26,6 +26,8 @@ for it in range(8):
         marks.append(ev()); marks[-1].record(); names.append("ring%d" % p)
         sp.sl[p].insert(sp.stage_sl[p], sp.counts[2 + p], sp.cap_sl)
         marks.append(ev()); marks[-1].record(); names.append("reservoir%d" % p)
+    sp.sample_minibatches(256)
+    marks.append(ev()); marks[-1].record(); names.append("sample_4x256")
     torch.cuda.synchronize()
     if it >= 3:
         for k, name in enumerate(names):
