@@ -47,6 +47,7 @@ __device__ __forceinline__ void batch_prefix(const Batch &B, uint32_t seg, uint6
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------
+constexpr int kRingUnroll = 4;
 // slot = ticket % cap; of a batch larger than the ring only the last `cap` records survive (the others
 // would be evicted by popleft(), replay_buffer.py:40).
 __global__ void __launch_bounds__(kBufThreads)
@@ -59,9 +60,28 @@ ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__res
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t idx = before + i;
-        if (idx >= first) ring[(total + idx) % cap] = src[i];
+    // slot of batch index idx = (total + idx) % cap without a 64-bit division per record: head = total % cap once, then
+    // one conditional subtraction (a second reduction only for batches larger than the ring).  kRingUnroll records per
+    // thread and iteration, the loads issued before the first store, so several 16-byte reads are in flight per thread.
+    const uint64_t head = total % cap;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kRingUnroll) {
+        uint4 v[kRingUnroll];
+#pragma unroll
+        for (int u = 0; u < kRingUnroll; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            if (i < cnt) v[u] = src[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kRingUnroll; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride, idx = before + i;
+            if (i < cnt && idx >= first) {
+                uint64_t slot = head + idx;
+                if (slot >= cap) slot -= cap;
+                if (slot >= cap) slot %= cap;
+                ring[slot] = v[u];
+            }
+        }
     }
 }
 
