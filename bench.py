@@ -422,7 +422,7 @@ def run_gpu(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 11 * args.steps,
+            "gpu_launches": 6 * args.steps,  # rollout + (ring insert, commit) + (reservoir stamp, write, commit), both players per launch
             "roofline": roofline, "cpu_baseline": cpu,
             "extra": {"env_only": {"kernel": "nfsp_step_fsm_kernel", "transitions_per_sec": env_rate,
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,

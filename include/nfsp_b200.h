@@ -182,6 +182,24 @@ int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d
  * resolved as in the sequential algorithm (largest ticket wins) via d_stamp uint64[cap]. */
 int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp, const void *d_recs,
                           uint32_t *d_counts, int n_segments, int64_t seg_cap, uint64_t seed, int mode, void *stream);
+/* The same two calls for several memories at once (the two players' rings in one launch, their reservoirs in another):
+ * request k is exactly nfsp_ring_insert / nfsp_reservoir_insert with these arguments.  d_stamp, seed, mode are read for
+ * reservoirs only. */
+#define NFSP_MAX_INSERT_REQS 4
+typedef struct {
+    void *d_mem;
+    int64_t cap;
+    uint64_t *d_total;
+    uint64_t *d_stamp;
+    const void *d_recs;
+    uint32_t *d_counts;
+    int32_t n_segments;
+    int64_t seg_cap;
+    uint64_t seed;
+    int32_t mode;
+} nfsp_insert_req;
+int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
+int nfsp_reservoir_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 /* random.sample(buffer, batch) (replay_buffer.py:46-51, ReservoirBuffer.py:33-37): `batch`
  * distinct positions (Floyd's algorithm, Philox keyed by (seed; call_idx)); d_idx int64[batch]
  * receives storage slots, d_n_out the number drawn = min(batch, size).  is_ring: positions are

@@ -26,7 +26,7 @@ SYMBOLS = [
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
-    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
+    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_sgd_apply",
 ]
 
@@ -35,6 +35,12 @@ class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
                 ("n_segments", C.c_int32), ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
                 ("d_forced_vec", C.c_void_p), ("variant", C.c_int32)]
+
+
+class InsertReq(C.Structure):
+    _fields_ = [("d_mem", C.c_void_p), ("cap", C.c_int64), ("d_total", C.c_void_p), ("d_stamp", C.c_void_p),
+                ("d_recs", C.c_void_p), ("d_counts", C.c_void_p), ("n_segments", C.c_int32), ("seg_cap", C.c_int64),
+                ("seed", C.c_uint64), ("mode", C.c_int32)]
 
 
 class SampleReq(C.Structure):
@@ -102,6 +108,8 @@ def lib():
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
     L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp]
     L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp]
+    L.nfsp_ring_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
+    L.nfsp_reservoir_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.nfsp_sample_minibatches.argtypes = [C.POINTER(SampleReq), C.c_int, C.c_int, vp, vp, vp]
     L.nfsp_gather_rl.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]

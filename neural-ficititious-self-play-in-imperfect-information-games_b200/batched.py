@@ -409,14 +409,19 @@ class SelfPlay:
         tiles with the accumulator in TMEM) or None = self.variant."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
-        io = _lib.RolloutIO()
-        for p in range(2):
-            io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
-        io.cap_rl, io.cap_sl, io.n_segments = self.cap_rl, self.cap_sl, self.n_seg
-        io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
+        want_debug = debug or forced_vec is not None
+        io = None if want_debug else getattr(self, "_io", None)  # the production argument block is built once
+        if io is None:
+            io = _lib.RolloutIO()
+            for p in range(2):
+                io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
+            io.cap_rl, io.cap_sl, io.n_segments = self.cap_rl, self.cap_sl, self.n_seg
+            io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
+            if not want_debug:
+                self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
         dbg = None
-        if debug or forced_vec is not None:
+        if want_debug:
             tr = torch.empty((3, n_steps, self.n), dtype=torch.int32, device=self.device)
             vec = torch.empty((n_steps, self.n, 3), dtype=torch.float32, device=self.device)
             fv = _as(forced_vec, torch.float32, self.device, (n_steps, self.n, 3))
@@ -456,12 +461,25 @@ class SelfPlay:
             self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
         self._fork.record(main)
         self._side.wait_event(self._fork)
-        with torch.cuda.stream(self._side):
-            for p in range(2):
-                self.sl[p].insert(self.stage_sl[p], self.counts[2 + p], self.cap_sl)
+
+        if not hasattr(self, "_flush_reqs"):  # pointers and geometry never change: the request blocks are built once
+            def reqs(mems, stages, rows, seg_cap):
+                arr = (_lib.InsertReq * 2)()
+                for p in range(2):
+                    r, mem = arr[p], mems[p]
+                    r.d_mem, r.cap, r.d_total = mem.data.data_ptr(), mem.capacity, mem.total.data_ptr()
+                    r.d_stamp = mem.stamp.data_ptr() if hasattr(mem, "stamp") else None
+                    r.d_recs, r.d_counts = stages[p].data_ptr(), self.counts[rows[p]].data_ptr()
+                    r.n_segments, r.seg_cap, r.seed, r.mode = self.n_seg, seg_cap, mem.seed, getattr(mem, "mode", 0)
+                return arr
+
+            self._flush_reqs = (reqs(self.sl, self.stage_sl, (2, 3), self.cap_sl), reqs(self.rl, self.stage_rl, (0, 1), self.cap_rl))
+        res_reqs, ring_reqs = self._flush_reqs
+        with torch.cuda.stream(self._side):  # both players' reservoirs: stamp, write, commit
+            check(lib().nfsp_reservoir_insert_multi(res_reqs, 2, _stream(self.device)))
             self._join.record(self._side)
-        for p in range(2):
-            self.rl[p].insert(self.stage_rl[p], self.counts[p], self.cap_rl)
+        # both players' rings: insert, commit
+        check(lib().nfsp_ring_insert_multi(ring_reqs, 2, _stream(self.device)))
         main.wait_event(self._join)
 
     def sample_minibatches(self, batch=256, to_host=False):
@@ -480,39 +498,41 @@ class SelfPlay:
                           torch.zeros(4, dtype=torch.int32, device=self.device))
         slab, host, idx, cnt = cache[key]
         st = _stream(self.device)
-
-        def cut(base, n, shape):
-            return base + n, (base, n, shape)
-
-        layout = []
-        for p in range(2):
-            o = p * per
-            spec = {}
-            for name, cols in (("s", 30), ("a", 3), ("r", 0), ("s2", 30), ("t", 0)):
-                n = b * max(cols, 1)
-                spec[name] = (o, n, (b, cols) if cols else (b,))
-                o += n
-            for name, cols in (("sl_s", 30), ("sl_a", 3)):
-                n = b * cols
-                spec[name] = (o, n, (b, cols))
-                o += n
-            layout.append(spec)
-        # one launch: CTA m draws the positions of memory m and expands its rows into its block of the slab
-        reqs = (_lib.SampleReq * 4)()
+        lkey = ("layout", b)
+        if lkey not in cache:
+            layout = []
+            for p in range(2):
+                o = p * per
+                spec = {}
+                for name, cols in (("s", 30), ("a", 3), ("r", 0), ("s2", 30), ("t", 0)):
+                    n = b * max(cols, 1)
+                    spec[name] = (o, n, (b, cols) if cols else (b,))
+                    o += n
+                for name, cols in (("sl_s", 30), ("sl_a", 3)):
+                    n = b * cols
+                    spec[name] = (o, n, (b, cols))
+                    o += n
+                layout.append(spec)
+            # one launch: CTAs of memory m draw its positions and expand its rows into its block of the slab
+            reqs = (_lib.SampleReq * 4)()
+            for p in range(2):
+                for k, mem in ((0, self.rl[p]), (1, self.sl[p])):
+                    r = reqs[2 * p + k]
+                    r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
+                    r.seed, r.is_ring = mem.seed, int(mem.is_ring)
+                    r.d_out = slab.data_ptr() + 4 * (p * per + k * 65 * b)
+            views = {src is host: [{k: src[o:o + n].view(shape) for k, (o, n, shape) in spec.items()} for spec in layout]
+                     for src in (slab, host)}
+            cache[lkey] = (reqs, views)
+        reqs, views = cache[lkey]
         for p in range(2):
             for k, mem in ((0, self.rl[p]), (1, self.sl[p])):
-                r = reqs[2 * p + k]
-                r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
-                r.seed, r.call_idx, r.is_ring = mem.seed, mem.sample_calls, int(mem.is_ring)
-                r.d_out = slab.data_ptr() + 4 * (p * per + k * 65 * b)
+                reqs[2 * p + k].call_idx = mem.sample_calls
                 mem.sample_calls += 1
         check(lib().nfsp_sample_minibatches(reqs, 4, b, _ptr(idx), _ptr(cnt), st))
-        src = slab
         if to_host:
             host.copy_(slab, non_blocking=True)
-            src = host
-        views = [{k: src[o:o + n].view(shape) for k, (o, n, shape) in spec.items()} for spec in layout]
-        return views, src
+        return views[bool(to_host)], (host if to_host else slab)
 
     def read_stats(self):
         v = self.stats.cpu().numpy()

@@ -46,20 +46,39 @@ __device__ __forceinline__ void batch_prefix(const Batch &B, uint32_t seg, uint6
     all = s_all;
 }
 
+// ---- memories of one launch ----------------------------------------------------------------------
+// The insert kernels take up to NFSP_MAX_INSERT_REQS memories at once (blockIdx.z = memory): the two players' rings
+// travel in one launch, their reservoirs in another -- at 64k games the flush is launch latency, not bandwidth.
+struct Mem {
+    uint4 *data;
+    unsigned long long *stamp;  // reservoirs only
+    uint64_t cap;
+    uint64_t *total;
+    Batch B;
+    uint64_t seed;
+    int mode;
+};
+struct MemSet {
+    Mem m[NFSP_MAX_INSERT_REQS];
+};
+
 // ---- K3 ------------------------------------------------------------------------------------------
 constexpr int kRingUnroll = 4;
 // slot = ticket % cap; of a batch larger than the ring only the last `cap` records survive (the others
 // would be evicted by popleft(), replay_buffer.py:40).
-__global__ void __launch_bounds__(kBufThreads)
-ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__restrict__ total_p, const Batch B) {
+__global__ void __launch_bounds__(kBufThreads) ring_insert_kernel(const MemSet S) {
+    const Mem &M = S.m[blockIdx.z];
+    const Batch &B = M.B;
     const uint32_t seg = blockIdx.y;
+    if (seg >= B.n_seg) return;
     uint64_t before, m;
     batch_prefix(B, seg, before, m);
-    const uint64_t total = *total_p;
+    const uint64_t total = *M.total, cap = M.cap;
     const uint64_t first = m > cap ? m - cap : 0;
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
+    uint4 *ring = M.data;
     // slot of batch index idx = (total + idx) % cap without a 64-bit division per record: head = total % cap once, then
     // one conditional subtraction (a second reduction only for batches larger than the ring).  kRingUnroll records per
     // thread and iteration, the loads issued before the first store, so several 16-byte reads are in flight per thread.
@@ -85,13 +104,15 @@ ring_insert_kernel(uint4 *__restrict__ ring, uint64_t cap, const uint64_t *__res
     }
 }
 
-// runs after the insert kernel(s) of a batch: total += n, staged counts cleared for the next rollout
-__global__ void __launch_bounds__(kBufThreads) commit_kernel(uint64_t *total_p, uint32_t *counts, const Batch B) {
+// runs after the insert kernel(s) of a batch, one CTA per memory: total += n, staged counts cleared for the next rollout
+__global__ void __launch_bounds__(kBufThreads) commit_kernel(const MemSet S) {
+    const Mem &M = S.m[blockIdx.x];
     uint64_t before, m;
-    batch_prefix(B, 0, before, m);
+    batch_prefix(M.B, 0, before, m);
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < B.n_seg; k += blockDim.x) counts[k] = 0;
-    if (threadIdx.x == 0) *total_p += m;
+    uint32_t *counts = const_cast<uint32_t *>(M.B.counts);
+    for (uint32_t k = threadIdx.x; k < M.B.n_seg; k += blockDim.x) counts[k] = 0;
+    if (threadIdx.x == 0) *M.total += m;
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------
@@ -112,13 +133,16 @@ __device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket
 constexpr int kResUnroll = 4;
 
 // pass 1: every accepted record stamps its slot with ticket+1; atomicMax keeps the latest
-__global__ void __launch_bounds__(kBufThreads)
-reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, const uint64_t *__restrict__ total_p,
-                       const Batch B, uint64_t seed, int mode) {
+__global__ void __launch_bounds__(kBufThreads) reservoir_stamp_kernel(const MemSet S) {
+    const Mem &M = S.m[blockIdx.z];
+    const Batch &B = M.B;
     const uint32_t seg = blockIdx.y;
+    if (seg >= B.n_seg) return;
     uint64_t before, m;
     batch_prefix(B, seg, before, m);
-    const uint64_t total = *total_p;
+    const uint64_t total = *M.total, cap = M.cap, seed = M.seed;
+    const int mode = M.mode;
+    unsigned long long *stamp = M.stamp;
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -136,13 +160,17 @@ reservoir_stamp_kernel(unsigned long long *__restrict__ stamp, uint64_t cap, con
 }
 
 // pass 2: the record whose ticket owns the stamp writes the payload (== sequential order of adds)
-__global__ void __launch_bounds__(kBufThreads)
-reservoir_write_kernel(uint4 *__restrict__ res, const unsigned long long *__restrict__ stamp, uint64_t cap,
-                       const uint64_t *__restrict__ total_p, const Batch B, uint64_t seed, int mode) {
+__global__ void __launch_bounds__(kBufThreads) reservoir_write_kernel(const MemSet S) {
+    const Mem &M = S.m[blockIdx.z];
+    const Batch &B = M.B;
     const uint32_t seg = blockIdx.y;
+    if (seg >= B.n_seg) return;
     uint64_t before, m;
     batch_prefix(B, seg, before, m);
-    const uint64_t total = *total_p;
+    const uint64_t total = *M.total, cap = M.cap, seed = M.seed;
+    const int mode = M.mode;
+    const unsigned long long *stamp = M.stamp;
+    uint4 *res = M.data;
     uint64_t cnt = B.counts[seg];
     if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
@@ -184,27 +212,35 @@ __device__ __forceinline__ int floyd_sample(uint64_t seed, uint64_t call_idx, ui
     for (int m = threadIdx.x; m < b; m += blockDim.x)
         draw[m] = mulhi64(buffer_u64(seed, (uint64_t)m, call_idx, STREAM_SAMPLE), lo + (uint64_t)m + 1u);
     __syncthreads();
-    // Fast path: if the draws are pairwise distinct, "already taken" never fires and pick == draw (the memories
-    // hold millions of records, so this is the normal case); checked with b*b/2 parallel compares.  Otherwise
-    // the sequential scan below resolves the collisions exactly as Floyd's algorithm does.
+    // Floyd: step m takes t = draw[m] unless t was taken before, else lo + m (always new).  Every earlier draw is in the
+    // set whether it was taken or replaced, so "taken before" = (some earlier draw equals t) or (t = lo + k for an
+    // earlier step k that was replaced).  The first term is b*b/2 independent compares; the second refers to ONE
+    // earlier step, k = t - lo < m, so the replaced flags are the least fixpoint of dup[m] |= dup[draw[m] - lo], reached
+    // by a few parallel sweeps (flags only turn on, references only point backwards) -- same picks as the sequential
+    // algorithm, no sequential scan even when draws collide (a 200 000-record ring and 256 draws: 15 % of the calls).
+    __shared__ unsigned char s_dup[kMaxBatch];
     for (int m = threadIdx.x; m < b; m += blockDim.x) {
         const uint64_t t = draw[m];
         bool dup = false;
         for (int k = 0; k < m; ++k) dup |= (draw[k] == t);
         if (dup) s_collision = 1;
-        pick[m] = t;
+        s_dup[m] = dup;
     }
     __syncthreads();
-    if (s_collision && threadIdx.x < 32) {
-        for (int m = 0; m < b; ++m) {
+    while (s_collision) {  // uniform: every thread reads the same flag between barriers
+        __syncthreads();
+        if (threadIdx.x == 0) s_collision = 0;
+        __syncthreads();
+        for (int m = threadIdx.x; m < b; m += blockDim.x) {
             const uint64_t t = draw[m];
-            bool dup = false;
-            for (int k = threadIdx.x; k < m; k += 32) dup |= (pick[k] == t);
-            dup = __any_sync(0xFFFFFFFFu, dup);
-            if (threadIdx.x == 0) pick[m] = dup ? lo + (uint64_t)m : t;
-            __syncwarp();
+            if (!s_dup[m] && t >= lo && t - lo < (uint64_t)m && s_dup[t - lo]) {
+                s_dup[m] = 1;
+                s_collision = 1;
+            }
         }
+        __syncthreads();
     }
+    for (int m = threadIdx.x; m < b; m += blockDim.x) pick[m] = s_dup[m] ? lo + (uint64_t)m : draw[m];
     __syncthreads();
     // deque position (oldest first) -> storage slot
     const uint64_t head = (is_ring && total >= cap) ? total % cap : 0;
@@ -308,58 +344,95 @@ gather_sl_kernel(const uint4 *__restrict__ res, const int64_t *__restrict__ idx,
     }
 }
 
-static dim3 insert_grid(int64_t seg_cap, int n_seg) {
+static dim3 insert_grid(int64_t seg_cap, int n_seg, int n_mems) {
     int64_t g = (seg_cap + kBufThreads - 1) / kBufThreads;
-    const int64_t lim = n_seg >= 148 * 8 ? 1 : (148 * 8 + n_seg - 1) / n_seg;  // about 8 CTAs per SM in total
+    const int64_t rows = (int64_t)n_seg * n_mems;
+    const int64_t lim = rows >= 148 * 8 ? 1 : (148 * 8 + rows - 1) / rows;  // about 8 CTAs per SM in total
     if (g > lim) g = lim;
     if (g < 1) g = 1;
-    return dim3((unsigned)g, (unsigned)n_seg, 1);
+    return dim3((unsigned)g, (unsigned)n_seg, (unsigned)n_mems);
 }
 
 }  // namespace nfsp
 
 using namespace nfsp;
 
-static int check_batch(const void *d_recs, const uint32_t *d_counts, int n_segments, int64_t seg_cap) {
-    NFSP_CHECK_ARG(d_recs && d_counts, "null staged batch");
-    NFSP_CHECK_ARG(n_segments >= 1 && n_segments <= 65535 && seg_cap >= 0, "bad segment geometry");
+// validates the requests and fills the kernels' argument; *seg_cap_max / *n_seg_max size the grid
+static int make_memset(const nfsp_insert_req *reqs, int n, bool reservoir, MemSet &S, int64_t *seg_cap_max, int *n_seg_max) {
+    NFSP_CHECK_ARG(reqs && n >= 1 && n <= NFSP_MAX_INSERT_REQS, "1..%d memories per call", NFSP_MAX_INSERT_REQS);
+    *seg_cap_max = 0;
+    *n_seg_max = 0;
+    for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) S.m[k] = Mem{};
+    for (int k = 0; k < n; ++k) {
+        const nfsp_insert_req &r = reqs[k];
+        NFSP_CHECK_ARG(r.d_mem && r.d_total && r.cap > 0, "bad memory %d", k);
+        NFSP_CHECK_ARG(r.d_recs && r.d_counts, "null staged batch %d", k);
+        NFSP_CHECK_ARG(r.n_segments >= 1 && r.n_segments <= 65535 && r.seg_cap >= 0, "bad segment geometry %d", k);
+        if (reservoir) {
+            NFSP_CHECK_ARG(r.d_stamp, "reservoir %d has no stamp array", k);
+            NFSP_CHECK_ARG(r.mode == 0 || r.mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
+        }
+        S.m[k].data = (uint4 *)r.d_mem;
+        S.m[k].stamp = (unsigned long long *)r.d_stamp;
+        S.m[k].cap = (uint64_t)r.cap;
+        S.m[k].total = r.d_total;
+        S.m[k].B = Batch{(const uint4 *)r.d_recs, r.d_counts, (uint32_t)r.n_segments, (uint64_t)r.seg_cap};
+        S.m[k].seed = r.seed;
+        S.m[k].mode = r.mode;
+        if (r.seg_cap > *seg_cap_max) *seg_cap_max = r.seg_cap;
+        if (r.n_segments > *n_seg_max) *n_seg_max = r.n_segments;
+    }
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
+    MemSet S;
+    int64_t seg_cap;
+    int n_seg;
+    const int rc = make_memset(reqs, n, false, S, &seg_cap, &n_seg);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ring_insert_kernel<<<insert_grid(seg_cap, n_seg, n), kBufThreads, 0, st>>>(S);
+    NFSP_LAUNCH_CHECK();
+    commit_kernel<<<n, kBufThreads, 0, st>>>(S);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_reservoir_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
+    MemSet S;
+    int64_t seg_cap;
+    int n_seg;
+    const int rc = make_memset(reqs, n, true, S, &seg_cap, &n_seg);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = insert_grid(seg_cap, n_seg, n);
+    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>(S);
+    NFSP_LAUNCH_CHECK();
+    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>(S);
+    NFSP_LAUNCH_CHECK();
+    commit_kernel<<<n, kBufThreads, 0, st>>>(S);
+    NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }
 
 extern "C" int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
                                 int n_segments, int64_t seg_cap, void *stream) {
-    NFSP_CHECK_ARG(d_ring && d_total && cap > 0, "bad arguments");
-    const int rc = check_batch(d_recs, d_counts, n_segments, seg_cap);
-    if (rc != NFSP_OK) return rc;
-    if (seg_cap == 0) return NFSP_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const Batch B{(const uint4 *)d_recs, d_counts, (uint32_t)n_segments, (uint64_t)seg_cap};
-    ring_insert_kernel<<<insert_grid(seg_cap, n_segments), kBufThreads, 0, st>>>((uint4 *)d_ring, (uint64_t)cap, d_total, B);
-    NFSP_LAUNCH_CHECK();
-    commit_kernel<<<1, kBufThreads, 0, st>>>(d_total, d_counts, B);
-    NFSP_LAUNCH_CHECK();
-    return NFSP_OK;
+    nfsp_insert_req r{};
+    r.d_mem = d_ring; r.cap = cap; r.d_total = d_total; r.d_recs = d_recs; r.d_counts = d_counts;
+    r.n_segments = n_segments; r.seg_cap = seg_cap;
+    return nfsp_ring_insert_multi(&r, 1, stream);
 }
 
 extern "C" int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp,
                                      const void *d_recs, uint32_t *d_counts, int n_segments, int64_t seg_cap,
                                      uint64_t seed, int mode, void *stream) {
-    NFSP_CHECK_ARG(d_res && d_total && d_stamp && cap > 0, "bad arguments");
-    NFSP_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
-    const int rc = check_batch(d_recs, d_counts, n_segments, seg_cap);
-    if (rc != NFSP_OK) return rc;
-    if (seg_cap == 0) return NFSP_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const Batch B{(const uint4 *)d_recs, d_counts, (uint32_t)n_segments, (uint64_t)seg_cap};
-    const dim3 grid = insert_grid(seg_cap, n_segments);
-    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>((unsigned long long *)d_stamp, (uint64_t)cap, d_total, B, seed, mode);
-    NFSP_LAUNCH_CHECK();
-    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>((uint4 *)d_res, (const unsigned long long *)d_stamp, (uint64_t)cap,
-                                                         d_total, B, seed, mode);
-    NFSP_LAUNCH_CHECK();
-    commit_kernel<<<1, kBufThreads, 0, st>>>(d_total, d_counts, B);
-    NFSP_LAUNCH_CHECK();
-    return NFSP_OK;
+    nfsp_insert_req r{};
+    r.d_mem = d_res; r.cap = cap; r.d_total = d_total; r.d_stamp = d_stamp; r.d_recs = d_recs; r.d_counts = d_counts;
+    r.n_segments = n_segments; r.seg_cap = seg_cap; r.seed = seed; r.mode = mode;
+    return nfsp_reservoir_insert_multi(&r, 1, stream);
 }
 
 extern "C" int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_total, int64_t cap,

@@ -1,7 +1,7 @@
 """Where the flush of a bench step goes: rollout(8) for 1M games, then each insert timed on its own with CUDA
 events (warm, L2 not flushed: the staged records are as the rollout left them).
 
-    python profiles/time_flush.py
+    python profiles/time_flush.py [n_games] [rl_capacity] [sl_capacity]
 """
 import os
 import sys
@@ -11,8 +11,10 @@ import torch  # noqa: E402
 
 import nfsp_b200  # noqa: E402
 
-n, T = 1 << 20, 8
-sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T)
+n, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20), 8
+rl_cap = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 25
+sl_cap = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 23
+sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=rl_cap, sl_capacity=sl_cap, max_steps_per_call=T)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 acc = {}
 for it in range(8):
@@ -28,6 +30,10 @@ for it in range(8):
         marks.append(ev()); marks[-1].record(); names.append("reservoir%d" % p)
     sp.sample_minibatches(256)
     marks.append(ev()); marks[-1].record(); names.append("sample_4x256")
+    sp.rollout(T, insert=False)
+    marks.append(ev()); marks[-1].record(); names.append("rollout_again")
+    sp.flush()
+    marks.append(ev()); marks[-1].record(); names.append("flush_two_streams")
     torch.cuda.synchronize()
     if it >= 3:
         for k, name in enumerate(names):
