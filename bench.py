@@ -405,7 +405,13 @@ def run_gpu(args):
                 "kernel_ms_per_launch": ker_ms / args.steps, "useful_tflops": kernel_rate * 4224 / 1e12}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get("rollout_kernel_bytes_per_launch")
+        tf = json.load(open(traffic_file))
+        roofline["traffic"] = tf.get("rollout_kernel_bytes_per_launch")
+        if args.variant != "tcgen05" and "rollout_kernel_ncu" in tf:
+            # what really bounds the kernel (ncu, not measured in this run): each decision has to bring 2 x 256 B of
+            # first-layer rows and 768 B of second-layer weights from shared memory into registers
+            roofline["limiter"] = "shared-memory register-fill bandwidth, not HBM"
+            roofline["ncu"] = tf["rollout_kernel_ncu"]
     cpu = None
     if world == 1:
         try:

@@ -262,6 +262,32 @@ def test_sample_indices_and_gather(nb):
     assert np.array_equal(a.cpu().numpy(), stored["a"])
 
 
+def test_set_weights_from_host_never_writes_through_a_callers_tensor(nb):
+    """set_weights(pinned host tensor) copies into a buffer the object owns (no allocation per step); a device tensor
+    handed in earlier stays the caller's.  The forward must follow whichever weights were set last."""
+    sp = nb.SelfPlay(256, seed=5)
+    obs = torch.randint(0, 1 << 30, (64,), dtype=torch.int32, device=sp.device)
+    net = torch.randint(0, 4, (64,), dtype=torch.int8, device=sp.device)
+    mine = nb.glorot_nets(9, sp.device)
+    keep = mine.clone()
+    sp.set_weights(mine)
+    out_a = sp.forward(obs, net).clone()
+    host = [nb.glorot_nets(s, sp.device).cpu().pin_memory() for s in (10, 11)]
+    outs = []
+    for h in host:
+        sp.set_weights(h)
+        torch.cuda.synchronize()
+        assert torch.equal(mine, keep)          # the caller's tensor was not overwritten
+        assert torch.equal(sp.weights.cpu(), h)
+        outs.append(sp.forward(obs, net).clone())
+    ptr = sp.weights.data_ptr()
+    sp.set_weights(host[0])                      # second host call: same device buffer, new contents
+    assert sp.weights.data_ptr() == ptr and torch.equal(sp.forward(obs, net), outs[0])
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(out_a, outs[0])
+    sp.set_weights(mine)
+    assert torch.equal(sp.forward(obs, net), out_a)
+
+
 def test_rollout_variants_agree_without_debug(nb):
     """Production (non-debug) kernels of both variants leave identical game words, counters and record sets
     whenever no decision is a last-bit near-tie (seeded so that none is)."""
