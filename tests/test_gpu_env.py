@@ -109,6 +109,47 @@ def test_nfsp_env_seeded_rollout_vs_oracle(nb, n, steps):
     assert torch.equal(env.state_words(), env2.state_words())
 
 
+def test_state_machine_and_packed_word_kernels_agree_at_full_size(nb):
+    """BASELINE config 2 size (2^20 games), 32 transitions per game: the table-driven kernel (Philox actions) and the
+    packed-word kernel (the same actions passed explicitly) must leave identical trace planes and game words, launch
+    after launch -- every (dealer, betting sequence, action) entry, deal and re-deal is hit tens of thousands of times."""
+    n, steps = 1 << 20, 16
+    a, b = nb.BatchedNfspEnv(n, seed=2024, eta=0.3), nb.BatchedNfspEnv(n, seed=2024, eta=0.3)
+    a.reset()
+    b.reset()
+    for _ in range(2):
+        ta = a.step(n_steps=steps, trace=True)
+        tb = b.step(actions=ta["action"].to(torch.int8), n_steps=steps, auto_reset=True, trace=True)
+        assert torch.equal(ta["raw"], tb["raw"])
+        assert torch.equal(a.state_words(), b.state_words())
+    hands = int(ta["terminated"].sum())
+    assert 2.4 < n * steps / hands < 2.8
+
+
+def test_legacy_state_machine_agrees_with_call_by_call_kernels_at_full_size(nb):
+    """2^20 games of the README loop: the table-driven rollout kernel against the SAME actions played through
+    nfsp_legacy_step / nfsp_legacy_get_new_state (the packed-word rules, one call per README line) until each game's
+    first hand ends; records and exported fields must match for every live game."""
+    n, iters = 1 << 20, 6
+    roll, manual = nb.BatchedLegacyEnv(n, seed=31), nb.BatchedLegacyEnv(n, seed=31)
+    roll.reset()
+    manual.load_state_words(roll.state_words())
+    rec = roll.rollout(iters, trace=True)
+    live = torch.ones(n, dtype=torch.bool, device=roll.device)
+    for k in range(iters):
+        acts = rec["action"][k].to(torch.int8)           # [n, 2]
+        sit = torch.full((n,), 4, dtype=torch.int8, device=roll.device)
+        manual.step(torch.where(live, acts[:, 0], sit), 0)
+        manual.step(torch.where(live, acts[:, 1], sit), 1)
+        out = [manual.get_new_state(torch.where(live, torch.full_like(sit, p), torch.full_like(sit, 2))) for p in (0, 1)]
+        for p in (0, 1):
+            got = torch.stack([rec["card"][k, :, p], rec["pub"][k, :, p], rec["pot"][k, :, p], rec["reward"][k, :, p],
+                               rec["terminal"][k, :, p]], 1)
+            assert torch.equal(got[live], out[p][live].to(got.dtype)), (k, p)
+        live &= ~(rec["terminal"][k, :, 0].bool() | rec["terminal"][k, :, 1].bool())
+    assert int(live.sum()) < n // 50  # nearly every first hand is over after 6 iterations
+
+
 def test_nfsp_env_sharding_invariance(nb):
     """a game's trace depends on its GLOBAL id only -- two shards == one batch."""
     n, steps = 4096, 20
