@@ -250,6 +250,15 @@ typedef struct {
 /* Agent.update_best_response_network / update_avg_response_network (agent.py:209-264), gradient part:
  * forward + backward of all four nets on one minibatch, read straight from the packed memories. */
 int nfsp_learner_grads(const nfsp_learner_io *io, void *stream);
+/* Keras' fit(x, y, batch_size = fit_batch, epochs = epochs) of all four nets (agent.py:243,261) on ONE GPU in a single
+ * launch: the SGD steps over the slices [0, fit_batch), [fit_batch, 2 fit_batch), ... of the `minibatch` sampled rows,
+ * `epochs` times, each step = the gradients of nfsp_learner_grads followed by nfsp_sgd_apply with scale 1 -- the
+ * weights stay in registers between the steps.  io->row0 / rows / d_grad are not read; io->d_stats receives the
+ * statistics of the first step.  d_weights_out float[4][2179] may be io->d_weights.  With more than one GPU the steps
+ * need a collective between gradient and update: use nfsp_learner_grads + all-reduce + nfsp_sgd_apply. */
+#define NFSP_MAX_FIT_STEPS 64
+int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                     float *d_weights_out, void *stream);
 /* keras SGD step (agent.py:45-46,243,261): w[k] -= lr[k] * scale * grad[k]; scale = 1/world after a SUM
  * all-reduce.  lr is a HOST array of 4 floats. */
 int nfsp_sgd_apply(float *d_weights, const float *d_grad, const float lr[4], float scale, void *stream);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
-    "nfsp_learner_grads", "nfsp_sgd_apply",
+    "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_sgd_apply",
 ]
 
 
@@ -115,6 +115,7 @@ def lib():
     L.nfsp_gather_rl.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.nfsp_gather_sl.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.nfsp_learner_grads.argtypes = [C.POINTER(LearnerIO), vp]
+    L.nfsp_learner_fit.argtypes = [C.POINTER(LearnerIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp, vp]
     L.nfsp_sgd_apply.argtypes = [vp, vp, C.POINTER(C.c_float * 4), C.c_float, vp]
     _lib = L
     return L

@@ -68,34 +68,40 @@ __device__ __forceinline__ void cta_sum3(float &a, float &b, float &c, float (*r
     c = red[slot][0][2] + red[slot][1][2];
 }
 
-__global__ void __launch_bounds__(kLearnThreads)
-learner_grad_kernel(const LearnerArgs A) {
-    __shared__ float red_all[kRowGroups][4][2][4];
-    __shared__ float part[kRowGroups][40][64];  // per group: gw1[30], gb1, gw2[3] per hidden unit; row 34: gb2, loss, expl
-    const int net = blockIdx.x, player = net >> 1, is_br = net & 1, group = threadIdx.x >> 6, j = threadIdx.x & 63;
-    float (*red)[2][4] = red_all[group];
-    float *g = A.grad + net * NFSP_NET_PARAMS;
-    if (!((A.net_mask >> net) & 1)) {
-        for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) g[e] = 0.f;
-        return;
-    }
+// Per-thread state of one net: the thread's column of W1, its row of W2, the output biases, and -- for a best-response
+// net -- the same of the target net.
+struct NetState {
     NetRegs W, T;
-    W.load(A.w + net * NFSP_NET_PARAMS, j);
-    const float b2_0 = A.w[net * NFSP_NET_PARAMS + 2176], b2_1 = A.w[net * NFSP_NET_PARAMS + 2177],
-                b2_2 = A.w[net * NFSP_NET_PARAMS + 2178];
-    float t2_0 = 0.f, t2_1 = 0.f, t2_2 = 0.f;
-    if (is_br) {
-        const float *wt = A.w_target + player * NFSP_NET_PARAMS;
-        T.load(wt, j);
-        t2_0 = wt[2176]; t2_1 = wt[2177]; t2_2 = wt[2178];
+    float b2[3], t2[3];
+    __device__ __forceinline__ void load(const LearnerArgs &A, int net, int j) {
+        const float *w = A.w + net * NFSP_NET_PARAMS;
+        W.load(w, j);
+        b2[0] = w[2176]; b2[1] = w[2177]; b2[2] = w[2178];
+        t2[0] = t2[1] = t2[2] = 0.f;
+        if (net & 1) {
+            const float *wt = A.w_target + (net >> 1) * NFSP_NET_PARAMS;
+            T.load(wt, j);
+            t2[0] = wt[2176]; t2[1] = wt[2177]; t2[2] = wt[2178];
+        }
     }
+};
+
+// One SGD step's sums over the rows [row0, row0 + rows) for net `net`: every group takes its rows round-robin, the
+// groups' partial sums meet in shared memory and are added in group order (deterministic).  On return (after a CTA
+// barrier) part[0][i][j] holds, for hidden unit j, the summed gradients of W1 rows i = 0..29, b1 (30), W2 (31..33) and
+// part[0][34][0..4] those of b2, the loss sum and the exploitability-proxy sum.
+__device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &N, int net, int row0, int rows,
+                                          float (*red_all)[4][2][4], float (*part)[40][64]) {
+    const int player = net >> 1, is_br = net & 1, group = threadIdx.x >> 6, j = threadIdx.x & 63;
+    float (*red)[2][4] = red_all[group];
+    const NetRegs &W = N.W, &T = N.T;
+    const float b2_0 = N.b2[0], b2_1 = N.b2[1], b2_2 = N.b2[2], t2_0 = N.t2[0], t2_1 = N.t2[1], t2_2 = N.t2[2];
     float gw1[30], gb1 = 0.f, gw2[3] = {0.f, 0.f, 0.f}, gb2[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 30; ++i) gw1[i] = 0.f;
     float loss = 0.f, expl = 0.f;
-    const float inv_rows = 1.0f / (float)A.rows;
-    for (int r = group; r < A.rows; r += kRowGroups) {
-        const int row = A.row0 + r;
+    for (int r = group; r < rows; r += kRowGroups) {
+        const int row = row0 + r;
         uint32_t s;
         float dz0, dz1, dz2;
         if (is_br) {
@@ -153,7 +159,6 @@ learner_grad_kernel(const LearnerArgs A) {
         }
         gb2[0] += dz0; gb2[1] += dz1; gb2[2] += dz2;
     }
-    // the groups' partial sums meet in shared memory and are added in group order (deterministic)
 #pragma unroll
     for (int i = 0; i < 30; ++i) part[group][i][j] = gw1[i];
     part[group][30][j] = gb1;
@@ -166,29 +171,104 @@ learner_grad_kernel(const LearnerArgs A) {
         part[group][34][4] = expl;
     }
     __syncthreads();
-    if (group != 0) return;
-    float tot[34];
+    if (group == 0) {
 #pragma unroll
-    for (int i = 0; i < 34; ++i) {
-        float v = part[0][i][j];
+        for (int i = 0; i < 34; ++i) {
+            float v = part[0][i][j];
 #pragma unroll
-        for (int k = 1; k < kRowGroups; ++k) v += part[k][i][j];
-        tot[i] = v;
+            for (int k = 1; k < kRowGroups; ++k) v += part[k][i][j];
+            part[0][i][j] = v;
+        }
+        if (j < 5) {
+            float v = part[0][34][j];
+#pragma unroll
+            for (int k = 1; k < kRowGroups; ++k) v += part[k][34][j];
+            part[0][34][j] = v;
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 30; ++i) g[i * 64 + j] = tot[i] * inv_rows;
-    g[1920 + j] = tot[30] * inv_rows;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[1984 + j * 3 + c] = tot[31 + c] * inv_rows;
-    if (j < 5) {
-        float v = part[0][34][j];
-#pragma unroll
-        for (int k = 1; k < kRowGroups; ++k) v += part[k][34][j];
-        if (j < 3) g[2176 + j] = v * inv_rows;
-        // stats: [0,1] exploitability-proxy sums of the BR nets, [2,3] their row counts, [4..7] loss sums per net
-        if (j == 3) A.stats[4 + net] = v;
-        if (j == 4 && is_br) { A.stats[player] = v; A.stats[2 + player] = (float)A.rows; }
+    __syncthreads();
+}
+
+// stats: [0,1] exploitability-proxy sums of the BR nets, [2,3] their row counts, [4..7] loss sums per net
+__device__ __forceinline__ void write_stats(float *stats, int net, int rows, float (*part)[40][64]) {
+    if (threadIdx.x == 0) {
+        stats[4 + net] = part[0][34][3];
+        if (net & 1) { stats[net >> 1] = part[0][34][4]; stats[2 + (net >> 1)] = (float)rows; }
     }
+}
+
+__global__ void __launch_bounds__(kLearnThreads)
+learner_grad_kernel(const LearnerArgs A) {
+    __shared__ float red_all[kRowGroups][4][2][4];
+    __shared__ float part[kRowGroups][40][64];  // per group: gw1[30], gb1, gw2[3] per hidden unit; row 34: gb2, loss, expl
+    const int net = blockIdx.x, j = threadIdx.x & 63;
+    float *g = A.grad + net * NFSP_NET_PARAMS;
+    if (!((A.net_mask >> net) & 1)) {
+        for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) g[e] = 0.f;
+        return;
+    }
+    NetState N;
+    N.load(A, net, j);
+    step_sums(A, N, net, A.row0, A.rows, red_all, part);
+    write_stats(A.stats, net, A.rows, part);
+    if (threadIdx.x >= 64) return;
+    const float inv_rows = 1.0f / (float)A.rows;
+#pragma unroll
+    for (int i = 0; i < 30; ++i) g[i * 64 + j] = part[0][i][j] * inv_rows;
+    g[1920 + j] = part[0][30][j] * inv_rows;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[1984 + j * 3 + c] = part[0][31 + c][j] * inv_rows;
+    if (j < 3) g[2176 + j] = part[0][34][j] * inv_rows;
+}
+
+// Keras' fit() of all four nets on ONE GPU in one launch (no collective between the SGD steps): n_steps slices
+// [row0_k, row0_k + rows_k) of the sampled minibatch, each step = the sums above, then w -= lr * mean gradient applied
+// to the weights every thread holds in registers (all row groups keep the same copy).  The statistics are those of the
+// first step, as the host-driven sequence reports them.
+struct FitArgs {
+    LearnerArgs A;
+    float *w_out;  // [4][2179], may alias A.w
+    int n_steps;
+    int row0[NFSP_MAX_FIT_STEPS], rows[NFSP_MAX_FIT_STEPS];
+    float lr[4];
+};
+__global__ void __launch_bounds__(kLearnThreads)
+learner_fit_kernel(const FitArgs F) {
+    __shared__ float red_all[kRowGroups][4][2][4];
+    __shared__ float part[kRowGroups][40][64];
+    const LearnerArgs &A = F.A;
+    const int net = blockIdx.x, j = threadIdx.x & 63;
+    if (!((A.net_mask >> net) & 1)) {
+        if (F.w_out != A.w)
+            for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) F.w_out[net * NFSP_NET_PARAMS + e] = A.w[net * NFSP_NET_PARAMS + e];
+        return;
+    }
+    NetState N;
+    N.load(A, net, j);
+    const float lr = F.lr[net];
+    for (int k = 0; k < F.n_steps; ++k) {
+        step_sums(A, N, net, F.row0[k], F.rows[k], red_all, part);
+        if (k == 0) write_stats(A.stats, net, F.rows[k], part);
+        const float inv_rows = 1.0f / (float)F.rows[k];
+        // the same arithmetic as sgd_apply_kernel on the stored mean gradient: w -= lr * 1.0f * (sum * inv_rows)
+#pragma unroll
+        for (int i = 0; i < 30; ++i) N.W.w1[i] -= lr * 1.0f * (part[0][i][j] * inv_rows);
+        N.W.b1 -= lr * 1.0f * (part[0][30][j] * inv_rows);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            N.W.w2[c] -= lr * 1.0f * (part[0][31 + c][j] * inv_rows);
+            N.b2[c] -= lr * 1.0f * (part[0][34][c] * inv_rows);
+        }
+        __syncthreads();  // part[] is rewritten by the next step
+    }
+    if (threadIdx.x >= 64) return;
+    float *w = F.w_out + net * NFSP_NET_PARAMS;
+#pragma unroll
+    for (int i = 0; i < 30; ++i) w[i * 64 + j] = N.W.w1[i];
+    w[1920 + j] = N.W.b1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[1984 + j * 3 + c] = N.W.w2[c];
+    if (j < 3) w[2176 + j] = N.b2[j];
 }
 
 // w[k] -= lr[k] * scale * grad[k]   (keras.optimizers.SGD without momentum, agent.py:45-46)
@@ -205,10 +285,8 @@ __global__ void sgd_apply_kernel(float *__restrict__ w, const float *__restrict_
 
 using namespace nfsp;
 
-extern "C" int nfsp_learner_grads(const nfsp_learner_io *io, void *stream) {
-    NFSP_CHECK_ARG(io != nullptr && io->d_weights && io->d_target_weights && io->d_grad && io->d_stats, "null argument");
-    NFSP_CHECK_ARG(io->rows >= 1 && io->row0 >= 0, "bad minibatch slice");
-    LearnerArgs A;
+static int make_learner_args(const nfsp_learner_io *io, LearnerArgs &A) {
+    NFSP_CHECK_ARG(io != nullptr && io->d_weights && io->d_target_weights && io->d_stats, "null argument");
     A.w = io->d_weights; A.w_target = io->d_target_weights;
     for (int p = 0; p < 2; ++p) {
         A.rl[p] = (const uint4 *)io->d_rl[p]; A.rl_idx[p] = io->d_rl_idx[p];
@@ -218,7 +296,38 @@ extern "C" int nfsp_learner_grads(const nfsp_learner_io *io, void *stream) {
     }
     A.row0 = io->row0; A.rows = io->rows; A.gamma = io->gamma; A.net_mask = io->net_mask;
     A.terminal_bootstraps = io->terminal_bootstraps; A.grad = io->d_grad; A.stats = io->d_stats;
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_learner_grads(const nfsp_learner_io *io, void *stream) {
+    LearnerArgs A;
+    const int rc = make_learner_args(io, A);
+    if (rc != NFSP_OK) return rc;
+    NFSP_CHECK_ARG(A.grad != nullptr, "null gradient buffer");
+    NFSP_CHECK_ARG(io->rows >= 1 && io->row0 >= 0, "bad minibatch slice");
     learner_grad_kernel<<<4, kLearnThreads, 0, (cudaStream_t)stream>>>(A);
+    NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                                float *d_weights_out, void *stream) {
+    NFSP_CHECK_ARG(lr && d_weights_out, "null argument");
+    NFSP_CHECK_ARG(minibatch >= 1 && fit_batch >= 1 && epochs >= 1, "bad fit geometry");
+    FitArgs F;
+    const int rc = make_learner_args(io, F.A);
+    if (rc != NFSP_OK) return rc;
+    F.w_out = d_weights_out;
+    F.n_steps = 0;
+    for (int e = 0; e < epochs; ++e)
+        for (int row0 = 0; row0 < minibatch; row0 += fit_batch) {
+            NFSP_CHECK_ARG(F.n_steps < NFSP_MAX_FIT_STEPS, "more than %d SGD steps per fit", NFSP_MAX_FIT_STEPS);
+            F.row0[F.n_steps] = row0;
+            F.rows[F.n_steps] = minibatch - row0 < fit_batch ? minibatch - row0 : fit_batch;
+            ++F.n_steps;
+        }
+    for (int k = 0; k < 4; ++k) F.lr[k] = lr[k];
+    learner_fit_kernel<<<4, kLearnThreads, 0, (cudaStream_t)stream>>>(F);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

@@ -2,7 +2,8 @@
 
 `Learner.update()` is `update_strategy()` (agent.py:192-194) of BOTH agents at once: it samples a
 minibatch from each of the four memories, then runs Keras' `fit(..., epochs=2)` (default batch 32,
-so 8 SGD steps) for the four nets.  Every SGD step is: one `nfsp_learner_grads` launch (all four
+so 8 SGD steps) for the four nets.  On one GPU the eight steps are ONE launch (`nfsp_learner_fit`: the
+weights stay in registers between the steps).  With several GPUs every SGD step is: one `nfsp_learner_grads` launch (all four
 nets, gradients into one flat fp32 buffer with the exploitability statistics behind them), ONE
 all-reduce of that buffer over the GPUs (NCCL; C1 + C2 of SURVEY 2a), one `nfsp_sgd_apply` launch.
 Weights therefore stay bit-identical on every rank.
@@ -38,7 +39,7 @@ def _world():
 
 class Learner:
     def __init__(self, selfplay, cfg=None, minibatch=128, fit_batch=32, epochs=2, lr_br=0.05, lr_ar=0.1, gamma=0.95,
-                 target_update_rate=150, terminal_bootstraps=False):
+                 target_update_rate=150, terminal_bootstraps=False, fused=True):
         if cfg is not None:
             minibatch = cfg.getint("Agent", "MiniBatchSize")
             lr_br, lr_ar = cfg.getfloat("Agent", "LearningRateBR"), cfg.getfloat("Agent", "LearningRateAR")
@@ -51,6 +52,7 @@ class Learner:
         self.lr_br = [self.lr_br0, self.lr_br0]
         self.target_update_rate = int(target_update_rate)
         self.terminal_bootstraps = bool(terminal_bootstraps)
+        self.fused = bool(fused)  # single GPU: the whole fit() as one kernel; False = one launch pair per SGD step
         self.target = selfplay.weights[[1, 3]].clone().contiguous()   # agent.py:70-72
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
         self.iteration = [0, 0]
@@ -59,8 +61,7 @@ class Learner:
         self.exploitability = [0.0, 0.0]
         self.updates = 0
 
-    # ---- one SGD step for all four nets -------------------------------------------------------------
-    def _step(self, idx_rl, idx_sl, row0, rows, mask):
+    def _io(self, idx_rl, idx_sl, row0, rows, mask):
         sp = self.sp
         io = _lib.LearnerIO()
         io.d_weights, io.d_target_weights = sp.weights.data_ptr(), self.target.data_ptr()
@@ -70,6 +71,19 @@ class Learner:
         io.row0, io.rows, io.gamma, io.net_mask = row0, rows, self.gamma, mask
         io.terminal_bootstraps = int(self.terminal_bootstraps)
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
+        return io
+
+    # ---- the whole fit() in one launch: one GPU, no collective between the SGD steps ---------------
+    def _fit_fused(self, idx_rl, idx_sl, mask):
+        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask)
+        lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
+        check(lib().nfsp_learner_fit(C.byref(io), self.minibatch, self.fit_batch, self.epochs, lr, _ptr(self.sp.weights),
+                                     _stream(self.device)))
+
+    # ---- one SGD step for all four nets -------------------------------------------------------------
+    def _step(self, idx_rl, idx_sl, row0, rows, mask):
+        sp = self.sp
+        io = self._io(idx_rl, idx_sl, row0, rows, mask)
         check(lib().nfsp_learner_grads(C.byref(io), _stream(self.device)))
         world = _world()
         if world > 1:  # C1 (gradients) + C2 (exploitability stats) in one collective
@@ -109,11 +123,15 @@ class Learner:
         idx_rl = [sp.rl[p].sample_slots(self.minibatch)[0] for p in range(2)]
         idx_sl = [sp.sl[p].sample_slots(self.minibatch)[0] for p in range(2)]
         stats = None
-        for _ in range(self.epochs):             # Keras fit(epochs=2), batch_size 32 (agent.py:243,261)
-            for row0 in range(0, self.minibatch, self.fit_batch):
-                self._step(idx_rl, idx_sl, row0, min(self.fit_batch, self.minibatch - row0), mask)
-                if stats is None:                # exploitability proxy of the sampled batch, first pass
-                    stats = self.flat[GRAD:].clone()
+        if _world() == 1 and self.fused:         # one launch for the 8 SGD steps (nfsp_learner_fit)
+            self._fit_fused(idx_rl, idx_sl, mask)
+            stats = self.flat[GRAD:].clone()     # statistics of the first step, as below
+        else:
+            for _ in range(self.epochs):         # Keras fit(epochs=2), batch_size 32 (agent.py:243,261)
+                for row0 in range(0, self.minibatch, self.fit_batch):
+                    self._step(idx_rl, idx_sl, row0, min(self.fit_batch, self.minibatch - row0), mask)
+                    if stats is None:            # exploitability proxy of the sampled batch, first pass
+                        stats = self.flat[GRAD:].clone()
         if sync:
             self._loss = stats.cpu().tolist()
         s = getattr(self, "_loss", [0.0] * N_STATS)

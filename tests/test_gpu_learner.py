@@ -100,6 +100,24 @@ def test_update_runs_schedules(nb):
     assert torch.isfinite(out["vec"]).all()
 
 
+def test_fit_in_one_launch_equals_the_step_by_step_sequence(nb):
+    """nfsp_learner_fit (8 SGD steps, weights in registers) against 8 x (nfsp_learner_grads, nfsp_sgd_apply) on the same
+    sampled rows: same statistics, weights equal to fp32 rounding of the same arithmetic (tolerance 1e-6 absolute on
+    weights of magnitude <= 0.3; the two paths differ at most in fused-multiply-add contraction)."""
+    from nfsp_b200.learner import Learner
+
+    a, b = _filled_selfplay(nb), _filled_selfplay(nb)
+    assert torch.equal(a.weights, b.weights)
+    La, Lb = Learner(a, cfg=nb.load_config(None), fused=True), Learner(b, cfg=nb.load_config(None), fused=False)
+    for k in range(3):
+        ra, rb = La.update(), Lb.update()
+        assert ra["trained"] == rb["trained"] == 0xF
+        assert np.allclose(ra["loss"], rb["loss"], rtol=1e-5, atol=1e-6)
+        assert abs(ra["exploitability"] - rb["exploitability"]) < 1e-5
+        d = (a.weights - b.weights).abs().max().item()
+        assert d < 1e-6, (k, d)
+
+
 def test_sgd_reduces_loss_on_a_fixed_minibatch(nb):
     from nfsp_b200.learner import GRAD, Learner
 
