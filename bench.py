@@ -317,6 +317,17 @@ def run_gpu(args):
     b.record()
     b.synchronize()
     learner_ms = sharding.max_over_ranks(a.elapsed_time(b) / 5, dev)
+    # the full self-play iteration of BASELINE configs[4]: rollout(8) + memory inserts + update_strategy() of both agents
+    # (with its all-reduces when world > 1), nothing read back between iterations
+    barrier()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        sp.rollout(T_PER_CALL)
+        learner.update(sync=False)
+    b.record()
+    b.synchronize()
+    train_ms = sharding.max_over_ranks(a.elapsed_time(b) / 5, dev)
 
     # env-only K1 (BASELINE configs[1]) beside it, same games count, trace planes written
     env = nfsp_b200.BatchedNfspEnv(n, seed=SEED, game0=game0, device=dev)
@@ -451,6 +462,8 @@ def run_gpu(args):
                       "rollout_64k_games": {"config": "BASELINE configs[2]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts",
                                             "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps},
                       "buffers": buffers,
+                      "training_step": {"what": "rollout(8) + memory inserts + Learner.update(sync=False) per iteration (BASELINE configs[4])",
+                                        "ms": train_ms, "transitions_per_sec": GAMES_PER_GPU * world * T_PER_CALL / (train_ms * 1e-3)},
                       "learner": {"update_ms": learner_ms, "sgd_steps_per_update": 8, "allreduce_floats": 4 * 2179 + 8,
                                   "exploitability_proxy": lstats.get("exploitability"), "trained_mask": lstats.get("trained")},
                       "hands": int(st[10]), "transitions_counted": int(st[11]), "records_dropped": int(st[12])}}

@@ -211,7 +211,8 @@ int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_tota
  * nfsp_sample_indices(seed, call_idx, ...) does and expands the rows as nfsp_gather_rl / nfsp_gather_sl do into d_out,
  * one contiguous block: ring (RL)  s[batch][30] a[batch][3] r[batch] s2[batch][30] t[batch]  = 65 * batch floats,
  * reservoir (SL)  s[batch][30] a[batch][3]  = 33 * batch floats.  d_idx int64[n_reqs][batch] (storage slots, -1 beyond
- * the records held) and d_n_out uint32[n_reqs] (rows sampled) may be NULL. */
+ * the records held) and d_n_out uint32[n_reqs] (rows sampled) may be NULL.  A request with d_out = NULL only reports its
+ * positions in d_idx (the learner kernels read the packed records themselves). */
 #define NFSP_MAX_SAMPLE_REQS 8
 typedef struct {
     const void *d_mem;        /* ring / reservoir storage, 16-byte records */

@@ -299,12 +299,13 @@ sample_gather_kernel(const SampleReqs R, int batch, int64_t *__restrict__ idx_ou
     const int row0 = (int)blockIdx.y * per, row1 = min(batch, row0 + per);
     if (threadIdx.x == 0 && blockIdx.y == 0 && n_out) n_out[m] = (uint32_t)b;
     const uint4 *mem = R.mem[m];
+    float *o = R.out[m];
     for (int k = row0 + threadIdx.x; k < row1; k += blockDim.x) {
         if (idx_out) idx_out[(int64_t)m * batch + k] = slot[k];
-        s_rec[k] = slot[k] >= 0 ? mem[slot[k]] : make_uint4(0, 0, 0, 0);
+        if (o) s_rec[k] = slot[k] >= 0 ? mem[slot[k]] : make_uint4(0, 0, 0, 0);
     }
+    if (!o) return;  // positions only (the learner reads the packed records itself)
     __syncthreads();
-    float *o = R.out[m];
     const int rows = max(row1 - row0, 0);
     if (R.is_ring[m]) {
         float *s = o, *a = s + 30 * batch, *r = a + 3 * batch, *s2 = r + batch, *t = s2 + 30 * batch;
@@ -451,7 +452,8 @@ extern "C" int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, 
     NFSP_CHECK_ARG(batch >= 1 && batch <= kMaxBatch, "batch must be in [1,%d]", kMaxBatch);
     SampleReqs R;
     for (int m = 0; m < n_reqs; ++m) {
-        NFSP_CHECK_ARG(reqs[m].d_mem && reqs[m].d_total && reqs[m].d_out && reqs[m].cap > 0, "bad request %d", m);
+        NFSP_CHECK_ARG(reqs[m].d_mem && reqs[m].d_total && reqs[m].cap > 0, "bad request %d", m);
+        NFSP_CHECK_ARG(reqs[m].d_out || d_idx, "request %d has neither an output block nor an index array", m);
         R.mem[m] = (const uint4 *)reqs[m].d_mem;
         R.total[m] = reqs[m].d_total;
         R.cap[m] = (uint64_t)reqs[m].cap;

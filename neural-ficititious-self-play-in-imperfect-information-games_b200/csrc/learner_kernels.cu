@@ -68,6 +68,24 @@ __device__ __forceinline__ void cta_sum3(float &a, float &b, float &c, float (*r
     c = red[slot][0][2] + red[slot][1][2];
 }
 
+// the same for nine values at once: the three forward passes of a best-response row (online Q(s), target Q(s2), target
+// Q(s)) do not depend on each other, so they share one round of shuffles and ONE barrier instead of three
+__device__ __forceinline__ void cta_sum9(float (&v)[9], float (*red)[2][4], int group) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    }
+    const int warp = (threadIdx.x >> 5) & 1;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) red[k / 3][warp][k % 3] = v[k];
+    }
+    group_sync(group);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = red[k / 3][0][k % 3] + red[k / 3][1][k % 3];
+}
+
 // Per-thread state of one net: the thread's column of W1, its row of W2, the output biases, and -- for a best-response
 // net -- the same of the target net.
 struct NetState {
@@ -90,8 +108,18 @@ struct NetState {
 // groups' partial sums meet in shared memory and are added in group order (deterministic).  On return (after a CTA
 // barrier) part[0][i][j] holds, for hidden unit j, the summed gradients of W1 rows i = 0..29, b1 (30), W2 (31..33) and
 // part[0][34][0..4] those of b2, the loss sum and the exploitability-proxy sum.
+// s_rec: the net's sampled records of rows [s_base, s_base + kMaxFitRows) prefetched into shared memory (the two
+// dependent global reads per row -- index, then record -- were most of a row's latency), or nullptr.
+constexpr int kMaxFitRows = 256;
+__device__ __forceinline__ void prefetch_rows(const LearnerArgs &A, int net, int base, int rows, uint4 *s_rec) {
+    const int player = net >> 1;
+    const uint4 *mem = (net & 1) ? A.rl[player] : A.sl[player];
+    const int64_t *idx = (net & 1) ? A.rl_idx[player] : A.sl_idx[player];
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) s_rec[r] = mem[idx[base + r]];
+    __syncthreads();
+}
 __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &N, int net, int row0, int rows,
-                                          float (*red_all)[4][2][4], float (*part)[40][64]) {
+                                          float (*red_all)[4][2][4], float (*part)[40][64], const uint4 *s_rec, int s_base) {
     const int player = net >> 1, is_br = net & 1, group = threadIdx.x >> 6, j = threadIdx.x & 63;
     float (*red)[2][4] = red_all[group];
     const NetRegs &W = N.W, &T = N.T;
@@ -105,20 +133,17 @@ __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &
         uint32_t s;
         float dz0, dz1, dz2;
         if (is_br) {
-            const uint4 rec = A.rl[player][A.rl_idx[player][row]];
+            const uint4 rec = s_rec ? s_rec[row - s_base] : A.rl[player][A.rl_idx[player][row]];
             s = rec.x;
             const uint32_t a = rec.w & 0xFFu, term = (rec.w >> 8) & 0xFFu;
             const float rew = __uint_as_float(rec.z);
             // online Q(s), target Q(s2), target Q(s) (exploitability proxy, agent.py:234-238)
-            const float h = W.hidden(s);
-            float z0 = h * W.w2[0], z1 = h * W.w2[1], z2 = h * W.w2[2];
-            cta_sum3(z0, z1, z2, red, 0, group);
-            const float ht = T.hidden(rec.y);
-            float y0 = ht * T.w2[0], y1 = ht * T.w2[1], y2 = ht * T.w2[2];
-            cta_sum3(y0, y1, y2, red, 1, group);
-            const float hs = T.hidden(s);
-            float e0 = hs * T.w2[0], e1 = hs * T.w2[1], e2 = hs * T.w2[2];
-            cta_sum3(e0, e1, e2, red, 2, group);
+            const float h = W.hidden(s), ht = T.hidden(rec.y), hs = T.hidden(s);
+            float v[9] = {h * W.w2[0], h * W.w2[1], h * W.w2[2], ht * T.w2[0], ht * T.w2[1], ht * T.w2[2],
+                          hs * T.w2[0], hs * T.w2[1], hs * T.w2[2]};
+            cta_sum9(v, red, group);
+            float z0 = v[0], z1 = v[1], z2 = v[2];
+            const float y0 = v[3], y1 = v[4], y2 = v[5], e0 = v[6], e1 = v[7], e2 = v[8];
             expl += fmaxf(fmaxf(fmaxf(e0 + t2_0, 0.f), fmaxf(e1 + t2_1, 0.f)), fmaxf(e2 + t2_2, 0.f));
             const float qn = fmaxf(fmaxf(fmaxf(y0 + t2_0, 0.f), fmaxf(y1 + t2_1, 0.f)), fmaxf(y2 + t2_2, 0.f));
             const float target = rew + ((term && !A.terminal_bootstraps) ? 0.f : A.gamma * qn);
@@ -136,7 +161,7 @@ __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &
 #pragma unroll
             for (int i = 0; i < 30; ++i) gw1[i] += ((s >> i) & 1u) ? dh : 0.f;
         } else {
-            const uint4 rec = A.sl[player][A.sl_idx[player][row]];
+            const uint4 rec = s_rec ? s_rec[row - s_base] : A.sl[player][A.sl_idx[player][row]];
             s = rec.x;
             const float ya = __uint_as_float(rec.y), yb = __uint_as_float(rec.z), yc = __uint_as_float(rec.w);
             const float h = W.hidden(s);
@@ -207,9 +232,12 @@ learner_grad_kernel(const LearnerArgs A) {
         for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) g[e] = 0.f;
         return;
     }
+    __shared__ uint4 s_rec[kMaxFitRows];
+    const bool pre = A.rows <= kMaxFitRows;
+    if (pre) prefetch_rows(A, net, A.row0, A.rows, s_rec);
     NetState N;
     N.load(A, net, j);
-    step_sums(A, N, net, A.row0, A.rows, red_all, part);
+    step_sums(A, N, net, A.row0, A.rows, red_all, part, pre ? s_rec : nullptr, A.row0);
     write_stats(A.stats, net, A.rows, part);
     if (threadIdx.x >= 64) return;
     const float inv_rows = 1.0f / (float)A.rows;
@@ -228,7 +256,7 @@ learner_grad_kernel(const LearnerArgs A) {
 struct FitArgs {
     LearnerArgs A;
     float *w_out;  // [4][2179], may alias A.w
-    int n_steps;
+    int n_steps, minibatch;
     int row0[NFSP_MAX_FIT_STEPS], rows[NFSP_MAX_FIT_STEPS];
     float lr[4];
 };
@@ -243,11 +271,14 @@ learner_fit_kernel(const FitArgs F) {
             for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kLearnThreads) F.w_out[net * NFSP_NET_PARAMS + e] = A.w[net * NFSP_NET_PARAMS + e];
         return;
     }
+    __shared__ uint4 s_rec[kMaxFitRows];
+    const bool pre = F.minibatch <= kMaxFitRows;
+    if (pre) prefetch_rows(A, net, 0, F.minibatch, s_rec);
     NetState N;
     N.load(A, net, j);
     const float lr = F.lr[net];
     for (int k = 0; k < F.n_steps; ++k) {
-        step_sums(A, N, net, F.row0[k], F.rows[k], red_all, part);
+        step_sums(A, N, net, F.row0[k], F.rows[k], red_all, part, pre ? s_rec : nullptr, 0);
         if (k == 0) write_stats(A.stats, net, F.rows[k], part);
         const float inv_rows = 1.0f / (float)F.rows[k];
         // the same arithmetic as sgd_apply_kernel on the stored mean gradient: w -= lr * 1.0f * (sum * inv_rows)
@@ -318,6 +349,7 @@ extern "C" int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fi
     const int rc = make_learner_args(io, F.A);
     if (rc != NFSP_OK) return rc;
     F.w_out = d_weights_out;
+    F.minibatch = minibatch;
     F.n_steps = 0;
     for (int e = 0; e < epochs; ++e)
         for (int row0 = 0; row0 < minibatch; row0 += fit_batch) {

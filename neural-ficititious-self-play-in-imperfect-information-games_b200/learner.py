@@ -73,6 +73,26 @@ class Learner:
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
         return io
 
+    def _sample_positions(self):
+        """sample_batch positions of the four memories (agent.py:217,260) in one launch; the same draws as four
+        sample_slots() calls.  Returns ([rl0, rl1], [sl0, sl1]) index tensors of `minibatch` storage slots."""
+        sp, b = self.sp, self.minibatch
+        if not hasattr(self, "_pos"):
+            self._pos = torch.empty((4, b), dtype=torch.int64, device=self.device)
+            reqs = (_lib.SampleReq * 4)()
+            for p in range(2):
+                for k, mem in ((0, sp.rl[p]), (1, sp.sl[p])):
+                    r = reqs[2 * p + k]
+                    r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
+                    r.seed, r.is_ring, r.d_out = mem.seed, int(mem.is_ring), None
+            self._pos_reqs = reqs
+        for p in range(2):
+            for k, mem in ((0, sp.rl[p]), (1, sp.sl[p])):
+                self._pos_reqs[2 * p + k].call_idx = mem.sample_calls
+                mem.sample_calls += 1
+        check(lib().nfsp_sample_minibatches(self._pos_reqs, 4, b, _ptr(self._pos), None, _stream(self.device)))
+        return [self._pos[0], self._pos[2]], [self._pos[1], self._pos[3]]
+
     # ---- the whole fit() in one launch: one GPU, no collective between the SGD steps ---------------
     def _fit_fused(self, idx_rl, idx_sl, mask):
         io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask)
@@ -120,8 +140,7 @@ class Learner:
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:
                 self.iteration[p] += 1          # agent.py:216
-        idx_rl = [sp.rl[p].sample_slots(self.minibatch)[0] for p in range(2)]
-        idx_sl = [sp.sl[p].sample_slots(self.minibatch)[0] for p in range(2)]
+        idx_rl, idx_sl = self._sample_positions()
         stats = None
         if _world() == 1 and self.fused:         # one launch for the 8 SGD steps (nfsp_learner_fit)
             self._fit_fused(idx_rl, idx_sl, mask)
