@@ -302,6 +302,146 @@ learner_fit_kernel(const FitArgs F) {
     if (j < 3) w[2176 + j] = N.b2[j];
 }
 
+// ---- fit(), the row-parallel formulation ------------------------------------------------------------
+// The register kernel above is bound by instruction latency: a CTA of 256 threads per net, eight rows one after the
+// other per 64-thread group, ~450 dependent instructions per row.  Here a net has 1024 threads and ONE WARP PER ROW (two
+// hidden units per lane: the 64-wide sums of layer 2 are shuffles, no barrier), the weights live in shared memory in the
+// reference's flat layout, so the hidden layer is one conflict-free LDS per SET input bit (<= 10) in the same order
+// as the register kernel adds them.  A second phase assembles the gradient of each weight from the rows' dh / h / dz in
+// row order and applies the SGD update in place.  Two barriers per SGD step.
+constexpr int kRowThreads = 1024, kRowWarps = kRowThreads / 32, kMaxStepRows = 64;
+struct RowFitSmem {
+    float w[2180], wt[2180];          // online net, target net (best response only)
+    uint4 rec[kMaxFitRows];           // the sampled records of the minibatch
+    float dh[kMaxStepRows][64], h[kMaxStepRows][64];
+    float dz[kMaxStepRows][4];
+    uint32_t obs[kMaxStepRows];
+    float loss[kMaxStepRows], expl[kMaxStepRows];
+};
+__device__ __forceinline__ float hidden_smem(const float *w, uint32_t obs, int j) {
+    float acc = 0.f;
+    uint32_t m = obs & 0x3FFFFFFFu;
+    while (m) {  // ascending input index, as NetRegs::hidden
+        const int i = __ffs(m) - 1;
+        m &= m - 1u;
+        acc += w[i * 64 + j];
+    }
+    return fmaxf(acc + w[1920 + j], 0.f);
+}
+__device__ __forceinline__ void warp_sum9(float (&v)[9]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    }
+}
+__global__ void __launch_bounds__(kRowThreads, 1)
+learner_fit_rows_kernel(const FitArgs F) {
+    extern __shared__ __align__(16) unsigned char fit_smem_raw[];
+    RowFitSmem &S = *reinterpret_cast<RowFitSmem *>(fit_smem_raw);
+    const LearnerArgs &A = F.A;
+    const int net = blockIdx.x, player = net >> 1, is_br = net & 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (!((A.net_mask >> net) & 1)) {
+        if (F.w_out != A.w)
+            for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) F.w_out[net * NFSP_NET_PARAMS + e] = A.w[net * NFSP_NET_PARAMS + e];
+        return;
+    }
+    for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
+        S.w[e] = A.w[net * NFSP_NET_PARAMS + e];
+        if (is_br) S.wt[e] = A.w_target[player * NFSP_NET_PARAMS + e];
+    }
+    prefetch_rows(A, net, 0, F.minibatch, S.rec);  // ends with a CTA barrier
+    const float lr = F.lr[net];
+    for (int k = 0; k < F.n_steps; ++k) {
+        const int row0 = F.row0[k], rows = F.rows[k];
+        // phase 1: forward, loss, dz and dh of one row per warp
+        for (int r = warp; r < rows; r += kRowWarps) {
+            const uint4 rec = S.rec[row0 + r];
+            const uint32_t s = rec.x;
+            const int j0 = lane, j1 = lane + 32;
+            const float h0 = hidden_smem(S.w, s, j0), h1 = hidden_smem(S.w, s, j1);
+            float dz0, dz1, dz2, loss, expl = 0.f;
+            if (is_br) {
+                const uint32_t a = rec.w & 0xFFu, term = (rec.w >> 8) & 0xFFu;
+                const float rew = __uint_as_float(rec.z);
+                const float ht0 = hidden_smem(S.wt, rec.y, j0), ht1 = hidden_smem(S.wt, rec.y, j1);
+                const float hs0 = hidden_smem(S.wt, s, j0), hs1 = hidden_smem(S.wt, s, j1);
+                float v[9];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    v[c] = h0 * S.w[1984 + j0 * 3 + c] + h1 * S.w[1984 + j1 * 3 + c];
+                    v[3 + c] = ht0 * S.wt[1984 + j0 * 3 + c] + ht1 * S.wt[1984 + j1 * 3 + c];
+                    v[6 + c] = hs0 * S.wt[1984 + j0 * 3 + c] + hs1 * S.wt[1984 + j1 * 3 + c];
+                }
+                warp_sum9(v);
+                const float t2_0 = S.wt[2176], t2_1 = S.wt[2177], t2_2 = S.wt[2178];
+                expl = fmaxf(fmaxf(fmaxf(v[6] + t2_0, 0.f), fmaxf(v[7] + t2_1, 0.f)), fmaxf(v[8] + t2_2, 0.f));  // agent.py:234-238
+                const float qn = fmaxf(fmaxf(fmaxf(v[3] + t2_0, 0.f), fmaxf(v[4] + t2_1, 0.f)), fmaxf(v[5] + t2_2, 0.f));
+                const float target = rew + ((term && !A.terminal_bootstraps) ? 0.f : A.gamma * qn);
+                const float z0 = v[0] + S.w[2176], z1 = v[1] + S.w[2177], z2 = v[2] + S.w[2178];
+                const float za = a == 0 ? z0 : (a == 1 ? z1 : z2);
+                const float err = target - fmaxf(za, 0.f);  // y - Q(s,a), the other outputs have zero error
+                const float ae = fabsf(err);
+                loss = (ae > 1.f ? ae - 0.5f : 0.5f * err * err) * (1.0f / 3.0f);
+                const float dq = -(ae > 1.f ? copysignf(1.f, err) : err) * (1.0f / 3.0f) * (za > 0.f ? 1.f : 0.f);
+                dz0 = a == 0 ? dq : 0.f; dz1 = a == 1 ? dq : 0.f; dz2 = a == 2 ? dq : 0.f;
+            } else {
+                const float ya = __uint_as_float(rec.y), yb = __uint_as_float(rec.z), yc = __uint_as_float(rec.w);
+                float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = h0 * S.w[1984 + j0 * 3 + c] + h1 * S.w[1984 + j1 * 3 + c];
+                warp_sum9(v);
+                const float z0 = v[0] + S.w[2176], z1 = v[1] + S.w[2177], z2 = v[2] + S.w[2178];
+                const float m = fmaxf(z0, fmaxf(z1, z2));
+                const float x0 = expf(z0 - m), x1 = expf(z1 - m), x2 = expf(z2 - m);
+                const float inv = 1.0f / (x0 + x1 + x2);
+                const float p0 = x0 * inv, p1 = x1 * inv, p2 = x2 * inv;
+                const float ysum = ya + yb + yc;
+                loss = -(ya * logf(fmaxf(p0, 1e-7f)) + yb * logf(fmaxf(p1, 1e-7f)) + yc * logf(fmaxf(p2, 1e-7f)));
+                dz0 = p0 * ysum - ya; dz1 = p1 * ysum - yb; dz2 = p2 * ysum - yc;
+            }
+            S.h[r][j0] = h0;
+            S.h[r][j1] = h1;
+            S.dh[r][j0] = h0 > 0.f ? (S.w[1984 + j0 * 3] * dz0 + S.w[1985 + j0 * 3] * dz1 + S.w[1986 + j0 * 3] * dz2) : 0.f;
+            S.dh[r][j1] = h1 > 0.f ? (S.w[1984 + j1 * 3] * dz0 + S.w[1985 + j1 * 3] * dz1 + S.w[1986 + j1 * 3] * dz2) : 0.f;
+            if (lane == 0) {
+                S.dz[r][0] = dz0; S.dz[r][1] = dz1; S.dz[r][2] = dz2;
+                S.obs[r] = s;
+                S.loss[r] = loss;
+                S.expl[r] = expl;
+            }
+        }
+        __syncthreads();
+        // phase 2: every weight's gradient summed over the rows in row order, then w -= lr * mean gradient in place
+        const float inv_rows = 1.0f / (float)rows;
+        for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
+            float g = 0.f;
+            if (e < 1920) {
+                const int i = e >> 6, j = e & 63;
+                for (int r = 0; r < rows; ++r) g += ((S.obs[r] >> i) & 1u) ? S.dh[r][j] : 0.f;
+            } else if (e < 1984) {
+                const int j = e - 1920;
+                for (int r = 0; r < rows; ++r) g += S.dh[r][j];
+            } else if (e < 2176) {
+                const int j = (e - 1984) / 3, c = (e - 1984) - 3 * j;
+                for (int r = 0; r < rows; ++r) g += S.h[r][j] * S.dz[r][c];
+            } else {
+                const int c = e - 2176;
+                for (int r = 0; r < rows; ++r) g += S.dz[r][c];
+            }
+            S.w[e] -= lr * 1.0f * (g * inv_rows);
+        }
+        if (k == 0 && threadIdx.x == 0) {  // the statistics of the first step, as the host-driven sequence reports them
+            float ls = 0.f, ex = 0.f;
+            for (int r = 0; r < rows; ++r) { ls += S.loss[r]; ex += S.expl[r]; }
+            A.stats[4 + net] = ls;
+            if (is_br) { A.stats[player] = ex; A.stats[2 + player] = (float)rows; }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) F.w_out[net * NFSP_NET_PARAMS + e] = S.w[e];
+}
+
 // w[k] -= lr[k] * scale * grad[k]   (keras.optimizers.SGD without momentum, agent.py:45-46)
 __global__ void sgd_apply_kernel(float *__restrict__ w, const float *__restrict__ grad, float lr0, float lr1, float lr2,
                                  float lr3, float scale) {
@@ -359,7 +499,13 @@ extern "C" int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fi
             ++F.n_steps;
         }
     for (int k = 0; k < 4; ++k) F.lr[k] = lr[k];
-    learner_fit_kernel<<<4, kLearnThreads, 0, (cudaStream_t)stream>>>(F);
+    if (minibatch <= kMaxFitRows && fit_batch <= kMaxStepRows) {  // one warp per row, weights in shared memory
+        // per call: the attribute belongs to the current device's context
+        NFSP_CUDA(cudaFuncSetAttribute(learner_fit_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowFitSmem)));
+        learner_fit_rows_kernel<<<4, kRowThreads, sizeof(RowFitSmem), (cudaStream_t)stream>>>(F);
+    } else {  // large batches: the register kernel
+        learner_fit_kernel<<<4, kLearnThreads, 0, (cudaStream_t)stream>>>(F);
+    }
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }

@@ -100,7 +100,8 @@ def test_update_runs_schedules(nb):
     assert torch.isfinite(out["vec"]).all()
 
 
-def test_fit_in_one_launch_equals_the_step_by_step_sequence(nb):
+@pytest.mark.parametrize("minibatch,fit_batch", [(128, 32), (100, 24), (320, 80)])
+def test_fit_in_one_launch_equals_the_step_by_step_sequence(nb, minibatch, fit_batch):
     """nfsp_learner_fit (8 SGD steps, weights in registers) against 8 x (nfsp_learner_grads, nfsp_sgd_apply) on the same
     sampled rows: same statistics, weights equal to fp32 rounding of the same arithmetic (tolerance 1e-6 absolute on
     weights of magnitude <= 0.3; the two paths differ at most in fused-multiply-add contraction)."""
@@ -108,7 +109,9 @@ def test_fit_in_one_launch_equals_the_step_by_step_sequence(nb):
 
     a, b = _filled_selfplay(nb), _filled_selfplay(nb)
     assert torch.equal(a.weights, b.weights)
-    La, Lb = Learner(a, cfg=nb.load_config(None), fused=True), Learner(b, cfg=nb.load_config(None), fused=False)
+    # (128, 32): the reference's sizes; (100, 24): ragged last slice; (320, 80): beyond the row-parallel kernel's shared
+    # memory, played by the register kernel
+    La, Lb = (Learner(x, minibatch=minibatch, fit_batch=fit_batch, fused=f) for x, f in ((a, True), (b, False)))
     for k in range(3):
         ra, rb = La.update(), Lb.update()
         assert ra["trained"] == rb["trained"] == 0xF
