@@ -260,6 +260,24 @@ int nfsp_learner_grads(const nfsp_learner_io *io, void *stream);
 #define NFSP_MAX_FIT_STEPS 64
 int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
                      float *d_weights_out, void *stream);
+/* The same fit when several GPUs of one box train together (SURVEY 8e, C1 + C2): the all-reduce of every SGD step runs
+ * INSIDE the kernel over peer memory (NVLink).  Each rank owns an exchange buffer of NFSP_PEER_BUF_FLOATS floats, zeroed
+ * once, that every other rank can address (CUDA IPC / torch symmetric memory); d_buf[r] is rank r's buffer as THIS
+ * process sees it.  Per step a rank publishes its mean gradients and statistics in its own buffer, release-stores the
+ * step's epoch into every peer's flag words, waits for the peers' flags and sums all buffers in rank order -- so the
+ * weights stay bit-identical on every rank.  epoch0 = SGD steps exchanged through these buffers so far (the same on all
+ * ranks; add the steps of this call afterwards).  *d_err becomes 1 if a peer did not answer within ~2 s (the kernel then
+ * carries on instead of hanging the GPU; the result is invalid).  Every rank must make the same call. */
+#define NFSP_MAX_PEERS 8
+#define NFSP_PEER_BUF_FLOATS 17536
+typedef struct {
+    int32_t world, rank;
+    void *d_buf[NFSP_MAX_PEERS];
+    uint32_t epoch0;
+    uint32_t *d_err;
+} nfsp_peers;
+int nfsp_learner_fit_peers(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                           float *d_weights_out, const nfsp_peers *peers, void *stream);
 /* keras SGD step (agent.py:45-46,243,261): w[k] -= lr[k] * scale * grad[k]; scale = 1/world after a SUM
  * all-reduce.  lr is a HOST array of 4 floats. */
 int nfsp_sgd_apply(float *d_weights, const float *d_grad, const float lr[4], float scale, void *stream);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
-    "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_sgd_apply",
+    "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
 ]
 
 
@@ -41,6 +41,14 @@ class InsertReq(C.Structure):
     _fields_ = [("d_mem", C.c_void_p), ("cap", C.c_int64), ("d_total", C.c_void_p), ("d_stamp", C.c_void_p),
                 ("d_recs", C.c_void_p), ("d_counts", C.c_void_p), ("n_segments", C.c_int32), ("seg_cap", C.c_int64),
                 ("seed", C.c_uint64), ("mode", C.c_int32)]
+
+
+MAX_PEERS, PEER_BUF_FLOATS = 8, 17536  # NFSP_MAX_PEERS, NFSP_PEER_BUF_FLOATS
+
+
+class Peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d_buf", C.c_void_p * MAX_PEERS), ("epoch0", C.c_uint32),
+                ("d_err", C.c_void_p)]
 
 
 class SampleReq(C.Structure):
@@ -116,6 +124,8 @@ def lib():
     L.nfsp_gather_sl.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.nfsp_learner_grads.argtypes = [C.POINTER(LearnerIO), vp]
     L.nfsp_learner_fit.argtypes = [C.POINTER(LearnerIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp, vp]
+    L.nfsp_learner_fit_peers.argtypes = [C.POINTER(LearnerIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp,
+                                         C.POINTER(Peers), vp]
     L.nfsp_sgd_apply.argtypes = [vp, vp, C.POINTER(C.c_float * 4), C.c_float, vp]
     _lib = L
     return L

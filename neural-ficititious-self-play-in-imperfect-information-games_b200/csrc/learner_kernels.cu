@@ -259,7 +259,30 @@ struct FitArgs {
     int n_steps, minibatch;
     int row0[NFSP_MAX_FIT_STEPS], rows[NFSP_MAX_FIT_STEPS];
     float lr[4];
+    // several GPUs training together: every rank's exchange buffer as this process sees it (peer memory over NVLink)
+    int world, rank;
+    float *peer[NFSP_MAX_PEERS];
+    uint32_t epoch0;     // SGD steps exchanged through these buffers so far
+    uint32_t *err;       // set to 1 if a peer did not answer in time
 };
+
+// exchange buffer of one rank, in floats: two parities x four nets x a slot of kPeerSlot floats (2179 mean gradients, then
+// loss sum, exploitability sum, rows), then world x 4 epoch flags written BY the peers
+constexpr int kPeerSlot = 2184, kPeerFlagOff = 2 * 4 * kPeerSlot;
+static_assert(kPeerFlagOff + NFSP_MAX_PEERS * 4 <= NFSP_PEER_BUF_FLOATS, "exchange buffer too small");
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_volatile_f32(const float *p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(kLearnThreads)
 learner_fit_kernel(const FitArgs F) {
     __shared__ float red_all[kRowGroups][4][2][4];
@@ -412,8 +435,14 @@ learner_fit_rows_kernel(const FitArgs F) {
             }
         }
         __syncthreads();
-        // phase 2: every weight's gradient summed over the rows in row order, then w -= lr * mean gradient in place
+        // phase 2: every weight's gradient summed over the rows in row order, then w -= lr * mean gradient in place.
+        // With peers the mean gradient goes into this rank's exchange buffer first and the update uses the sum over
+        // all ranks' buffers, read over NVLink in rank order: the all-reduce of the step, inside the kernel.
         const float inv_rows = 1.0f / (float)rows;
+        const bool peers = F.world > 1;
+        const uint32_t epoch = F.epoch0 + (uint32_t)k + 1u;
+        const int slot = ((int)(epoch & 1u) * 4 + net) * kPeerSlot;
+        float *mine = peers ? F.peer[F.rank] + slot : nullptr;
         for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
             float g = 0.f;
             if (e < 1920) {
@@ -429,13 +458,52 @@ learner_fit_rows_kernel(const FitArgs F) {
                 const int c = e - 2176;
                 for (int r = 0; r < rows; ++r) g += S.dz[r][c];
             }
-            S.w[e] -= lr * 1.0f * (g * inv_rows);
+            if (peers) mine[e] = g * inv_rows;
+            else S.w[e] -= lr * 1.0f * (g * inv_rows);
         }
         if (k == 0 && threadIdx.x == 0) {  // the statistics of the first step, as the host-driven sequence reports them
             float ls = 0.f, ex = 0.f;
             for (int r = 0; r < rows; ++r) { ls += S.loss[r]; ex += S.expl[r]; }
-            A.stats[4 + net] = ls;
-            if (is_br) { A.stats[player] = ex; A.stats[2 + player] = (float)rows; }
+            if (peers) {
+                mine[2180] = ls; mine[2181] = ex; mine[2182] = (float)rows;
+            } else {
+                A.stats[4 + net] = ls;
+                if (is_br) { A.stats[player] = ex; A.stats[2 + player] = (float)rows; }
+            }
+        }
+        if (peers) {
+            __threadfence_system();  // this rank's slot is complete before any peer sees the flag
+            __syncthreads();
+            const int t = threadIdx.x;
+            if (t < F.world && t != F.rank) {
+                st_release_sys(reinterpret_cast<uint32_t *>(F.peer[t] + kPeerFlagOff) + F.rank * 4 + net, epoch);
+                const uint32_t *flag = reinterpret_cast<const uint32_t *>(F.peer[F.rank] + kPeerFlagOff) + t * 4 + net;
+                const long long t0 = clock64();
+                while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+                    if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; never hang the GPU
+                        *F.err = 1u;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+            }
+            __syncthreads();
+            const float scale = 1.0f / (float)F.world;
+            for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
+                float g = 0.f;
+                for (int r = 0; r < F.world; ++r) g += ld_volatile_f32(F.peer[r] + slot + e);
+                S.w[e] -= lr * scale * g;
+            }
+            if (k == 0 && threadIdx.x == 0) {
+                float ls = 0.f, ex = 0.f, rw = 0.f;
+                for (int r = 0; r < F.world; ++r) {
+                    ls += ld_volatile_f32(F.peer[r] + slot + 2180);
+                    ex += ld_volatile_f32(F.peer[r] + slot + 2181);
+                    rw += ld_volatile_f32(F.peer[r] + slot + 2182);
+                }
+                A.stats[4 + net] = ls;
+                if (is_br) { A.stats[player] = ex; A.stats[2 + player] = rw; }
+            }
         }
         __syncthreads();
     }
@@ -481,8 +549,28 @@ extern "C" int nfsp_learner_grads(const nfsp_learner_io *io, void *stream) {
     return NFSP_OK;
 }
 
+static int learner_fit_impl(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                            float *d_weights_out, const nfsp_peers *peers, void *stream);
+
 extern "C" int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
                                 float *d_weights_out, void *stream) {
+    return learner_fit_impl(io, minibatch, fit_batch, epochs, lr, d_weights_out, nullptr, stream);
+}
+
+extern "C" int nfsp_learner_fit_peers(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                                      float *d_weights_out, const nfsp_peers *peers, void *stream) {
+    NFSP_CHECK_ARG(peers && peers->world >= 2 && peers->world <= NFSP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                   "2..%d peers", NFSP_MAX_PEERS);
+    NFSP_CHECK_ARG(peers->d_err, "null error word");
+    for (int r = 0; r < peers->world; ++r) NFSP_CHECK_ARG(peers->d_buf[r], "null exchange buffer of rank %d", r);
+    NFSP_CHECK_ARG(minibatch <= nfsp::kMaxFitRows && fit_batch <= nfsp::kMaxStepRows,
+                   "the peer exchange lives in the row-parallel kernel: minibatch <= %d, fit_batch <= %d", nfsp::kMaxFitRows,
+                   nfsp::kMaxStepRows);
+    return learner_fit_impl(io, minibatch, fit_batch, epochs, lr, d_weights_out, peers, stream);
+}
+
+static int learner_fit_impl(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
+                            float *d_weights_out, const nfsp_peers *peers, void *stream) {
     NFSP_CHECK_ARG(lr && d_weights_out, "null argument");
     NFSP_CHECK_ARG(minibatch >= 1 && fit_batch >= 1 && epochs >= 1, "bad fit geometry");
     FitArgs F;
@@ -499,6 +587,12 @@ extern "C" int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fi
             ++F.n_steps;
         }
     for (int k = 0; k < 4; ++k) F.lr[k] = lr[k];
+    F.world = 1; F.rank = 0; F.epoch0 = 0u; F.err = nullptr;
+    for (int r = 0; r < NFSP_MAX_PEERS; ++r) F.peer[r] = nullptr;
+    if (peers) {
+        F.world = peers->world; F.rank = peers->rank; F.epoch0 = peers->epoch0; F.err = peers->d_err;
+        for (int r = 0; r < peers->world; ++r) F.peer[r] = (float *)peers->d_buf[r];
+    }
     if (minibatch <= kMaxFitRows && fit_batch <= kMaxStepRows) {  // one warp per row, weights in shared memory
         // per call: the attribute belongs to the current device's context
         NFSP_CUDA(cudaFuncSetAttribute(learner_fit_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowFitSmem)));

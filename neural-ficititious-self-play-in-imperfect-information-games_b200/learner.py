@@ -55,6 +55,9 @@ class Learner:
         self.fused = bool(fused)  # single GPU: the whole fit() as one kernel; False = one launch pair per SGD step
         self.target = selfplay.weights[[1, 3]].clone().contiguous()   # agent.py:70-72
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
+        self._peers = None
+        if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
+            self._setup_peers()
         self.iteration = [0, 0]
         self.target_update_count = [0, 0]
         self.temp = [1.0, 1.0]
@@ -92,6 +95,39 @@ class Learner:
                 mem.sample_calls += 1
         check(lib().nfsp_sample_minibatches(self._pos_reqs, 4, b, _ptr(self._pos), None, _stream(self.device)))
         return [self._pos[0], self._pos[2]], [self._pos[1], self._pos[3]]
+
+    # ---- several GPUs of one box: the all-reduce of every SGD step inside the fit kernel, over peer memory ----
+    def _setup_peers(self):
+        """One exchange buffer per rank that every rank can address (torch symmetric memory: CUDA IPC under the hood).
+        Falls back to the NCCL path (one all-reduce per SGD step) if the ranks cannot map each other's memory."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty(_lib.PEER_BUF_FLOATS, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            torch.cuda.synchronize(self.device)
+            dist.barrier()  # every buffer is zero before anybody's first flag can arrive
+            p = _lib.Peers()
+            p.world, p.rank = dist.get_world_size(), dist.get_rank()
+            if p.world > _lib.MAX_PEERS:
+                raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
+            for r in range(p.world):
+                p.d_buf[r] = int(hdl.buffer_ptrs[r])
+            self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            p.d_err = self._peer_err.data_ptr()
+            self._peers, self._peer_keep, self._epoch = p, (buf, hdl), 0
+        except Exception as e:  # noqa: BLE001  (no peer access: NCCL per step, same results up to summation order)
+            self._peers = None
+            self._peer_note = "peer exchange unavailable: %r" % (e,)
+
+    def _fit_peers(self, idx_rl, idx_sl, mask):
+        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask)
+        lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
+        self._peers.epoch0 = self._epoch & 0xFFFFFFFF
+        check(lib().nfsp_learner_fit_peers(C.byref(io), self.minibatch, self.fit_batch, self.epochs, lr,
+                                           _ptr(self.sp.weights), C.byref(self._peers), _stream(self.device)))
+        self._epoch += self.epochs * ((self.minibatch + self.fit_batch - 1) // self.fit_batch)
 
     # ---- the whole fit() in one launch: one GPU, no collective between the SGD steps ---------------
     def _fit_fused(self, idx_rl, idx_sl, mask):
@@ -142,8 +178,12 @@ class Learner:
                 self.iteration[p] += 1          # agent.py:216
         idx_rl, idx_sl = self._sample_positions()
         stats = None
-        if _world() == 1 and self.fused:         # one launch for the 8 SGD steps (nfsp_learner_fit)
-            self._fit_fused(idx_rl, idx_sl, mask)
+        if self.fused and (_world() == 1 or self._peers is not None):
+            # one launch for the 8 SGD steps; with peers the per-step all-reduce happens inside it over NVLink
+            if _world() == 1:
+                self._fit_fused(idx_rl, idx_sl, mask)
+            else:
+                self._fit_peers(idx_rl, idx_sl, mask)
             stats = self.flat[GRAD:].clone()     # statistics of the first step, as below
         else:
             for _ in range(self.epochs):         # Keras fit(epochs=2), batch_size 32 (agent.py:243,261)
@@ -153,6 +193,8 @@ class Learner:
                         stats = self.flat[GRAD:].clone()
         if sync:
             self._loss = stats.cpu().tolist()
+            if self._peers is not None and int(self._peer_err.item()):
+                raise RuntimeError("a peer GPU did not answer during the gradient exchange")
         s = getattr(self, "_loss", [0.0] * N_STATS)
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:

@@ -1,0 +1,67 @@
+"""Two or more GPUs of one box (not collected by pytest; run it under torchrun):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_learner_check.py
+
+The fit with the all-reduce inside the kernel (peer memory, nfsp_learner_fit_peers) against the same fit as eight
+launch pairs with one NCCL all-reduce each, on identical memories and sampled rows: same statistics, weights equal to
+1e-6 absolute (the two differ in the order the ranks' gradients are summed), and -- for the peer path -- weights
+bit-identical on every rank."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import nfsp_b200  # noqa: E402
+from nfsp_b200.learner import Learner  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n, steps = 4096, 8
+
+
+def filled():
+    sp = nfsp_b200.SelfPlay(n, seed=5, game0=rank * n, device=dev, eta=0.3, epsilon=0.2, rl_capacity=1 << 16,
+                            sl_capacity=1 << 16, max_steps_per_call=steps)
+    w = sp.weights.clone()
+    w[:, 1920:1984] = 0.05
+    w[:, 2176:] = 0.1
+    sp.set_weights(w)
+    for _ in range(4):
+        sp.rollout(steps)
+    return sp
+
+
+a, b = filled(), filled()
+La, Lb = Learner(a, fused=True), Learner(b, fused=False)
+assert La._peers is not None, getattr(La, "_peer_note", "no peers")
+for k in range(4):
+    ra, rb = La.update(), Lb.update()
+    assert ra["trained"] == rb["trained"] == 0xF, (ra, rb)
+    assert np.allclose(ra["loss"], rb["loss"], rtol=1e-5, atol=1e-5), (ra["loss"], rb["loss"])
+    assert abs(ra["exploitability"] - rb["exploitability"]) < 1e-5
+    d = (a.weights - b.weights).abs().max().item()
+    assert d < 1e-6, (k, d)
+    mine = a.weights.clone()
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(mine, ref), "peer path: weights differ between ranks"
+ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+for name, L in (("peer exchange", La), ("nccl per step", Lb)):
+    dist.barrier()
+    s, e = ev(), ev()
+    s.record()
+    for _ in range(10):
+        L.update(sync=False)
+    e.record()
+    e.synchronize()
+    if rank == 0:
+        print("%-14s %.1f us per update" % (name, s.elapsed_time(e) * 100))
+assert int(La._peer_err.item()) == 0
+if rank == 0:
+    print("mgpu learner check ok: world", world)
+dist.destroy_process_group()
