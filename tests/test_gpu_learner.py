@@ -121,6 +121,77 @@ def test_fit_in_one_launch_equals_the_step_by_step_sequence(nb, minibatch, fit_b
         assert d < 1e-6, (k, d)
 
 
+def test_peer_exchange_protocol_two_ranks_on_one_gpu(nb):
+    """nfsp_learner_fit_peers (the all-reduce of every SGD step inside the kernel) with TWO ranks played by two kernels
+    running side by side on two streams of one GPU, each with its own exchange buffer.  Reference: the same eight steps
+    as nfsp_learner_grads of both ranks, their gradients added on the device, nfsp_sgd_apply with scale 1/2.  Weights
+    must be bit-identical between the ranks and within 1e-6 of the reference; the statistics are the sums over ranks."""
+    from nfsp_b200 import _lib
+    from nfsp_b200._lib import check
+    from nfsp_b200.batched import _ptr, _stream
+    from nfsp_b200.learner import GRAD, Learner
+
+    sps = [_filled_selfplay(nb), _filled_selfplay(nb, n=2048)]      # different games -> different memories
+    w0 = sps[0].weights.clone()
+    sps[1].set_weights(w0.clone())
+    Ls = [Learner(sp, fused=False) for sp in sps]
+    idx = [L._sample_positions() for L in Ls]
+    lr = (C.c_float * 4)(0.1, 0.05, 0.1, 0.05)
+    # reference, step by step
+    stats_ref = None
+    for _ in range(2):
+        for row0 in range(0, 128, 32):
+            for L, (irl, isl) in zip(Ls, idx):
+                io = L._io(irl, isl, row0, 32, 0xF)
+                check(nb.lib().nfsp_learner_grads(C.byref(io), _stream(L.device)))
+            total = Ls[0].flat + Ls[1].flat
+            if stats_ref is None:
+                stats_ref = total[GRAD:].clone()
+            for L in Ls:
+                check(nb.lib().nfsp_sgd_apply(_ptr(L.sp.weights), _ptr(total), C.byref(lr), 0.5, _stream(L.device)))
+    ref = [L.sp.weights.clone() for L in Ls]
+    assert torch.equal(ref[0], ref[1])
+    # the same through the peer exchange: two kernels that wait for each other
+    dev = sps[0].device
+    bufs = [torch.zeros(_lib.PEER_BUF_FLOATS, dtype=torch.float32, device=dev) for _ in range(2)]
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    for epoch0 in (0, 8):   # two calls: the parities and epochs carry on from one fit to the next
+        for L in Ls:
+            L.sp.weights.copy_(w0)
+        torch.cuda.synchronize()
+        for r, (L, (irl, isl)) in enumerate(zip(Ls, idx)):
+            io = L._io(irl, isl, 0, 128, 0xF)
+            p = _lib.Peers()
+            p.world, p.rank, p.epoch0, p.d_err = 2, r, epoch0, err.data_ptr()
+            for q in range(2):
+                p.d_buf[q] = bufs[q].data_ptr()
+            with torch.cuda.stream(streams[r]):
+                check(nb.lib().nfsp_learner_fit_peers(C.byref(io), 128, 32, 2, lr, _ptr(L.sp.weights), C.byref(p),
+                                                         _stream(dev)))
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0, "a rank timed out waiting for its peer"
+        assert torch.equal(Ls[0].sp.weights, Ls[1].sp.weights)
+        assert (Ls[0].sp.weights - ref[0]).abs().max().item() < 1e-6
+        for L in Ls:
+            assert torch.allclose(L.flat[GRAD:], stats_ref, rtol=1e-5, atol=1e-5)
+
+
+def test_peer_exchange_on_real_gpus_when_there_are_two():
+    """tests/mgpu_learner_check.py under torchrun (peer memory over NVLink against the NCCL path); needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(root, "tests", "mgpu_learner_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "mgpu learner check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_sgd_reduces_loss_on_a_fixed_minibatch(nb):
     from nfsp_b200.learner import GRAD, Learner
 
