@@ -451,10 +451,11 @@ class SelfPlay:
         return rl, sl
 
     def flush(self):
-        """Move the staged records into the memories (stream-ordered, no host sync).  The reservoir inserts are three
-        small latency-bound launches per player on 1/13 of the records; they run on a side stream beside the
-        bandwidth-bound ring inserts (different memories, different rows of the count array) and join the caller's
-        stream before this returns."""
+        """Move the staged records into the memories (stream-ordered, no host sync): both players' rings in one
+        insert + commit pair on the caller's stream, both reservoirs as stamp + write + commit -- latency-bound, 1/13 of
+        the records -- on a side stream beside them (different memories, different rows of the count array).  The side
+        stream starts after the rollout and joins the caller's stream before this returns, so whatever follows (the
+        next rollout overwrites the staging arrays) waits for both."""
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_side"):
             self._side = torch.cuda.Stream(self.device)
