@@ -341,16 +341,6 @@ struct RowFitSmem {
     uint32_t obs[kMaxStepRows];
     float loss[kMaxStepRows], expl[kMaxStepRows];
 };
-__device__ __forceinline__ float hidden_smem(const float *w, uint32_t obs, int j) {
-    float acc = 0.f;
-    uint32_t m = obs & 0x3FFFFFFFu;
-    while (m) {  // ascending input index, as NetRegs::hidden
-        const int i = __ffs(m) - 1;
-        m &= m - 1u;
-        acc += w[i * 64 + j];
-    }
-    return fmaxf(acc + w[1920 + j], 0.f);
-}
 __device__ __forceinline__ void warp_sum9(float (&v)[9]) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -382,13 +372,34 @@ learner_fit_rows_kernel(const FitArgs F) {
             const uint4 rec = S.rec[row0 + r];
             const uint32_t s = rec.x;
             const int j0 = lane, j1 = lane + 32;
-            const float h0 = hidden_smem(S.w, s, j0), h1 = hidden_smem(S.w, s, j1);
+            // the hidden units of this lane for the online net on s and, for a best-response net, the target net on s
+            // and s2: ONE loop over the set bits of s (four independent loads per bit) and one over those of s2, each
+            // accumulator summed in ascending input order as in NetRegs::hidden
+            float h0 = 0.f, h1 = 0.f, hs0 = 0.f, hs1 = 0.f, ht0 = 0.f, ht1 = 0.f;
+            for (uint32_t m = s & 0x3FFFFFFFu; m; m &= m - 1u) {
+                const int i = (__ffs(m) - 1) * 64;
+                h0 += S.w[i + j0];
+                h1 += S.w[i + j1];
+                if (is_br) {
+                    hs0 += S.wt[i + j0];
+                    hs1 += S.wt[i + j1];
+                }
+            }
+            h0 = fmaxf(h0 + S.w[1920 + j0], 0.f);
+            h1 = fmaxf(h1 + S.w[1920 + j1], 0.f);
             float dz0, dz1, dz2, loss, expl = 0.f;
             if (is_br) {
                 const uint32_t a = rec.w & 0xFFu, term = (rec.w >> 8) & 0xFFu;
                 const float rew = __uint_as_float(rec.z);
-                const float ht0 = hidden_smem(S.wt, rec.y, j0), ht1 = hidden_smem(S.wt, rec.y, j1);
-                const float hs0 = hidden_smem(S.wt, s, j0), hs1 = hidden_smem(S.wt, s, j1);
+                for (uint32_t m = rec.y & 0x3FFFFFFFu; m; m &= m - 1u) {
+                    const int i = (__ffs(m) - 1) * 64;
+                    ht0 += S.wt[i + j0];
+                    ht1 += S.wt[i + j1];
+                }
+                hs0 = fmaxf(hs0 + S.wt[1920 + j0], 0.f);
+                hs1 = fmaxf(hs1 + S.wt[1920 + j1], 0.f);
+                ht0 = fmaxf(ht0 + S.wt[1920 + j0], 0.f);
+                ht1 = fmaxf(ht1 + S.wt[1920 + j1], 0.f);
                 float v[9];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -447,12 +458,15 @@ learner_fit_rows_kernel(const FitArgs F) {
             float g = 0.f;
             if (e < 1920) {
                 const int i = e >> 6, j = e & 63;
+#pragma unroll 8
                 for (int r = 0; r < rows; ++r) g += ((S.obs[r] >> i) & 1u) ? S.dh[r][j] : 0.f;
             } else if (e < 1984) {
                 const int j = e - 1920;
+#pragma unroll 8
                 for (int r = 0; r < rows; ++r) g += S.dh[r][j];
             } else if (e < 2176) {
                 const int j = (e - 1984) / 3, c = (e - 1984) - 3 * j;
+#pragma unroll 8
                 for (int r = 0; r < rows; ++r) g += S.h[r][j] * S.dz[r][c];
             } else {
                 const int c = e - 2176;
