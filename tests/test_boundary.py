@@ -127,3 +127,36 @@ def test_dropin_modules_import_without_gpu(nb):
     import numpy as np
 
     assert newenv.action_code(np.array([[0.0, 0.5, 0.5], [0, 0, 0], [0.1, 0.2, 0.9]])).tolist() == [1, 3, 2]
+
+
+def test_ctypes_mirrors_match_the_header(nb, tmp_path):
+    """Every struct of include/nfsp_b200.h has the size and field offsets of its ctypes mirror in _lib.py, and the
+    constants agree: a C program compiled against the header (gcc, no CUDA needed) prints them."""
+    from nfsp_b200 import _lib
+
+    structs = {"nfsp_rollout_io": _lib.RolloutIO, "nfsp_insert_req": _lib.InsertReq, "nfsp_sample_req": _lib.SampleReq,
+               "nfsp_learner_io": _lib.LearnerIO, "nfsp_peers": _lib.Peers}
+    consts = {"NFSP_RULES_LEGACY": _lib.RULES_LEGACY, "NFSP_RULES_NFSP": _lib.RULES_NFSP, "NFSP_OBS_DIM": _lib.OBS_DIM,
+              "NFSP_ACTIONS": _lib.ACTIONS, "NFSP_HIDDEN": _lib.HIDDEN, "NFSP_NET_PARAMS": _lib.NET_PARAMS,
+              "NFSP_EXPORT_FIELDS": _lib.EXPORT_FIELDS, "NFSP_LEGACY_EXPORT_FIELDS": _lib.LEGACY_EXPORT_FIELDS,
+              "NFSP_STATS_FIELDS": _lib.STATS_FIELDS, "NFSP_MAX_PEERS": _lib.MAX_PEERS,
+              "NFSP_PEER_BUF_FLOATS": _lib.PEER_BUF_FLOATS}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nfsp_b200.h"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    for name in consts:
+        lines.append('printf("%s %%ld\\n", (long)(%s));' % (name, name))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, (name, field)
+    for name, value in consts.items():
+        assert int(got[name]) == value, name
