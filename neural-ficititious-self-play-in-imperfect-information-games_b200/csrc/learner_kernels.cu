@@ -454,13 +454,30 @@ learner_fit_rows_kernel(const FitArgs F) {
         const uint32_t epoch = F.epoch0 + (uint32_t)k + 1u;
         const int slot = ((int)(epoch & 1u) * 4 + net) * kPeerSlot;
         float *mine = peers ? F.peer[F.rank] + slot : nullptr;
-        for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
+        auto apply = [&](int e, float g) {
+            if (peers) mine[e] = g * inv_rows;
+            else S.w[e] -= lr * 1.0f * (g * inv_rows);
+        };
+        // W1: warp i owns input i and both halves of the hidden units.  Only ~30 % of the input bits are set: the rows
+        // that have bit i come from one ballot (lane r tests row r) and only those are added, in row order -- adding the
+        // zeros of the other rows would not change a bit of the sum.
+        for (int i = warp; i < 30; i += kRowWarps) {
+            float g0 = 0.f, g1 = 0.f;
+            for (int rb = 0; rb < rows; rb += 32) {
+                const int r = rb + lane;
+                for (uint32_t m = __ballot_sync(0xFFFFFFFFu, r < rows && ((S.obs[r] >> i) & 1u)); m; m &= m - 1u) {
+                    const int rr = rb + __ffs(m) - 1;
+                    g0 += S.dh[rr][lane];
+                    g1 += S.dh[rr][lane + 32];
+                }
+            }
+            apply(i * 64 + lane, g0);
+            apply(i * 64 + lane + 32, g1);
+        }
+        // b1, W2, b2: one element per thread, summed over the rows in row order
+        for (int e = 1920 + threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
             float g = 0.f;
-            if (e < 1920) {
-                const int i = e >> 6, j = e & 63;
-#pragma unroll 8
-                for (int r = 0; r < rows; ++r) g += ((S.obs[r] >> i) & 1u) ? S.dh[r][j] : 0.f;
-            } else if (e < 1984) {
+            if (e < 1984) {
                 const int j = e - 1920;
 #pragma unroll 8
                 for (int r = 0; r < rows; ++r) g += S.dh[r][j];
@@ -472,8 +489,7 @@ learner_fit_rows_kernel(const FitArgs F) {
                 const int c = e - 2176;
                 for (int r = 0; r < rows; ++r) g += S.dz[r][c];
             }
-            if (peers) mine[e] = g * inv_rows;
-            else S.w[e] -= lr * 1.0f * (g * inv_rows);
+            apply(e, g);
         }
         if (k == 0 && threadIdx.x == 0) {  // the statistics of the first step, as the host-driven sequence reports them
             float ls = 0.f, ex = 0.f;
