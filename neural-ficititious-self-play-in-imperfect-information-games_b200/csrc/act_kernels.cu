@@ -201,7 +201,7 @@ rollout_kernel(const RolloutArgs A) {
             bulk_g2s(smem_u32(sw) + off, reinterpret_cast<const uint8_t *>(A.pack) + off, len, bar);
         }
     }
-    mbar_wait(bar, 0);
+    bool image_ready = false;  // waited for just before the first MLP evaluation: the copy overlaps the first step's game logic
 
     FastCounters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
@@ -230,6 +230,10 @@ rollout_kernel(const RolloutArgs A) {
             const uint32_t xrow = sg >= 9u ? 3u + ((((ca * 3u + g.pub()) * 2u + dl) << 2) | g.fin0()) : ca;
             const uint32_t yrow = 75u + dl * 18u + sg;
             float v0, v1, v2;
+            if (!image_ready) {
+                mbar_wait(bar, 0);
+                image_ready = true;
+            }
             mlp_forward_tables(sw, xrow, yrow, g.p() * 2u + (uint32_t)d.pol, rot, v0, v1, v2);
             if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; }
             fast_finish<kDebug>(g, s_lut, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
@@ -238,6 +242,7 @@ rollout_kernel(const RolloutArgs A) {
         if (live) A.state[i] = g.pack();
         c.wide.trans += live ? A.n_steps : 0;
     }
+    if (!image_ready) mbar_wait(bar, 0);  // no block came this way: the copy into this CTA's shared memory must still land
     c.spill();
     if (A.stats) c.wide.commit(s_stats, A.stats);
 }
