@@ -129,6 +129,9 @@ int nfsp_expand_obs(const uint32_t *d_masks, int64_t n, float *d_out, void *stre
  * each NFSP_NET_PARAMS floats in Keras Dense order W1[30][64], b1[64], W2[64][3], b2[3]
  * (agent.py:90-116).  Repacks them into the kernels' layouts inside the handle. */
 int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *stream);
+/* The same from host memory (pinned for a truly asynchronous copy): float[4][2179] is copied into d_weights on the
+ * stream, then the images are built from it -- one call for the learner -> actor weight hand-over of a step. */
+int nfsp_act_set_weights_from_host(nfsp_env_t h, const float *h_weights, float *d_weights, void *stream);
 /* batched Model.predict (agent.py:126,143): d_obs uint32[n] masks, d_net int8[n] net index;
  * d_out float[n][3] = Q-values (relu head) for BR nets, softmax probabilities for average nets */
 int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "nfsp_legacy_reset", "nfsp_legacy_set_hands", "nfsp_legacy_step", "nfsp_legacy_get_new_state",
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
-    "nfsp_act_set_weights", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
+    "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
 ]
@@ -111,6 +111,7 @@ def lib():
     L.nfsp_legacy_export.argtypes = [vp, vp, vp]
     L.nfsp_expand_obs.argtypes = [vp, C.c_int64, vp, vp]
     L.nfsp_act_set_weights.argtypes = [vp, vp, vp]
+    L.nfsp_act_set_weights_from_host.argtypes = [vp, vp, vp, vp]
     L.nfsp_act_forward.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_act_forward_tc.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]

@@ -385,11 +385,14 @@ class SelfPlay:
         copy) is copied into the device tensor this object already holds: no allocation on the step path."""
         on_host = not (isinstance(weights, torch.Tensor) and weights.is_cuda)
         if on_host and getattr(self, "_own_weights", False) and isinstance(weights, torch.Tensor) \
-                and weights.dtype == torch.float32 and tuple(weights.shape) == tuple(self.weights.shape):
-            self.weights.copy_(weights, non_blocking=True)
-        else:
-            self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
-            self._own_weights = on_host  # a device tensor handed in stays the caller's: never written through
+                and weights.dtype == torch.float32 and weights.is_contiguous() and tuple(weights.shape) == tuple(self.weights.shape):
+            # host -> device copy and the rebuild of the weight images in ONE library call (cudaMemcpyAsync on the stream)
+            self._host_src = weights  # the copy is asynchronous: keep the source alive until the next hand-over
+            check(lib().nfsp_act_set_weights_from_host(self.env._h, C.c_void_p(weights.data_ptr()), _ptr(self.weights),
+                                                       _stream(self.device)))
+            return
+        self.weights = _as(weights, torch.float32, self.device, (4, _lib.NET_PARAMS))
+        self._own_weights = on_host  # a device tensor handed in stays the caller's: never written through
         check(lib().nfsp_act_set_weights(self.env._h, _ptr(self.weights), _stream(self.device)))
 
     def forward(self, obs_masks, net_idx, tensor_cores=False):

@@ -25,8 +25,9 @@ constexpr int kW2Floats = 4 * 3 * kFwdRowQuads * 4;
 constexpr int kB2Floats = 4 * 4;
 constexpr int kPackFloats = kW1Floats + kW2Floats + kB2Floats;
 
-__global__ void pack_weights_kernel(const float *__restrict__ w, float *__restrict__ pack) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats; e += gridDim.x * blockDim.x) {
+// element e of the batched forward's weight image
+__device__ __forceinline__ float pack_weights_value(const float *__restrict__ w, int e) {
+    {
         float v = 0.f;
         if (e < kW1Floats) {
             const int c = e & 3, pos = (e >> 2) % kFwdRowQuads, row = (e >> 2) / kFwdRowQuads;
@@ -42,7 +43,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
             const int f = e - kW1Floats - kW2Floats, c = f & 3, net = f >> 2;
             if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
         }
-        pack[e] = v;
+        return v;
     }
 }
 
@@ -80,8 +81,9 @@ __device__ __forceinline__ uint32_t seq_bits(int rr, int d, int id) {
     return bits;
 }
 
-__global__ void pack_tables_kernel(const float *__restrict__ w, float *__restrict__ img) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kTabImageFloats; e += gridDim.x * blockDim.x) {
+// element e of the rollout's table image
+__device__ __forceinline__ float pack_tables_value(const float *__restrict__ w, int e) {
+    {
         float v = 0.f;
         if (e < kTabFloats) {
             const int x = e & 3, pos = (e >> 2) % kRowQuads, row = (e >> 2) / kRowQuads;
@@ -111,8 +113,14 @@ __global__ void pack_tables_kernel(const float *__restrict__ w, float *__restric
             const int f = e - kTabFloats - kTabW2Floats, c = f & 3, net = f >> 2;
             if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
         }
-        img[e] = v;
+        return v;
     }
+}
+
+// both images in one launch: pack = [batched-forward image (kPackFloats) | rollout table image (kTabImageFloats)]
+__global__ void pack_images_kernel(const float *__restrict__ w, float *__restrict__ pack) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats + kTabImageFloats; e += gridDim.x * blockDim.x)
+        pack[e] = e < kPackFloats ? pack_weights_value(w, e) : pack_tables_value(w, e - kPackFloats);
 }
 
 // one decision of net `net`: layer 1 as two rotated row reads streamed into layer 2
@@ -263,15 +271,21 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
     }
-    pack_weights_kernel<<<(kPackFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
-    NFSP_LAUNCH_CHECK();
-    pack_tables_kernel<<<(kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights,
-                                                                                         h->d_wpack + kPackFloats);
+    pack_images_kernel<<<(kPackFloats + kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
     NFSP_LAUNCH_CHECK();
     const int rc = nfsp_pack_tc_image(h, d_weights, (cudaStream_t)stream);
     if (rc != NFSP_OK) return rc;
     h->has_weights = true;
     return NFSP_OK;
+}
+
+extern "C" int nfsp_act_set_weights_from_host(nfsp_env_t h, const float *h_weights, float *d_weights, void *stream) {
+    NFSP_CHECK_ARG(h != nullptr && h_weights != nullptr && d_weights != nullptr, "null argument");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
+    NFSP_CUDA(cudaMemcpyAsync(d_weights, h_weights, sizeof(float) * 4 * NFSP_NET_PARAMS, cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+    return nfsp_act_set_weights(h, d_weights, stream);
 }
 
 extern "C" int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
