@@ -269,14 +269,16 @@ def test_legacy_rollout_is_independent_of_launch_batching(nb):
     """One launch of 12 README iterations == launches of 7 + 5 == twelve launches of 1: between launches a live hand
     travels as the packed word and comes back through the state-key table of the table-driven kernel."""
     n = 50_000
-    envs = [nb.BatchedLegacyEnv(n, seed=8) for _ in range(3)]
+    envs = [nb.BatchedLegacyEnv(n, seed=8) for _ in range(4)]
     for e in envs:
         e.reset()
+    envs[3].rollout(12)  # the kernel variant that writes no records must leave the same words
     whole = envs[0].rollout(12, trace=True)["raw"]
     parts = torch.cat([envs[1].rollout(7, trace=True)["raw"], envs[1].rollout(5, trace=True)["raw"]], dim=1)
     ones = torch.cat([envs[2].rollout(1, trace=True)["raw"] for _ in range(12)], dim=1)
     assert torch.equal(whole, parts) and torch.equal(whole, ones)
-    assert torch.equal(envs[0].state_words(), envs[1].state_words()) and torch.equal(envs[0].state_words(), envs[2].state_words())
+    for e in envs[1:]:
+        assert torch.equal(envs[0].state_words(), e.state_words())
     live = int((whole[0, -1, :, 0] >> 24 & 1).eq(0).sum())
     assert live > n // 4  # plenty of hands were still live at the launch boundaries
 
