@@ -175,6 +175,9 @@ def test_walking_the_legacy_image_reproduces_the_oracle_records(legacy_image):
     b.reset(0)
     ref = b.rollout(1, iters)
     key = (seed & M32, seed >> 32)
+    keys = img.view(np.uint8)[L_KEY_OFF: L_KEY_OFF + 4096]
+    assert int((keys != 0xFF).sum()) == rows and keys[5 | 5 << 3] == 0  # a fresh hand (left 4/4, pots 0/0) is row 0
+    live_keys = set()
     ended = 0
     for g in range(n):
         x = [int(v) for v in orc.philox((g, 0, 0, 0), key)]
@@ -197,5 +200,14 @@ def test_walking_the_legacy_image_reproduces_the_oracle_records(legacy_image):
             need = w0 & L_TERM
             ended += 1 if need else 0
             assert need or nx % L_ROW == 0 and nx // L_ROW < rows
+            if not need:
+                # the state-key table (packed word -> row, used when a live hand crosses a launch boundary): the key of
+                # the state the ORACLE is in now must lead to the row the entry points at
+                skey = 0
+                for p in (0, 1):
+                    m = int(ref[t, g, p]["misc"])
+                    skey |= ((m >> 2) & 7) << (3 * p) | ((m >> 5) & 7) << (6 + 2 * p) | (1 if ref[t, g, p]["reward"] != 0 else 0) << (10 + p)
+                assert int(keys[skey]) == nx // L_ROW, "game %d iteration %d" % (g, t)
+                live_keys.add(skey)
             six = nx
-    assert ended > n * iters // 8
+    assert ended > n * iters // 8 and len(live_keys) > 20
