@@ -502,10 +502,13 @@ learner_fit_rows_kernel(const FitArgs F) {
             }
         }
         if (peers) {
-            __threadfence_system();  // this rank's slot is complete before any peer sees the flag
+            // this rank's slot must be complete before any peer sees the flag: the CTA barrier orders every thread's
+            // stores before the publishing threads, whose system-scope fence + release store make them visible
+            // (cumulativity) -- one fence per peer instead of one per thread
             __syncthreads();
             const int t = threadIdx.x;
             if (t < F.world && t != F.rank) {
+                __threadfence_system();
                 st_release_sys(reinterpret_cast<uint32_t *>(F.peer[t] + kPeerFlagOff) + F.rank * 4 + net, epoch);
                 const uint32_t *flag = reinterpret_cast<const uint32_t *>(F.peer[F.rank] + kPeerFlagOff) + t * 4 + net;
                 const long long t0 = clock64();
