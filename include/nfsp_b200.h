@@ -160,6 +160,8 @@ typedef struct {
     int32_t variant;      /* first layer on: 1 = CUDA cores (sum of two precombined weight rows, bank-conflict-free
                              shared-memory gathers), 2 = tensor cores (tcgen05.mma, TMEM accumulator),
                              0 = library default */
+    int32_t reserve_sms;  /* CUDA-core variant: SMs left free for kernels of other streams (the learner's fit running
+                             beside the rollout); the persistent grid is sm_count - reserve_sms CTAs.  0 = use them all */
 } nfsp_rollout_io;
 #define NFSP_ROLLOUT_DEFAULT_VARIANT 1
 

@@ -407,9 +407,10 @@ class SelfPlay:
 
     VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2}
 
-    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None):
+    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0):
         """variant: "cuda" (first layer as row sums on CUDA cores), "tcgen05" (first layer as tensor-core
-        tiles with the accumulator in TMEM) or None = self.variant."""
+        tiles with the accumulator in TMEM) or None = self.variant.  reserve_sms: SMs the persistent rollout grid
+        leaves to kernels of other streams (the learner beside it, PipelinedTrainer)."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
         want_debug = debug or forced_vec is not None
@@ -423,6 +424,7 @@ class SelfPlay:
             if not want_debug:
                 self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
+        io.reserve_sms = int(reserve_sms)
         dbg = None
         if want_debug:
             tr = torch.empty((3, n_steps, self.n), dtype=torch.int32, device=self.device)

@@ -332,7 +332,8 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         return NFSP_OK;
     }
     NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    const int grid = grid_for(h->n, kRollThreads, h->sm_count, 1);
+    NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
+    const int grid = grid_for(h->n, kRollThreads, h->sm_count - io->reserve_sms, 1);
     if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     NFSP_LAUNCH_CHECK();

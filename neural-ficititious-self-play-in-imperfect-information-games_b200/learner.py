@@ -64,10 +64,10 @@ class Learner:
         self.exploitability = [0.0, 0.0]
         self.updates = 0
 
-    def _io(self, idx_rl, idx_sl, row0, rows, mask):
+    def _io(self, idx_rl, idx_sl, row0, rows, mask, w_in=None):
         sp = self.sp
         io = _lib.LearnerIO()
-        io.d_weights, io.d_target_weights = sp.weights.data_ptr(), self.target.data_ptr()
+        io.d_weights, io.d_target_weights = (sp.weights if w_in is None else w_in).data_ptr(), self.target.data_ptr()
         for p in range(2):
             io.d_rl[p], io.d_rl_idx[p] = sp.rl[p].data.data_ptr(), idx_rl[p].data_ptr()
             io.d_sl[p], io.d_sl_idx[p] = sp.sl[p].data.data_ptr(), idx_sl[p].data_ptr()
@@ -121,20 +121,21 @@ class Learner:
             self._peers = None
             self._peer_note = "peer exchange unavailable: %r" % (e,)
 
-    def _fit_peers(self, idx_rl, idx_sl, mask):
-        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask)
+    def _fit_peers(self, idx_rl, idx_sl, mask, w_in=None, w_out=None):
+        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask, w_in)
         lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
         self._peers.epoch0 = self._epoch & 0xFFFFFFFF
         check(lib().nfsp_learner_fit_peers(C.byref(io), self.minibatch, self.fit_batch, self.epochs, lr,
-                                           _ptr(self.sp.weights), C.byref(self._peers), _stream(self.device)))
+                                           _ptr(self.sp.weights if w_out is None else w_out), C.byref(self._peers),
+                                           _stream(self.device)))
         self._epoch += self.epochs * ((self.minibatch + self.fit_batch - 1) // self.fit_batch)
 
     # ---- the whole fit() in one launch: one GPU, no collective between the SGD steps ---------------
-    def _fit_fused(self, idx_rl, idx_sl, mask):
-        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask)
+    def _fit_fused(self, idx_rl, idx_sl, mask, w_in=None, w_out=None):
+        io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask, w_in)
         lr = (C.c_float * 4)(self.lr_ar, self.lr_br[0], self.lr_ar, self.lr_br[1])
-        check(lib().nfsp_learner_fit(C.byref(io), self.minibatch, self.fit_batch, self.epochs, lr, _ptr(self.sp.weights),
-                                     _stream(self.device)))
+        check(lib().nfsp_learner_fit(C.byref(io), self.minibatch, self.fit_batch, self.epochs, lr,
+                                     _ptr(self.sp.weights if w_out is None else w_out), _stream(self.device)))
 
     # ---- one SGD step for all four nets -------------------------------------------------------------
     def _step(self, idx_rl, idx_sl, row0, rows, mask):
@@ -166,12 +167,21 @@ class Learner:
         self._all_ready = mask == 15
         return mask
 
-    def update(self, sync=True):
+    def update(self, sync=True, weights_in=None, weights_out=None, pack=True):
         """update_strategy() of both agents.  Returns a dict of statistics; with sync=False nothing is read back
-        from the device (the loss / exploitability-proxy entries are then the previous synchronised values)."""
+        from the device (the loss / exploitability-proxy entries are then the previous synchronised values).
+        weights_in / weights_out (float32 [4, 2179] device tensors): train FROM / INTO these instead of the acting
+        weights of the SelfPlay object, and with pack=False leave the acting nets alone -- what PipelinedTrainer needs
+        to run this update beside the next rollout.  Only the one-launch fit supports it."""
         sp = self.sp
         mask = self._ready_mask()
+        one_launch = self.fused and (_world() == 1 or self._peers is not None)
+        if (weights_in is not None or weights_out is not None) and not one_launch:
+            raise ValueError("weights_in / weights_out need the one-launch fit (fused=True; peers when world > 1)")
+        w_new = sp.weights if weights_out is None else weights_out
         if mask == 0:
+            if weights_out is not None:
+                weights_out.copy_(sp.weights if weights_in is None else weights_in)
             return {"trained": 0}
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:
@@ -181,9 +191,9 @@ class Learner:
         if self.fused and (_world() == 1 or self._peers is not None):
             # one launch for the 8 SGD steps; with peers the per-step all-reduce happens inside it over NVLink
             if _world() == 1:
-                self._fit_fused(idx_rl, idx_sl, mask)
+                self._fit_fused(idx_rl, idx_sl, mask, weights_in, weights_out)
             else:
-                self._fit_peers(idx_rl, idx_sl, mask)
+                self._fit_peers(idx_rl, idx_sl, mask, weights_in, weights_out)
             stats = self.flat[GRAD:].clone()     # statistics of the first step, as below
         else:
             for _ in range(self.epochs):         # Keras fit(epochs=2), batch_size 32 (agent.py:243,261)
@@ -204,16 +214,65 @@ class Learner:
                 it = self.iteration[p]
                 self.temp[p] = (1 + 0.02 * math.sqrt(it)) ** (-1)    # agent.py:247
                 if self.target_update_count[p] % self.target_update_rate == 0:   # agent.py:266-273
-                    self.target[p].copy_(sp.weights[2 * p + 1])
+                    self.target[p].copy_(w_new[2 * p + 1])
                 self.target_update_count[p] += 1
                 self.lr_br[p] = self.lr_br0 / (1 + 0.003 * math.sqrt(it))        # agent.py:251
         if any((mask >> (2 * p + 1)) & 1 for p in range(2)):
             it = max(self.iteration)
             sp.epsilon = sp.epsilon ** 1 / it                                    # agent.py:253 (sic)
-        sp.set_weights(sp.weights)  # rebuild the kernels' weight images
+        if pack:
+            sp.set_weights(sp.weights)  # rebuild the kernels' weight images
         self.updates += 1
         return {"trained": mask, "exploitability": sum(self.exploitability), "loss": s[4:8], "epsilon": sp.epsilon,
                 "lr_br": list(self.lr_br)}
+
+
+class PipelinedTrainer:
+    """Self-play with the learner BESIDE the actor: update j runs on its own stream while rollout j+1 plays.
+
+    The sequential loop (main.train, agent.py:130-156) is rollout -> memories -> update -> rollout with the new nets.
+    Here rollout j+1 starts right after the memories of step j are written, with the nets that update j is still
+    reading (W_j); update j's result W_{j+1} is picked up by rollout j+2.  So the acting nets lag ONE update behind the
+    sequential loop -- NFSP learns off-policy from its memories, the reference's own update cadence is arbitrary
+    (every 128 decisions of a batch-1 game) -- and in exchange the learner's time (and, with several GPUs, its gradient
+    exchange) disappears behind the rollout.  Mechanics: the fit trains from one weight tensor into another
+    (two tensors, alternating), so the acting images can be rebuilt from W_j while update j reads it; the rollout's
+    persistent grid leaves `reserve_sms` SMs free (the fit is four CTAs that need an SM each); events order
+    memories-written -> update -> memories-written-again.  Deterministic: the same weights, memories and games as the
+    sequential loop run with that lag (tests/test_gpu_train.py)."""
+
+    def __init__(self, selfplay, learner, reserve_sms=4):
+        self.sp, self.learner, self.reserve_sms = selfplay, learner, int(reserve_sms)
+        self.w = [selfplay.weights.clone(), selfplay.weights.clone()]  # W_j lives in w[j % 2]
+        self.stream = torch.cuda.Stream(selfplay.device)
+        self.flushed = torch.cuda.Event()
+        self.updated = [torch.cuda.Event(), torch.cuda.Event()]        # update j records updated[j % 2]
+        self.j = 0
+
+    def step(self, n_steps, sync=False):
+        """One iteration; sync=True also reads this update's statistics back (the host then waits for the update)."""
+        sp, j = self.sp, self.j
+        main = torch.cuda.current_stream(sp.device)
+        if j >= 2:
+            main.wait_event(self.updated[j % 2])          # update j-2 wrote W_{j-1}
+        sp.set_weights(self.w[(j - 1) % 2] if j >= 1 else self.w[0])   # acting nets: W_{j-1} (W_0 for the first two steps)
+        sp.rollout(n_steps, insert=False, reserve_sms=self.reserve_sms)
+        if j >= 1:
+            main.wait_event(self.updated[(j - 1) % 2])    # update j-1 has read its records: the memories may change
+        sp.flush()
+        self.flushed.record(main)
+        self.stream.wait_event(self.flushed)
+        with torch.cuda.stream(self.stream):
+            out = self.learner.update(sync=sync, weights_in=self.w[j % 2], weights_out=self.w[(j + 1) % 2], pack=False)
+            self.updated[j % 2].record(self.stream)
+        self.j = j + 1
+        return out
+
+    def finish(self):
+        """Wait for the last update and make its weights the acting nets; returns them."""
+        torch.cuda.current_stream(self.sp.device).wait_stream(self.stream)
+        self.sp.set_weights(self.w[self.j % 2])
+        return self.w[self.j % 2]
 
 
 # ---- single-game drop-in: agent.Agent.update_*_network ----------------------------------------------------

@@ -26,7 +26,7 @@ from . import sharding
 from .batched import SelfPlay
 from .config import load_config
 from .exploitability import exploitability
-from .learner import Learner
+from .learner import Learner, PipelinedTrainer
 
 
 def sampled_actions(stats, player):
@@ -37,15 +37,23 @@ def sampled_actions(stats, player):
 
 
 def train(sp: SelfPlay, learner: Learner, episodes: int, steps_per_call: int = 8, report_every: int = 100,
-          world: int = 1, log=print, true_exploitability: bool = True):
+          world: int = 1, log=print, true_exploitability: bool = True, pipelined: bool = False):
     """main.train (main.py:21-124).  Plays until `episodes` hands have finished over all games and ranks.
-    Returns the list of reported rows (the reference's `plotter`, main.py:75, plus what it prints)."""
+    Returns the list of reported rows (the reference's `plotter`, main.py:75, plus what it prints).
+    pipelined: the learner's update runs beside the next rollout (learner.PipelinedTrainer: acting nets one update
+    behind, the learner's time hidden)."""
     rows, calls, t0 = [], 0, time.time()
+    trainer = PipelinedTrainer(sp, learner) if pipelined else None
     while True:
         calls += 1
         report = calls % report_every == 0 or calls == 1
-        sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
-        st = learner.update(sync=report)      # agent.py:153-154 -> 192-194 -> 209-264; host reads only when reporting
+        if trainer is None:
+            sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
+            st = learner.update(sync=report)      # agent.py:153-154 -> 192-194 -> 209-264; host reads only when reporting
+        else:
+            st = trainer.step(steps_per_call, sync=report)
+            if report:                            # the exact exploitability below is that of the newest nets
+                trainer.finish()
         if not report:
             continue
         tot = sharding.allreduce_stats(sp.stats).tolist()
@@ -78,6 +86,7 @@ def main(argv=None):
     ap.add_argument("--steps-per-call", type=int, default=8)
     ap.add_argument("--report-every", type=int, default=100)
     ap.add_argument("--no-true-exploitability", action="store_true")
+    ap.add_argument("--pipelined", action="store_true", help="run the learner's update beside the next rollout")
     args = ap.parse_args(argv)
     cfg = load_config(args.config)
     rank, world, local = sharding.env_rank_world()
@@ -96,7 +105,7 @@ def main(argv=None):
     episodes = args.episodes if args.episodes is not None else cfg.getint("Common", "Episodes")
     rows = train(sp, learner, episodes, args.steps_per_call, args.report_every, world,
                  log=print if rank == 0 else (lambda *a, **k: None),
-                 true_exploitability=not args.no_true_exploitability)
+                 true_exploitability=not args.no_true_exploitability, pipelined=args.pipelined)
     if world > 1:
         dist.destroy_process_group()
     return rows

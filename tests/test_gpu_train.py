@@ -55,3 +55,40 @@ def test_train_loop_runs_and_reports(nb):
     assert np.isfinite(rows[-1]["exploitability"]["value"]) and rows[-1]["exploitability"]["value"] >= 0
     assert not torch.equal(w0, sp.weights)            # the learner moved the nets
     assert any("Exploitability" in s for s in lines)  # main.py:73's line is printed
+
+
+def test_pipelined_trainer_equals_the_sequential_loop_run_with_one_update_of_lag(nb):
+    """PipelinedTrainer (update j on its own stream beside rollout j+1, the rollout grid four SMs short) against the
+    plain loop made to act with the same nets (rollout j with W_{j-1}): the events must order everything, so weights,
+    game words and memories come out bit-identical.  4096 games = one 32-game block per staging segment, so the order
+    of the staged records does not depend on how the blocks were scheduled."""
+    from nfsp_b200.learner import Learner, PipelinedTrainer
+
+    def make():
+        sp = nb.SelfPlay(4096, seed=21, eta=0.3, epsilon=0.2, rl_capacity=1 << 15, sl_capacity=1 << 15, max_steps_per_call=8)
+        for _ in range(3):
+            sp.rollout(8)
+        return sp
+
+    K = 7
+    a, b = make(), make()
+    La, Lb = Learner(a, cfg=nb.load_config(None)), Learner(b, cfg=nb.load_config(None))
+    chain = a.weights.clone()                    # W_j, trained in place by the plain learner
+    hist = [chain.clone()]                       # hist[j] = W_j
+    for j in range(K):
+        a.set_weights(hist[j - 1 if j >= 1 else 0].clone())
+        a.rollout(8)
+        a.set_weights(chain)
+        assert La.update(sync=False)["trained"] == 0xF
+        hist.append(chain.clone())
+    T = PipelinedTrainer(b, Lb)
+    for j in range(K):
+        assert T.step(8)["trained"] == 0xF
+    final = T.finish()
+    torch.cuda.synchronize()
+    assert torch.equal(final, hist[K]) and not torch.equal(hist[K], hist[0])
+    assert torch.equal(a.env.state_words(), b.env.state_words())
+    for p in range(2):
+        assert int(a.rl[p].total.item()) == int(b.rl[p].total.item()) and torch.equal(a.rl[p].data, b.rl[p].data)
+        assert int(a.sl[p].total.item()) == int(b.sl[p].total.item()) and torch.equal(a.sl[p].data, b.sl[p].data)
+    assert La.iteration == Lb.iteration and abs(a.epsilon - b.epsilon) < 1e-15
