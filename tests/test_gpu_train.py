@@ -39,7 +39,8 @@ def test_policy_tables_come_from_the_cuda_forward(nb):
     assert a["value"] < 5.0   # nobody can win more than the largest pot per hand
 
 
-def test_train_loop_runs_and_reports(nb):
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_train_loop_runs_and_reports(nb, pipelined):
     from nfsp_b200 import main as drv
     from nfsp_b200.learner import Learner
 
@@ -47,7 +48,7 @@ def test_train_loop_runs_and_reports(nb):
     w0 = sp.weights.clone()
     learner = Learner(sp, cfg=nb.load_config(None))
     lines = []
-    rows = drv.train(sp, learner, episodes=60_000, steps_per_call=8, report_every=10, log=lines.append)
+    rows = drv.train(sp, learner, episodes=60_000, steps_per_call=8, report_every=10, log=lines.append, pipelined=pipelined)
     assert rows and rows[-1]["hands"] >= 60_000
     assert rows[-1]["transitions"] == rows[-1]["calls"] * 8 * 4096
     for p in range(2):
