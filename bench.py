@@ -338,19 +338,21 @@ def run_gpu(args):
     # the same iteration with the update beside the next rollout (learner.PipelinedTrainer: acting nets one update behind)
     from nfsp_b200.learner import PipelinedTrainer
 
-    trainer = PipelinedTrainer(sp, learner)
-    for _ in range(3):
-        trainer.step(T_PER_CALL)
-    barrier()
-    a, b = ev(), ev()
-    a.record()
-    for _ in range(10):
-        trainer.step(T_PER_CALL)
-    b.record()
-    b.synchronize()
-    pipe_ms = sharding.max_over_ranks(a.elapsed_time(b) / 10, dev)
-    trainer.finish()
-    torch.cuda.synchronize()
+    pipe_ms = None
+    if learner.one_launch:  # needs the one-launch fit (with several GPUs: peer memory); every rank takes the same branch
+        trainer = PipelinedTrainer(sp, learner)
+        for _ in range(3):
+            trainer.step(T_PER_CALL)
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(10):
+            trainer.step(T_PER_CALL)
+        b.record()
+        b.synchronize()
+        pipe_ms = sharding.max_over_ranks(a.elapsed_time(b) / 10, dev)
+        trainer.finish()
+        torch.cuda.synchronize()
 
     # env-only K1 (BASELINE configs[1]) beside it, same games count, trace planes written
     env = nfsp_b200.BatchedNfspEnv(n, seed=SEED, game0=game0, device=dev)
@@ -488,7 +490,7 @@ def run_gpu(args):
                       "training_step": {"what": "rollout(8) + memory inserts + Learner.update(sync=False) per iteration (BASELINE configs[4])",
                                         "ms": train_ms, "transitions_per_sec": GAMES_PER_GPU * world * T_PER_CALL / (train_ms * 1e-3),
                                         "pipelined_ms": pipe_ms,
-                                        "pipelined_transitions_per_sec": GAMES_PER_GPU * world * T_PER_CALL / (pipe_ms * 1e-3),
+                                        "pipelined_transitions_per_sec": (GAMES_PER_GPU * world * T_PER_CALL / (pipe_ms * 1e-3)) if pipe_ms else None,
                                         "pipelined": "update j beside rollout j+1 (acting nets one update behind), 4 SMs left to the learner"},
                       "learner": {"update_ms": learner_ms, "sgd_steps_per_update": 8, "allreduce_floats": 4 * 2179 + 8,
                                   "exploitability_proxy": lstats.get("exploitability"), "trained_mask": lstats.get("trained")},

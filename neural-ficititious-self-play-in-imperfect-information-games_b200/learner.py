@@ -64,6 +64,12 @@ class Learner:
         self.exploitability = [0.0, 0.0]
         self.updates = 0
 
+    @property
+    def one_launch(self) -> bool:
+        """The whole fit runs as one kernel (one GPU, or several with the peer exchange): what weights_in / weights_out
+        and PipelinedTrainer need.  The same on every rank (the peer set-up is collective)."""
+        return self.fused and (_world() == 1 or self._peers is not None)
+
     def _io(self, idx_rl, idx_sl, row0, rows, mask, w_in=None):
         sp = self.sp
         io = _lib.LearnerIO()
@@ -175,8 +181,7 @@ class Learner:
         to run this update beside the next rollout.  Only the one-launch fit supports it."""
         sp = self.sp
         mask = self._ready_mask()
-        one_launch = self.fused and (_world() == 1 or self._peers is not None)
-        if (weights_in is not None or weights_out is not None) and not one_launch:
+        if (weights_in is not None or weights_out is not None) and not self.one_launch:
             raise ValueError("weights_in / weights_out need the one-launch fit (fused=True; peers when world > 1)")
         w_new = sp.weights if weights_out is None else weights_out
         if mask == 0:
@@ -242,6 +247,9 @@ class PipelinedTrainer:
     sequential loop run with that lag (tests/test_gpu_train.py)."""
 
     def __init__(self, selfplay, learner, reserve_sms=4):
+        if not learner.one_launch:
+            raise RuntimeError("PipelinedTrainer needs the one-launch fit: fused=True, minibatch <= 256, fit batch <= 64 and, "
+                               "with several GPUs, peer memory (%s)" % getattr(learner, "_peer_note", "see Learner._setup_peers"))
         self.sp, self.learner, self.reserve_sms = selfplay, learner, int(reserve_sms)
         self.w = [selfplay.weights.clone(), selfplay.weights.clone()]  # W_j lives in w[j % 2]
         self.stream = torch.cuda.Stream(selfplay.device)
