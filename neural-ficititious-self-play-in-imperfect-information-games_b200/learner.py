@@ -126,6 +126,9 @@ class Learner:
         except Exception as e:  # noqa: BLE001  (no peer access: NCCL per step, same results up to summation order)
             self._peers = None
             self._peer_note = "peer exchange unavailable: %r" % (e,)
+            import warnings
+
+            warnings.warn("nfsp_b200 learner: %s; using one NCCL all-reduce per SGD step" % self._peer_note, RuntimeWarning)
 
     def _fit_peers(self, idx_rl, idx_sl, mask, w_in=None, w_out=None):
         io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask, w_in)
