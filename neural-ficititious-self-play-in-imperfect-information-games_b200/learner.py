@@ -58,6 +58,12 @@ class Learner:
         self._peers = None
         if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
             self._setup_peers()
+            # every rank must take the same path (a rank in the peer exchange and one in an NCCL all-reduce would wait
+            # for each other forever): the exchange is used only if the set-up worked everywhere
+            ok = torch.tensor([1 if self._peers is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self._peers = None
         self.iteration = [0, 0]
         self.target_update_count = [0, 0]
         self.temp = [1.0, 1.0]
