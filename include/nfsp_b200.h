@@ -61,6 +61,10 @@ uint64_t nfsp_env_step_counter(nfsp_env_t h);
 int nfsp_env_set_step_counter(nfsp_env_t h, uint64_t step);
 /* device pointer to the n_games packed words */
 void *nfsp_env_state_ptr(nfsp_env_t h);
+/* Protocol-error word of the rollout kernels (synchronises the device): 0 = none.  The warp-specialised rollout bounds
+ * every wait it makes (queues, mbarriers); a wait that runs out sets a bit here and the kernel ends instead of hanging
+ * the GPU -- the launch's results are then invalid.  Nothing comparable exists in the reference (single thread). */
+int nfsp_env_kernel_error(nfsp_env_t h, uint32_t *out);
 /* copy the n_games packed 64-bit words out of / into the handle (checkpoint / resume, sharding tests) */
 int nfsp_env_save_state(nfsp_env_t h, uint64_t *d_out, void *stream);
 int nfsp_env_load_state(nfsp_env_t h, const uint64_t *d_in, void *stream);
@@ -158,9 +162,11 @@ typedef struct {
     float *d_vec;         /* float[n_steps][n][3] score vectors actually used, or NULL          */
     const float *d_forced_vec; /* float[n_steps][n][3] or NULL: use these instead of the nets   */
     int32_t variant;      /* first layer on: 1 = CUDA cores (sum of two precombined weight rows, bank-conflict-free
-                             shared-memory gathers), 2 = tensor cores (tcgen05.mma, TMEM accumulator),
-                             0 = library default */
-    int32_t reserve_sms;  /* CUDA-core variant: SMs left free for kernels of other streams (the learner's fit running
+                             shared-memory gathers), 2 = tensor cores, one mixed-net tile per 128-thread group,
+                             3 = tensor cores, warp-specialised: env warps -> per-net tile queues -> tcgen05.mma on
+                             net-homogeneous M128 N64 tiles -> epilogue warpgroups (TMEM -> relu -> 64x3 with W2 from
+                             the constant bank), 0 = library default */
+    int32_t reserve_sms;  /* variants 1 and 3: SMs left free for kernels of other streams (the learner's fit running
                              beside the rollout); the persistent grid is sm_count - reserve_sms CTAs.  0 = use them all */
 } nfsp_rollout_io;
 #define NFSP_ROLLOUT_DEFAULT_VARIANT 1
@@ -171,6 +177,12 @@ typedef struct {
  * with auto re-deal.  Records are appended to the segmented staging arrays with warp-aggregated
  * atomics; move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
 int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io, void *stream);
+/* Tuning of variant 3: SM cycles a partly filled tile of an average-policy / a best-response net may wait for more rows
+ * before its MMAs are issued anyway (defaults 1500 / 700). */
+int nfsp_rollout_tune(nfsp_env_t h, int patience_avg, int patience_br);
+/* Cycle counters of variant 3's three roles (only counted by a library built with -DNFSP_TQ_PROF, else zeros);
+ * layout in csrc/rollout_tq.cu.  Synchronises the device. */
+int nfsp_rollout_profile(nfsp_env_t h, uint64_t *out24);
 
 /* ------------------------------------------------------------------ memories -------------- */
 /* A staged batch is n_segments segments of seg_cap 16-byte slots with one device count each

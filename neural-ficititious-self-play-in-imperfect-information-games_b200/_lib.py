@@ -20,12 +20,12 @@ EXPORT_FIELDS, LEGACY_EXPORT_FIELDS, STATS_FIELDS = 24, 14, 16
 SYMBOLS = [
     "nfsp_version", "nfsp_last_error", "nfsp_device_info",
     "nfsp_env_create", "nfsp_env_destroy", "nfsp_env_num_games", "nfsp_env_rules", "nfsp_env_step_counter",
-    "nfsp_env_set_step_counter", "nfsp_env_state_ptr", "nfsp_env_save_state", "nfsp_env_load_state",
+    "nfsp_env_set_step_counter", "nfsp_env_state_ptr", "nfsp_env_kernel_error", "nfsp_env_save_state", "nfsp_env_load_state",
     "nfsp_env_reset", "nfsp_env_set_hands", "nfsp_env_step", "nfsp_fsm_image", "nfsp_legacy_fsm_image", "nfsp_env_observe", "nfsp_env_export",
     "nfsp_legacy_reset", "nfsp_legacy_set_hands", "nfsp_legacy_step", "nfsp_legacy_get_new_state",
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
-    "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout",
+    "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_tune", "nfsp_rollout_profile",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
 ]
@@ -94,6 +94,9 @@ def lib():
     L.nfsp_env_set_step_counter.argtypes = [vp, C.c_uint64]
     L.nfsp_env_state_ptr.argtypes = [vp]
     L.nfsp_env_state_ptr.restype = vp
+    L.nfsp_env_kernel_error.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.nfsp_rollout_tune.argtypes = [vp, C.c_int, C.c_int]
+    L.nfsp_rollout_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.nfsp_env_save_state.argtypes = [vp, vp, vp]
     L.nfsp_env_load_state.argtypes = [vp, vp, vp]
     L.nfsp_env_reset.argtypes = [vp, i8p, C.c_double, vp]

@@ -405,7 +405,7 @@ class SelfPlay:
         check(fn(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
         return out
 
-    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2}
+    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3}
 
     def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0):
         """variant: "cuda" (first layer as row sums on CUDA cores), "tcgen05" (first layer as tensor-core

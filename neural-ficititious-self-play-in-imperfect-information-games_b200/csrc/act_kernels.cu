@@ -247,6 +247,7 @@ rollout_kernel(const RolloutArgs A) {
             fast_finish<kDebug>(g, s_lut, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
             if ((t & 15) == 15) c.spill();
         }
+        c.spill();  // the 5-bit counters must not run on into the warp's next block of games
         if (live) A.state[i] = g.pack();
         c.wide.trans += live ? A.n_steps : 0;
     }
@@ -273,7 +274,9 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     }
     pack_images_kernel<<<(kPackFloats + kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
     NFSP_LAUNCH_CHECK();
-    const int rc = nfsp_pack_tc_image(h, d_weights, (cudaStream_t)stream);
+    int rc = nfsp_pack_tc_image(h, d_weights, (cudaStream_t)stream);
+    if (rc != NFSP_OK) return rc;
+    rc = nfsp_tq_set_weights(h, d_weights, (cudaStream_t)stream);
     if (rc != NFSP_OK) return rc;
     h->has_weights = true;
     return NFSP_OK;
@@ -323,8 +326,16 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.work = h->d_work;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
-    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 2, "variant must be 0 (default), 1 (CUDA cores) or 2 (tcgen05)");
+    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 3,
+                   "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group) or 3 (tcgen05, warp-specialised)");
     const int variant = io->variant == 0 ? NFSP_ROLLOUT_DEFAULT_VARIANT : io->variant;
+    NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
+    if (variant == 3) {
+        const int rc = nfsp_rollout_tq_launch(h, A, debug, io->reserve_sms, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        h->step += (uint64_t)n_steps;
+        return NFSP_OK;
+    }
     if (variant == 2) {
         const int rc = nfsp_rollout_tc_launch(h, A, debug, (cudaStream_t)stream);
         if (rc != NFSP_OK) return rc;
@@ -332,7 +343,6 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         return NFSP_OK;
     }
     NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
     const int grid = grid_for(h->n, kRollThreads, h->sm_count - io->reserve_sms, 1);
     if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);

@@ -404,6 +404,7 @@ rollout_tc_kernel(const RolloutArgs A) {
             if ((s & 15) == 15) c.spill();
             TC_T1(tm_fin);
         }
+        c.spill();  // the 5-bit counters must not run on into the group's next tile of games
         if (live) A.state[i] = g.pack();
         c.wide.trans += live ? A.n_steps : 0;
     }

@@ -99,6 +99,7 @@ extern "C" int nfsp_env_destroy(nfsp_env_t h) {
     if (h->d_wpack) cudaFree(h->d_wpack);
     if (h->d_work) cudaFree(h->d_work);
     if (h->d_wtc_wide) cudaFree(h->d_wtc_wide);
+    nfsp_tq_release(h);
     delete h;
     return NFSP_OK;
 }
@@ -112,6 +113,22 @@ extern "C" int nfsp_env_set_step_counter(nfsp_env_t h, uint64_t step) {
     return NFSP_OK;
 }
 extern "C" void *nfsp_env_state_ptr(nfsp_env_t h) { return h ? h->d_state : nullptr; }
+
+extern "C" int nfsp_env_kernel_error(nfsp_env_t h, uint32_t *out) {
+    NFSP_CHECK_ARG(h != nullptr && out != nullptr, "null argument");
+    *out = 0u;
+    if (!h->d_err) return NFSP_OK;
+    DeviceGuard guard(h->device);
+    NFSP_CUDA(cudaMemcpy(out, h->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_rollout_tune(nfsp_env_t h, int patience_avg, int patience_br) {
+    NFSP_CHECK_ARG(h != nullptr && patience_avg >= 0 && patience_br >= 0, "bad arguments");
+    h->tq_patience[0] = (uint32_t)patience_avg;
+    h->tq_patience[1] = (uint32_t)patience_br;
+    return NFSP_OK;
+}
 
 extern "C" int nfsp_env_save_state(nfsp_env_t h, uint64_t *d_out, void *stream) {
     NFSP_CHECK_ARG(h != nullptr && d_out != nullptr, "null argument");

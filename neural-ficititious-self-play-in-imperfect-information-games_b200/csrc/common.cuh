@@ -20,6 +20,11 @@ struct nfsp_env_s {
     uint32_t *d_work;    // dynamic work counter of the fused rollout
     void *d_wtc_wide;    // tensor-core operand image of layer 1, the four nets side by side along N (act_tc_kernels.cu)
     bool has_weights;
+    // warp-specialised tcgen05 rollout (rollout_tq.cu)
+    int w2_slot = -1;         // this handle's slot of the constant-bank image of the second layers, -1 = none yet
+    void *d_w2img = nullptr;  // device copy of that image
+    uint32_t *d_err = nullptr;  // protocol-error word of the rollout kernel (0 = none), see nfsp_env_kernel_error
+    uint32_t tq_patience[2] = {1500u, 700u};  // cycles a partly filled tile of an average / best-response net may wait
 };
 
 // builds and uploads the table image of nfsp_step_fsm_kernel (env_kernels.cu); the handle's device is current
@@ -27,6 +32,9 @@ int nfsp_fsm_upload(nfsp_env_t h);
 
 // builds the tensor-core operand image of the acting nets (act_tc_kernels.cu)
 int nfsp_pack_tc_image(nfsp_env_t h, const float *d_weights, cudaStream_t st);
+// second-layer image of the warp-specialised rollout: constant-bank slot of the handle (rollout_tq.cu)
+int nfsp_tq_set_weights(nfsp_env_t h, const float *d_weights, cudaStream_t st);
+void nfsp_tq_release(nfsp_env_t h);
 
 namespace nfsp {
 

@@ -10,6 +10,8 @@
 namespace nfsp { struct RolloutArgs; }
 // launches the tcgen05 variant of the fused rollout (act_tc_kernels.cu)
 int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug, cudaStream_t st);
+// launches the warp-specialised tcgen05 rollout (rollout_tq.cu)
+int nfsp_rollout_tq_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug, int reserve_sms, cudaStream_t st);
 
 namespace nfsp {
 
