@@ -108,7 +108,6 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a protocol error must end the kernel, never hang the GPU
 __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t *err, uint32_t code) {
-#pragma unroll 1
     for (uint32_t it = 0; it < kSpinLimit; ++it)
         if (mbar_try(bar, parity)) return true;
     atomicOr(err, code);
@@ -692,7 +691,6 @@ rollout_tq_kernel(const TqArgs T) {
             const uint32_t full = smem_u32(&ctl->full[slot]);
             bool quit = false;
             const long long tq_e1 = TQ_CLK();
-#pragma unroll 1
             for (uint32_t it = 0;; ++it) {
                 if (mbar_try(full, parity)) break;
                 if (ld_vol(&ctl->quit)) { quit = true; break; }
@@ -721,7 +719,7 @@ rollout_tq_kernel(const TqArgs T) {
                 continue;
             }
             const uint32_t taddr = tmem_base + slot * 64u + (wq << 21);
-#ifdef NFSP_TQ_W2_SMEM
+#ifndef NFSP_TQ_W2_CONST
             const float4 out = rows_forward(sW2 + net * 3u, sW2[16 * 12 + net], (net & 1u) != 0u, taddr, empty);
 #else
             const float4 out = rows_forward_const(T.w2_slot, net, taddr, empty);
