@@ -1,0 +1,289 @@
+"""-m gpu: parity against the CPU oracle AT THE SIZES BASELINE.json's configs name (round-1 verdict: the parity
+tests stopped short of the benchmarked shapes and compared GPU with GPU there).
+
+  config 2  2^20 games, uniform-random actions, both rule sets: trace planes and game words bit for bit vs the oracle
+  config 3  65 536 games, eta 0.1, epsilon 0.06, 8 decisions x 4 launches, every rollout variant: traces, records,
+            counters bit for bit (teacher-forced on the kernel's own score vectors), score vectors within 1e-5
+  config 4  ring of 200 000 + reservoir of 2 000 000 records fed 65 536 + 6 554 records per step until the ring has
+            wrapped many times and the reservoir replaces, then 256-row minibatches: contents, totals and sampled
+            rows bit for bit vs the sequential oracle
+  bench     2^20 games, eta 0.1, epsilon 0.06, 8 decisions (the shape bench.py times): traces, record MULTISETS,
+            counters and game words vs the oracle, debug and production launch -- the staged ORDER at this size
+            depends on warp scheduling (several blocks of games share a staging segment), so records are compared
+            order-free
+
+The oracle runs its batches with OpenMP, so each case is seconds of host time.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402
+
+TOL = 1e-5  # BASELINE.json north_star: "within 1e-5 absolute (fp32)"
+VARIANTS = ["cuda", "tcgen05", "tcgen05_ws"]
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nfsp_b200
+
+    assert torch.cuda.is_available()
+    return nfsp_b200
+
+
+def canon(recs):
+    a = np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def raw16(recs):
+    return np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4)
+
+
+def glorot(nb, seed=1234):
+    return nb.glorot_nets(seed, "cuda").cpu().numpy()
+
+
+def oracle_nets(nb, w):
+    return orc.Nets([nb.split_net(w[k]) for k in range(4)])
+
+
+# ------------------------------------------------------------------------------------------------ config 2
+def test_config2_nfsp_env_full_size_vs_oracle(nb):
+    """newenv.py:192-349 + main.py:28-67 on 2^20 games x 16 transitions (Philox deals and actions, auto re-deal)."""
+    n, steps, seed, eta = 1 << 20, 16, 1234, 0.1
+    env = nb.BatchedNfspEnv(n, seed=seed, eta=eta)
+    env.reset()
+    tr = env.step(n_steps=steps, trace=True)["raw"].cpu().numpy().view(np.uint32)
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(eta))
+    ref = b.rollout_env(1, steps, orc.u32_frac(eta))
+    assert np.array_equal(tr[0], ref["obs"])
+    assert np.array_equal(tr[1].view(np.float32), ref["reward"])
+    assert np.array_equal(tr[2], ref["misc"])
+
+
+def test_config2_legacy_env_full_size_vs_oracle(nb):
+    """leduc/env.py under the README loop (README.md:15-38) on 2^20 games x 16 iterations = 32 transitions each."""
+    n, iters, seed = 1 << 20, 16, 1234
+    env = nb.BatchedLegacyEnv(n, seed=seed)
+    env.reset()
+    rec = env.rollout(iters, trace=True)["raw"].cpu().numpy()
+    b = orc.LegacyBatch(n, seed)
+    b.reset(0)
+    ref = b.rollout(1, iters)
+    w = rec[0].view(np.uint32)
+    sb = lambda x: ((x & 0xFF).astype(np.int16) ^ 0x80) - 0x80  # noqa: E731
+    assert np.array_equal(sb(w), ref["card"]) and np.array_equal(sb(w >> 8), ref["pub"])
+    assert np.array_equal(sb(w >> 16), ref["pot"]) and np.array_equal(sb(w >> 24), ref["terminal"])
+    assert np.array_equal(rec[1], ref["reward"])
+    assert np.array_equal(rec[2].view(np.uint32), ref["misc"])
+
+
+# ------------------------------------------------------------------------------------------------ config 3
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_config3_rollout_64k_games_vs_oracle(nb, variant):
+    """BASELINE configs[2] as stated: 65 536 games, eta 0.1, epsilon 0.06, Glorot nets from seed 1234; 4 launches of
+    8 decisions.  Everything Agent.play / main.train produce, launch after launch."""
+    n, steps, calls, seed, eta, eps = 65536, 8, 4, 1234, 0.1, 0.06
+    w = glorot(nb, seed)
+    sp = nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=eps, rl_capacity=200000,
+                     sl_capacity=2000000, max_steps_per_call=steps, variant=variant)
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(eta))
+    nets = oracle_nets(nb, w)
+    tot = dict(actions=np.zeros((2, 3), np.int64), played=np.zeros(2, np.int64), reward_half=np.zeros(2, np.int64), hands=0)
+    for c in range(calls):
+        out = sp.rollout(steps, insert=False, debug=True)
+        rl, sl = sp.staged()
+        sp.counts.zero_()
+        vec = out["vec"].cpu().numpy()
+        ref = b.rollout_act(1 + c * steps, steps, nets, orc.u32_frac(eta), orc.u32_frac(eps), forced_vec=vec)
+        tr = out["raw"].cpu().numpy().view(np.uint32)
+        assert np.array_equal(tr[0], ref["trace"]["obs"]), c
+        assert np.array_equal(tr[1].view(np.float32), ref["trace"]["reward"]), c
+        assert np.array_equal(tr[2], ref["trace"]["misc"]), c
+        assert np.abs(vec - ref["vec"]).max() <= TOL, c
+        for p in range(2):
+            assert np.array_equal(canon(rl[p]), canon(ref["rl"][p])), (c, p)
+            assert np.array_equal(canon(sl[p]), canon(ref["sl"][p])), (c, p)
+        for k in ("actions", "played", "reward_half"):
+            tot[k] += ref[k]
+        tot["hands"] += ref["hands"]
+    st = sp.read_stats()
+    to_s = lambda v: v - (1 << 64) if v >= 1 << 63 else v  # noqa: E731
+    assert [st["a0_fold"], st["a0_call"], st["a0_raise"]] == list(tot["actions"][0])
+    assert [st["a1_fold"], st["a1_call"], st["a1_raise"]] == list(tot["actions"][1])
+    assert [st["played0"], st["played1"]] == list(tot["played"])
+    assert [to_s(st["reward0_half"]), to_s(st["reward1_half"])] == list(tot["reward_half"])
+    assert st["hands"] == tot["hands"] and st["transitions"] == n * steps * calls and st["dropped"] == 0
+
+
+# ------------------------------------------------------------------------------------------------ bench shape
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_bench_shape_rollout_1m_games_vs_oracle(nb, variant):
+    """The shape bench.py times -- 2^20 games, 8 decisions, eta 0.1, epsilon 0.06, Glorot nets of seed 1234 -- against the
+    oracle playing the same Philox streams.
+
+    (1) debug launch, teacher-forced on the kernel's own score vectors: trace planes, record multisets and counters
+        bit for bit, score vectors within 1e-5 of the oracle's networks;
+    (2) the PRODUCTION launch (no debug outputs) from the same start: its game words, counters and records must equal
+        those of the debug launch exactly -- the two templates only differ in what they write out.
+    The staged ORDER at this size depends on warp scheduling (several blocks of 32 games share a staging segment), so
+    records are compared as multisets."""
+    n, steps, seed, eta, eps = 1 << 20, 8, 1234, 0.1, 0.06
+    w = glorot(nb, seed)
+    mk = lambda: nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=eps, rl_capacity=1 << 25,  # noqa: E731
+                             sl_capacity=1 << 23, max_steps_per_call=steps, variant=variant)
+    sp = mk()
+    out = sp.rollout(steps, insert=False, debug=True)
+    rl, sl = sp.staged()
+    vec = out["vec"].cpu().numpy()
+    tr = out["raw"].cpu().numpy().view(np.uint32)
+    del out
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(eta))
+    ref = b.rollout_act(1, steps, oracle_nets(nb, w), orc.u32_frac(eta), orc.u32_frac(eps), forced_vec=vec)
+    assert np.array_equal(tr[0], ref["trace"]["obs"])
+    assert np.array_equal(tr[1].view(np.float32), ref["trace"]["reward"])
+    assert np.array_equal(tr[2], ref["trace"]["misc"])
+    assert np.abs(vec - ref["vec"]).max() <= TOL
+    st = sp.read_stats()
+    assert st["transitions"] == n * steps and st["dropped"] == 0 and st["hands"] == ref["hands"]
+    assert [st["a0_fold"], st["a0_call"], st["a0_raise"]] == list(ref["actions"][0])
+    assert [st["a1_fold"], st["a1_call"], st["a1_raise"]] == list(ref["actions"][1])
+    canon_dbg = []
+    for p in range(2):
+        got_rl, got_sl = canon(rl[p]), canon(sl[p])
+        assert np.array_equal(got_rl, canon(ref["rl"][p])) and np.array_equal(got_sl, canon(ref["sl"][p]))
+        canon_dbg.append((got_rl, got_sl))
+    words = sp.env.state_words().cpu().numpy()
+    del ref, tr, vec, rl, sl
+    prod = mk()
+    prod.rollout(steps, insert=False)
+    assert np.array_equal(prod.env.state_words().cpu().numpy(), words) and prod.read_stats() == st
+    rl, sl = prod.staged()
+    for p in range(2):
+        assert np.array_equal(canon(rl[p]), canon_dbg[p][0]) and np.array_equal(canon(sl[p]), canon_dbg[p][1])
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+def test_config4_memories_200k_ring_2m_reservoir_vs_oracle(nb):
+    """BASELINE configs[3]: RL ring of 200 000 and SL reservoir of 2 000 000 records; per step 65 536 RL and 6 554 SL
+    records (eta * N); 330 steps put 21.6 M records through the ring (108 wraps) and 2.16 M through the reservoir
+    (fill, then Algorithm R replacement), followed by 256-row minibatches.  Contents, totals, sampled slots and the
+    dense rows vs the sequential oracle (replay_buffer.py:30-59, ReservoirBuffer.py:18-43)."""
+    cap_rl, cap_sl, n_rl, n_sl, steps, batch = 200_000, 2_000_000, 65_536, 6_554, 330, 256
+    dev = torch.device("cuda")
+    ring = nb.DeviceRing(cap_rl, seed=11, device=dev)
+    res = nb.DeviceReservoir(cap_sl, seed=12, device=dev, mode="R")
+    rng = np.random.RandomState(5)
+    all_rl = np.zeros(steps * n_rl, orc.RL_DT)
+    all_sl = np.zeros(steps * n_sl, orc.SL_DT)
+    all_rl.view(np.uint32).reshape(-1, 4)[:] = rng.randint(0, 1 << 30, size=(steps * n_rl, 4), dtype=np.uint32)
+    all_sl.view(np.uint32).reshape(-1, 4)[:] = rng.randint(0, 1 << 30, size=(steps * n_sl, 4), dtype=np.uint32)
+    d_rl = torch.from_numpy(all_rl.view(np.int32).reshape(-1, 4)).to(dev)
+    d_sl = torch.from_numpy(all_sl.view(np.int32).reshape(-1, 4)).to(dev)
+    for k in range(steps):
+        cnt = torch.tensor([n_rl], dtype=torch.int32, device=dev)
+        ring.insert(d_rl[k * n_rl:(k + 1) * n_rl], cnt)
+        cnt = torch.tensor([n_sl], dtype=torch.int32, device=dev)
+        res.insert(d_sl[k * n_sl:(k + 1) * n_sl], cnt)
+    data, count, total = orc.ring_insert_all(all_rl, cap_rl)
+    got = ring.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)
+    assert int(ring.total.item()) == total == steps * n_rl and ring.size() == count == cap_rl
+    assert np.array_equal(raw16(got), raw16(data))
+    data_s, count_s, total_s = orc.reservoir_insert_all(all_sl, cap_sl, res.seed)
+    got = res.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+    assert int(res.total.item()) == total_s == steps * n_sl > cap_sl and res.size() == count_s == cap_sl
+    assert np.array_equal(raw16(got), raw16(data_s))
+    assert not np.array_equal(raw16(got), raw16(all_sl[:cap_sl]))  # replacement did happen
+    for call in range(3):
+        s, a, r, s2, t, idx, n_got = ring.sample(batch)
+        want = orc.sample_indices(ring.seed, call, cap_rl, batch)  # deque positions, oldest first
+        slots = (total % cap_rl + want) % cap_rl
+        assert int(n_got.item()) == batch and np.array_equal(idx.cpu().numpy(), slots)
+        rec = data[slots]
+        assert np.array_equal(s.cpu().numpy(), ((rec["s"][:, None] >> np.arange(30)) & 1).astype(np.float32))
+        assert np.array_equal(s2.cpu().numpy(), ((rec["s2"][:, None] >> np.arange(30)) & 1).astype(np.float32))
+        assert np.array_equal(r.cpu().numpy().view(np.uint32), rec["r"].view(np.uint32))
+        s_, a_, idx_, n_ = res.sample(batch)
+        want = orc.sample_indices(res.seed, call, cap_sl, batch)
+        assert int(n_.item()) == batch and np.array_equal(idx_.cpu().numpy(), want)
+        rec = data_s[want]
+        assert np.array_equal(s_.cpu().numpy(), ((rec["s"][:, None] >> np.arange(30)) & 1).astype(np.float32))
+        assert np.array_equal(a_.cpu().numpy().view(np.uint32), rec["a"].view(np.uint32))
+
+
+def test_config4_memories_fed_by_the_rollout_vs_oracle(nb):
+    """The same capacities fed by the fused rollout itself: 65 536 games, eta 0.1, one decision per step (about 65 k RL
+    and 6.5 k SL records per step, the figures of configs[3]), 40 steps: the ring wraps 6 times.  Both players'
+    memories vs the sequential oracle fed with the staged records in ticket order."""
+    n, seed, steps = 65536, 4321, 40
+    sp = nb.SelfPlay(n, seed=seed, eta=0.1, epsilon=0.06, rl_capacity=200_000, sl_capacity=2_000_000, max_steps_per_call=1)
+    rings = [[], []]
+    ress = [[], []]
+    for _ in range(steps):
+        sp.rollout(1, insert=False)
+        rl, sl = sp.staged()
+        for p in range(2):
+            rings[p].append(rl[p].astype(orc.RL_DT))
+            ress[p].append(sl[p].astype(orc.SL_DT))
+        sp.flush()
+    for p in range(2):
+        recs = np.concatenate(rings[p])
+        data, count, total = orc.ring_insert_all(recs, 200_000)
+        got = sp.rl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)
+        assert int(sp.rl[p].total.item()) == total > 5 * 200_000
+        assert np.array_equal(raw16(got), raw16(data))
+        recs = np.concatenate(ress[p])
+        data, count, total = orc.reservoir_insert_all(recs, 2_000_000, sp.sl[p].seed)
+        got = sp.sl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+        assert int(sp.sl[p].total.item()) == total and np.array_equal(raw16(got)[:count], raw16(data)[:count])
+
+
+# ------------------------------------------------------------------------------------------------ MLP, independent reference
+def test_forward_against_an_independent_torch_reference(nb):
+    """Q-values and policy probabilities of every forward path against torch.nn.functional on the CPU in float64 and
+    float32 (agent.py:101-103 relu/relu head, 110-112 relu/softmax head) -- a reference that shares no code with the
+    kernels or with oracle/leduc_oracle.c -- on all 2^16 observation masks a few bit patterns wide plus random ones."""
+    import torch.nn.functional as F
+
+    rng = np.random.RandomState(3)
+    w = glorot(nb, 77)
+    w[:, 1920:1984] = rng.uniform(-0.2, 0.2, (4, 64))   # non-zero biases too
+    w[:, 2176:] = rng.uniform(-0.2, 0.2, (4, 3))
+    sp = nb.SelfPlay(64, weights=torch.from_numpy(w), seed=1)
+    masks = np.concatenate([rng.randint(0, 1 << 30, 60000), np.arange(4096), (np.arange(4096) << 18)]).astype(np.int64)
+    masks &= (1 << 30) - 1
+    net = rng.randint(0, 4, len(masks)).astype(np.int8)
+    x64 = torch.from_numpy(((masks[:, None] >> np.arange(30)) & 1).astype(np.float64))
+    want = torch.zeros((len(masks), 3), dtype=torch.float64)
+    want32 = torch.zeros((len(masks), 3), dtype=torch.float32)
+    for k in range(4):
+        m = torch.from_numpy(net == k)
+        for dt, dst in ((torch.float64, want), (torch.float32, want32)):
+            W1 = torch.from_numpy(w[k, :1920].reshape(30, 64)).to(dt)
+            b1 = torch.from_numpy(w[k, 1920:1984]).to(dt)
+            W2 = torch.from_numpy(w[k, 1984:2176].reshape(64, 3)).to(dt)
+            b2 = torch.from_numpy(w[k, 2176:]).to(dt)
+            h = F.relu(F.linear(x64[m].to(dt), W1.t(), b1))
+            y = F.linear(h, W2.t(), b2)
+            dst[m] = (F.relu(y) if k & 1 else F.softmax(y, dim=-1)).to(dst.dtype)
+    assert float((want - want32.double()).abs().max()) < 2e-6  # the reference's own fp32 rounding
+    d_masks = torch.from_numpy(masks.astype(np.int32)).cuda()
+    d_net = torch.from_numpy(net).cuda()
+    for tc in (False, True):
+        got = sp.forward(d_masks, d_net, tensor_cores=tc).cpu().double()
+        assert float((got - want).abs().max()) <= TOL, tc
+    # and the C oracle against the same independent reference
+    nets = oracle_nets(nb, w)
+    sub = slice(0, 4000)
+    x32 = x64[sub].float().numpy()
+    for k in range(4):
+        m = net[sub] == k
+        ref = nets.forward(k, x32[m], "br" if k & 1 else "avg")
+        assert np.abs(ref - want[sub][torch.from_numpy(m)].numpy()).max() <= TOL
