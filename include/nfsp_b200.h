@@ -165,10 +165,23 @@ typedef struct {
                              shared-memory gathers), 2 = tensor cores, one mixed-net tile per 128-thread group,
                              3 = tensor cores, warp-specialised: env warps -> per-net tile queues -> tcgen05.mma on
                              net-homogeneous M128 N64 tiles -> epilogue warpgroups (TMEM -> relu -> 64x3 with W2 from
-                             the constant bank), 0 = library default */
-    int32_t reserve_sms;  /* variants 1 and 3: SMs left free for kernels of other streams (the learner's fit running
+                             the constant bank), 4 = CUDA cores with net-sorted warp groups (see below),
+                             0 = library default */
+    int32_t reserve_sms;  /* variants 1, 3 and 4: SMs left free for kernels of other streams (the learner's fit running
                              beside the rollout); the persistent grid is sm_count - reserve_sms CTAs.  0 = use them all */
+    /* variants 1 and 4, all NULL / 0 otherwise: the RL records go straight into the players' rings instead of d_rl
+     * (ReplayBuffer.add, replay_buffer.py:30-41, done by the rollout kernel itself): ticket = atomic add on
+     * *d_ring_total[p] (records ever inserted, advanced by the kernel), slot = ticket % ring_cap.  d_rl is not
+     * written and needs no nfsp_ring_insert afterwards.  Requires 2 * n * n_steps <= ring_cap: the records of one
+     * launch must not lap the ring (their order inside a launch is the order of the atomic tickets). */
+    void *d_ring[2];
+    uint64_t *d_ring_total[2];
+    int64_t ring_cap;
 } nfsp_rollout_io;
+/* 4 = CUDA cores, the decisions of a four-warp group sorted by net so that warps are net-homogeneous, records appended
+ * with one set of atomics per group: n_segments must be 1 (csrc/rollout_sorted.cu).  An experiment kept for the record:
+ * an LDS.128 costs four shared-memory cycles whatever its lanes read, so net-homogeneous warps save nothing
+ * (profiles/r02/sorted_rollout_notes.txt) */
 #define NFSP_ROLLOUT_DEFAULT_VARIANT 1
 
 /* The fused hot path: for n_steps, every game does one Agent.play decision (agent.py:130-156)

@@ -34,7 +34,8 @@ SYMBOLS = [
 class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
                 ("n_segments", C.c_int32), ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
-                ("d_forced_vec", C.c_void_p), ("variant", C.c_int32), ("reserve_sms", C.c_int32)]
+                ("d_forced_vec", C.c_void_p), ("variant", C.c_int32), ("reserve_sms", C.c_int32),
+                ("d_ring", C.c_void_p * 2), ("d_ring_total", C.c_void_p * 2), ("ring_cap", C.c_int64)]
 
 
 class InsertReq(C.Structure):

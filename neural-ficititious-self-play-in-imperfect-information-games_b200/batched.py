@@ -356,7 +356,10 @@ class SelfPlay:
 
     def __init__(self, n_games, weights=None, seed=1234, game0=0, device=None, eta=0.1, epsilon=0.06,
                  rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R",
-                 variant="default"):
+                 variant="default", direct_rings=False):
+        """direct_rings: the rollout kernel writes the RL records straight into the players' rings (variants "cuda" and
+        "sorted"; needs 2 * n_games * max_steps_per_call <= rl_capacity so that one launch cannot lap a ring): no staging
+        copy, `flush()` then only moves the SL records into the reservoirs.  "auto" = on when that condition holds."""
         self.variant = variant
         self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
         self.device, self.n = self.env.device, self.env.n
@@ -364,16 +367,25 @@ class SelfPlay:
         self.max_steps = int(max_steps_per_call)
         self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
         self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
-        # staging: n_seg segments; the 32 games starting at g append to segment (g/32) % n_seg.  Worst case per
+        sorted_variant = self.VARIANTS[variant] == 4
+        can_direct = self.VARIANTS[variant] in (0, 1, 4) and 2 * self.n * self.max_steps <= int(rl_capacity)
+        if direct_rings == "auto":
+            direct_rings = can_direct
+        if direct_rings and not can_direct:
+            raise ValueError("direct_rings needs variant 'cuda' or 'sorted' and 2 * n_games * max_steps_per_call <= rl_capacity")
+        self.direct_rings = bool(direct_rings)
+        # staging.  Variant "sorted" appends through ONE cursor per memory (a dense array, n_seg = 1); the warp-per-block
+        # variants use n_seg segments: the 32 games starting at g append to segment (g/32) % n_seg.  Worst case per
         # player, game and step: 2 RL records (previous + terminal) and 1 SL record.
         blocks = (self.n + 31) // 32
         self.n_seg = 1
-        while self.n_seg * 2 <= min(blocks, 1024):
+        while not sorted_variant and self.n_seg * 2 <= min(blocks, 1024):
             self.n_seg *= 2
         per_seg = ((blocks + self.n_seg - 1) // self.n_seg) * 32   # games that can map to one segment
         self.cap_rl = 2 * per_seg * self.max_steps
         self.cap_sl = per_seg * self.max_steps
-        self.stage_rl = [torch.empty((self.n_seg * self.cap_rl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
+        rl_slots = 1 if self.direct_rings else self.n_seg * self.cap_rl
+        self.stage_rl = [torch.empty((rl_slots, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
         self.stage_sl = [torch.empty((self.n_seg * self.cap_sl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
         self.counts = torch.zeros((4, self.n_seg), dtype=torch.int32, device=self.device)
         self.stats = torch.zeros(_lib.STATS_FIELDS, dtype=torch.int64, device=self.device)
@@ -405,11 +417,12 @@ class SelfPlay:
         check(fn(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
         return out
 
-    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3}
+    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4}
 
     def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0):
-        """variant: "cuda" (first layer as row sums on CUDA cores), "tcgen05" (first layer as tensor-core
-        tiles with the accumulator in TMEM) or None = self.variant.  reserve_sms: SMs the persistent rollout grid
+        """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
+        net), "tcgen05" / "tcgen05_ws" (first layer as tensor-core tiles with the accumulator in TMEM) or None =
+        self.variant.  reserve_sms: SMs the persistent rollout grid
         leaves to kernels of other streams (the learner beside it, PipelinedTrainer)."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
@@ -421,9 +434,17 @@ class SelfPlay:
                 io.d_rl[p], io.d_sl[p] = self.stage_rl[p].data_ptr(), self.stage_sl[p].data_ptr()
             io.cap_rl, io.cap_sl, io.n_segments = self.cap_rl, self.cap_sl, self.n_seg
             io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
+            if self.direct_rings:
+                for p in range(2):
+                    io.d_ring[p], io.d_ring_total[p] = self.rl[p].data.data_ptr(), self.rl[p].total.data_ptr()
+                io.ring_cap = self.rl[0].capacity
             if not want_debug:
                 self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
+        if self.direct_rings and io.variant not in (0, 1, 4):
+            raise ValueError("this SelfPlay was built with direct_rings: only the CUDA-core variants can run on it")
+        if (io.variant == 4) != (self.VARIANTS[self.variant] == 4):
+            raise ValueError("variant 'sorted' appends through one cursor per memory: build the SelfPlay with variant='sorted'")
         io.reserve_sms = int(reserve_sms)
         dbg = None
         if want_debug:
@@ -484,8 +505,9 @@ class SelfPlay:
         with torch.cuda.stream(self._side):  # both players' reservoirs: stamp, write, commit
             check(lib().nfsp_reservoir_insert_multi(res_reqs, 2, _stream(self.device)))
             self._join.record(self._side)
-        # both players' rings: insert, commit
-        check(lib().nfsp_ring_insert_multi(ring_reqs, 2, _stream(self.device)))
+        # both players' rings: insert, commit (nothing to move when the rollout kernel wrote the rings itself)
+        if not self.direct_rings:
+            check(lib().nfsp_ring_insert_multi(ring_reqs, 2, _stream(self.device)))
         main.wait_event(self._join)
 
     def sample_minibatches(self, batch=256, to_host=False):

@@ -10,6 +10,7 @@
 #include "mlp_math.cuh"
 #include "ptx_helpers.cuh"
 #include "rollout_fast.cuh"
+#include "rollout_tables.cuh"
 
 namespace nfsp {
 
@@ -22,7 +23,6 @@ constexpr int kRollThreads = 1024;  // rollout_kernel: one CTA per SM
 constexpr int kFwdRowQuads = 24;
 constexpr int kW1Floats = 128 * kFwdRowQuads * 4;
 constexpr int kW2Floats = 4 * 3 * kFwdRowQuads * 4;
-constexpr int kB2Floats = 4 * 4;
 constexpr int kPackFloats = kW1Floats + kW2Floats + kB2Floats;
 
 // element e of the batched forward's weight image
@@ -47,95 +47,10 @@ __device__ __forceinline__ float pack_weights_value(const float *__restrict__ w,
     }
 }
 
-// ---- group-factorised first layer (rollout path) --------------------------------------------------
-// Under main.train's turn order an observation is (cards of the actor, round-0 betting sequence,
-// round-1 betting sequence); each group takes few values, so W1^T x + b1 is the sum of TWO precombined
-// rows X + Y.  The rows are sums of W1 rows only (input independent), rebuilt whenever the weights change.
-//   per net 111 rows:
-//     X  0-2    round 0: private card c (+ b1)
-//        3-74   round 1: 3 + ((c*3 + pub)*2 + dealer)*4 + f, f = finished round-0 sequence CC, RC, CRC, RRC
-//               = card rows + public card + round-0 history bits (+ b1)
-//     Y  75-110 75 + dealer*18 + sigma, sigma = 9*round + sequence id so far in that round
-//               (0 -, 1 C, 2 R, 3 CC, 4 CR, 5 RC, 6 RR, 7 CRC, 8 RRC)
-// Shared-memory layout: a row is 24 float4 "quads": the 16 quads of the 64 hidden units followed by a copy of
-// the first 8, so a thread can read its row starting at quad rot = game & 7 with immediate offsets.  The 8
-// threads of a quarter-warp then hit 8 different 16-byte bank groups whatever rows they gather: the row
-// gathers are bank-conflict free (the straight layout ran at 2.0-2.5x the ideal wavefront count, ncu r01a).
-// W2 uses the same rotated layout, [net][output][24 quads], so a quad of h meets its own weights.
-constexpr int kNetRows = 111, kRowQuads = 24;
-constexpr int kTabRows = 4 * kNetRows;
-constexpr int kTabFloats = kTabRows * kRowQuads * 4;
-constexpr int kTabW2Floats = 4 * 3 * kRowQuads * 4;
-constexpr int kTabImageFloats = kTabFloats + kTabW2Floats + kB2Floats;
-constexpr int kTabImageBytes = kTabImageFloats * 4;
-
-// history bits of betting sequence `id` in round rr when `d` deals (the dealer opens, players alternate)
-__device__ __forceinline__ uint32_t seq_bits(int rr, int d, int id) {
-    const int s0 = id == 0 ? 0 : (id == 1 || id == 3 || id == 4 || id == 7 ? 1 : 2);
-    const int s1 = id < 3 ? 0 : (id == 3 || id == 5 ? 1 : 2);
-    const int s2 = id >= 7 ? 1 : 0;
-    const int sl[3] = {s0, s1, s2};
-    uint32_t bits = 0;
-    for (int k = 0; k < 3; ++k)
-        if (sl[k]) bits |= 1u << (((k & 1) ^ d) * 12 + rr * 6 + k * 2 + (sl[k] - 1));
-    return bits;
-}
-
-// element e of the rollout's table image
-__device__ __forceinline__ float pack_tables_value(const float *__restrict__ w, int e) {
-    {
-        float v = 0.f;
-        if (e < kTabFloats) {
-            const int x = e & 3, pos = (e >> 2) % kRowQuads, row = (e >> 2) / kRowQuads;
-            const int net = row / kNetRows, r = row % kNetRows, j = (pos & 15) * 4 + x;
-            const float *W1 = w + net * NFSP_NET_PARAMS;  // W1[i*64 + j]
-            uint32_t bits = 0;                            // observation bits this row stands for
-            bool bias = false;
-            if (r < 3) {
-                bits = 1u << (24 + r);
-                bias = true;
-            } else if (r < 75) {
-                const int idx = r - 3, f = idx & 3, d = (idx >> 2) & 1, cp = idx >> 3, c = cp / 3, pub = cp % 3;
-                const int fin[4] = {3, 5, 7, 8};
-                bits = (1u << (24 + c)) | (1u << (27 + c)) | (1u << (27 + pub)) | seq_bits(0, d, fin[f]);
-                bias = true;
-            } else {
-                bits = seq_bits(((r - 75) % 18) / 9, (r - 75) / 18, (r - 75) % 9);
-            }
-            for (int i = 0; i < 30; ++i)
-                if ((bits >> i) & 1u) v += W1[i * 64 + j];
-            if (bias) v += W1[1920 + j];
-        } else if (e < kTabFloats + kTabW2Floats) {
-            const int f = e - kTabFloats, x = f & 3, pos = (f >> 2) % kRowQuads, c = ((f >> 2) / kRowQuads) % 3;
-            const int net = (f >> 2) / (3 * kRowQuads);
-            v = w[net * NFSP_NET_PARAMS + 1984 + ((pos & 15) * 4 + x) * 3 + c];
-        } else {
-            const int f = e - kTabFloats - kTabW2Floats, c = f & 3, net = f >> 2;
-            if (c < 3) v = w[net * NFSP_NET_PARAMS + 2176 + c];
-        }
-        return v;
-    }
-}
-
 // both images in one launch: pack = [batched-forward image (kPackFloats) | rollout table image (kTabImageFloats)]
 __global__ void pack_images_kernel(const float *__restrict__ w, float *__restrict__ pack) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats + kTabImageFloats; e += gridDim.x * blockDim.x)
         pack[e] = e < kPackFloats ? pack_weights_value(w, e) : pack_tables_value(w, e - kPackFloats);
-}
-
-// one decision of net `net`: layer 1 as two rotated row reads streamed into layer 2
-__device__ __forceinline__ void mlp_forward_tables(const float *__restrict__ st, uint32_t xrow, uint32_t yrow,
-                                                   uint32_t net, uint32_t rot, float &o0, float &o1, float &o2) {
-    const float4 *T = reinterpret_cast<const float4 *>(st);
-    const float4 *xr = T + (net * kNetRows + xrow) * kRowQuads + rot;
-    const float4 *yr = T + (net * kNetRows + yrow) * kRowQuads + rot;
-    const float4 *wr = T + kTabRows * kRowQuads + net * (3 * kRowQuads) + rot;
-    Layer2Acc acc;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        acc.quad_sum(xr[q], yr[q], wr[q], wr[kRowQuads + q], wr[2 * kRowQuads + q]);
-    }
-    acc.head(reinterpret_cast<const float4 *>(st + kTabFloats + kTabW2Floats)[net], net & 1u, o0, o1, o2);
 }
 
 // forward of one net on one observation mask; sw = packed image in shared memory.  The first layer is the sum of the
@@ -186,7 +101,7 @@ act_forward_kernel(const float *__restrict__ pack, const uint32_t *__restrict__ 
 // One persistent CTA per SM (the table image fills most of its shared memory); a warp owns 32 consecutive
 // games for the launch's steps, the games' state lives in registers in the actor-relative form of
 // nfsp_fast.cuh and goes back to HBM as the packed word.
-template <bool kDebug>
+template <bool kDebug, bool kDirect>
 __global__ void __launch_bounds__(kRollThreads, 1)
 rollout_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) float sw[];  // table image, kTabImageBytes
@@ -228,7 +143,7 @@ rollout_kernel(const RolloutArgs A) {
         const uint64_t game = A.game0 + (uint64_t)i;
         const uint32_t rot = (uint32_t)game & 7u;
         WarpStage W;
-        W.init(A, (uint32_t)(base >> 5) & (A.n_seg - 1u));
+        W.init(A, (uint32_t)(base >> 5) & (A.n_seg - 1u), kDirect);
         NfspFast g;
         g.unpack(live ? A.state[i] : 0ull);
         for (int t = 0; t < A.n_steps; ++t) {
@@ -244,7 +159,7 @@ rollout_kernel(const RolloutArgs A) {
             }
             mlp_forward_tables(sw, xrow, yrow, g.p() * 2u + (uint32_t)d.pol, rot, v0, v1, v2);
             if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; }
-            fast_finish<kDebug>(g, s_lut, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
+            fast_finish<kDebug, kDirect>(g, s_lut, A, W, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c);
             if ((t & 15) == 15) c.spill();
         }
         c.spill();  // the 5-bit counters must not run on into the warp's next block of games
@@ -269,8 +184,12 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats)));
         NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
         NFSP_CUDA(cudaFuncSetAttribute(act_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackFloats * sizeof(float))));
-        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
-        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
+        const int rc = nfsp_rollout_sorted_configure();
+        if (rc != NFSP_OK) return rc;
     }
     pack_images_kernel<<<(kPackFloats + kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
     NFSP_LAUNCH_CHECK();
@@ -304,6 +223,26 @@ extern "C" int nfsp_act_forward(nfsp_env_t h, const uint32_t *d_obs, const int8_
     return NFSP_OK;
 }
 
+int nfsp_rollout_direct_args(const nfsp_rollout_io *io, RolloutArgs &A, bool *direct) {
+    for (int q = 0; q < 2; ++q) { A.ring[q] = nullptr; A.ring_total[q] = nullptr; }
+    A.ring_cap = 0u;
+    A.ring_magic = 0ull;
+    *direct = io->d_ring[0] != nullptr || io->d_ring[1] != nullptr;
+    if (!*direct) return NFSP_OK;
+    NFSP_CHECK_ARG(io->d_ring[0] && io->d_ring[1] && io->d_ring_total[0] && io->d_ring_total[1],
+                   "the direct ring append needs both rings and their totals");
+    NFSP_CHECK_ARG(io->ring_cap > 1 && io->ring_cap < ((int64_t)1 << 32), "ring capacity out of range");
+    NFSP_CHECK_ARG(2 * A.n * (int64_t)A.n_steps <= io->ring_cap,
+                   "direct ring append needs 2 * n * n_steps <= ring capacity (a launch must not lap the ring)");
+    for (int q = 0; q < 2; ++q) {
+        A.ring[q] = (uint4 *)io->d_ring[q];
+        A.ring_total[q] = (unsigned long long *)io->d_ring_total[q];
+    }
+    A.ring_cap = (uint32_t)io->ring_cap;
+    A.ring_magic = ~0ull / (uint64_t)io->ring_cap;
+    return NFSP_OK;
+}
+
 extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io,
                             void *stream) {
     NFSP_CHECK_ARG(h != nullptr && io != nullptr, "null argument");
@@ -326,10 +265,22 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.work = h->d_work;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
-    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 3,
-                   "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group) or 3 (tcgen05, warp-specialised)");
+    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 4,
+                   "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group), 3 (tcgen05, warp-specialised) or 4 (CUDA cores, net-sorted groups)");
     const int variant = io->variant == 0 ? NFSP_ROLLOUT_DEFAULT_VARIANT : io->variant;
     NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
+    bool direct = false;
+    {
+        const int rc = nfsp_rollout_direct_args(io, A, &direct);
+        if (rc != NFSP_OK) return rc;
+    }
+    NFSP_CHECK_ARG(!direct || variant == 1 || variant == 4, "the direct ring append (d_ring) exists in variants 1 and 4 only");
+    if (variant == 4) {
+        const int rc = nfsp_rollout_sorted_launch(h, A, io, debug, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        h->step += (uint64_t)n_steps;
+        return NFSP_OK;
+    }
     if (variant == 3) {
         const int rc = nfsp_rollout_tq_launch(h, A, debug, io->reserve_sms, (cudaStream_t)stream);
         if (rc != NFSP_OK) return rc;
@@ -344,8 +295,10 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     }
     NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), (cudaStream_t)stream));
     const int grid = grid_for(h->n, kRollThreads, h->sm_count - io->reserve_sms, 1);
-    if (debug) rollout_kernel<true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
-    else rollout_kernel<false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
+    if (debug && direct) rollout_kernel<true, true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
+    else if (debug) rollout_kernel<true, false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
+    else if (direct) rollout_kernel<false, true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
+    else rollout_kernel<false, false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     NFSP_LAUNCH_CHECK();
     h->step += (uint64_t)n_steps;
     return NFSP_OK;

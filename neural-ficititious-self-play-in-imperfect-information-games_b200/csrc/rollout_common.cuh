@@ -13,6 +13,12 @@ int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug,
 // launches the warp-specialised tcgen05 rollout (rollout_tq.cu)
 int nfsp_rollout_tq_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug, int reserve_sms, cudaStream_t st);
 
+// launches the net-sorted CUDA-core rollout (rollout_sorted.cu); sets its kernels' shared-memory attribute once per device
+int nfsp_rollout_sorted_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st);
+// validates nfsp_rollout_io.d_ring* and fills the direct-ring fields of A; *direct = the call appends directly
+int nfsp_rollout_direct_args(const nfsp_rollout_io *io, nfsp::RolloutArgs &A, bool *direct);
+int nfsp_rollout_sorted_configure();
+
 namespace nfsp {
 
 // ---- warp-aggregated record append -------------------------------------------------------------
@@ -39,7 +45,20 @@ struct RolloutArgs {
     uint32_t *trace;
     float *vec;
     const float *forced;
+    // direct ring append (nfsp_rollout_io.d_ring*): the RL records go straight into the players' rings
+    uint4 *ring[2];
+    unsigned long long *ring_total[2];  // records ever inserted = the ticket counter
+    uint32_t ring_cap;
+    uint64_t ring_magic;                // floor((2^64 - 1) / ring_cap): ticket % ring_cap without a division
 };
+
+// ticket % cap for a ring (replay_buffer.py:36-41: slot of the ticket-th record ever added)
+__device__ __forceinline__ uint32_t ring_slot(unsigned long long ticket, uint32_t cap, uint64_t magic) {
+    const unsigned long long q = __umul64hi(ticket, magic);  // floor(ticket / cap) or one less
+    unsigned long long r = ticket - q * cap;
+    if (r >= cap) r -= cap;
+    return (uint32_t)r;
+}
 
 // per-thread counters; the action histogram packs 3 x 21-bit fields per player (flushed before overflow)
 struct Counters {

@@ -13,10 +13,12 @@ import nfsp_b200  # noqa: E402
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 n, T = 1 << 20, 8
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ("cuda", "tcgen05", "tcgen05_ws")
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ("cuda", "cuda+direct", "sorted", "sorted+direct", "tcgen05", "tcgen05_ws")
 tune = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
 for variant in variants:
-    sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T, variant=variant)
+    direct = variant.endswith("+direct")
+    sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T,
+                            variant=variant.split("+")[0], direct_rings=direct)
     if tune:
         from nfsp_b200._lib import lib
         lib().nfsp_rollout_tune(sp.env._h, tune[0], tune[1])

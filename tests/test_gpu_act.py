@@ -105,7 +105,7 @@ def test_forward_tensor_core_mixed_nets_ragged(nb):
         assert np.abs(got - ref).max() <= TOL and np.abs(base - ref).max() <= TOL, n
 
 
-@pytest.mark.parametrize("variant", ["cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["sorted", "cuda", "tcgen05", "tcgen05_ws"])
 @pytest.mark.parametrize("n,steps,eta,eps", [(1, 30, 0.5, 0.5), (1000, 12, 0.1, 0.06), (50_000, 8, 0.3, 0.2)])
 def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps, variant):
     """The fused act+step+remember kernel vs the oracle's restatement of Agent.play/main.train."""
@@ -142,7 +142,7 @@ def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps, variant):
         assert abs(float(pol.mean()) - eta) < 5 * (eta * (1 - eta) / pol.numel()) ** 0.5 + 1e-3
 
 
-@pytest.mark.parametrize("variant", ["cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["sorted", "cuda", "tcgen05", "tcgen05_ws"])
 def test_fused_rollout_golden_hands(nb, golden_dir, variant):
     """All 20 352 reference hands (incl. zero vectors and argmax ties) through the fused kernel with the
     reference's scripted score vectors; records must equal the oracle's, which is pinned to the
@@ -293,7 +293,7 @@ def test_rollout_variants_agree_without_debug(nb):
     whenever no decision is a last-bit near-tie (seeded so that none is)."""
     n, steps = 20_000, 8
     res = []
-    for variant in ("cuda", "tcgen05", "tcgen05_ws"):
+    for variant in ("cuda", "sorted", "tcgen05", "tcgen05_ws"):
         sp = nb.SelfPlay(n, seed=77, eta=0.2, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12,
                          max_steps_per_call=steps, variant=variant)
         sp.rollout(steps, insert=False)
@@ -305,7 +305,7 @@ def test_rollout_variants_agree_without_debug(nb):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("variant", ["cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["sorted", "cuda", "tcgen05", "tcgen05_ws"])
 @pytest.mark.parametrize("n", [1, 31, 129, 1000])
 def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
     """One launch of 19 steps == 19 launches of one step (game words, counters, record multisets), for sizes that
@@ -333,7 +333,7 @@ def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
     assert res[0][1]["transitions"] == n * steps and res[0][1]["dropped"] == 0
 
 
-@pytest.mark.parametrize("variant", ["cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["sorted", "cuda", "tcgen05", "tcgen05_ws"])
 def test_staging_overflow_drops_and_never_writes_past_a_segment(nb, variant):
     """compute-sanitizer is closed on this pool, so the bounds are checked by hand: staging segments far too small
     for the rollout, canary words behind every segment.  Records that do not fit are counted as dropped, the
@@ -344,6 +344,8 @@ def test_staging_overflow_drops_and_never_writes_past_a_segment(nb, variant):
     from nfsp_b200.batched import check, lib, _stream
 
     n, steps, seed, n_seg, cap, guard = 3000, 8, 5, 8, 40, 8
+    if variant == "sorted":  # one cursor per memory: a single dense array, just as short of the records produced
+        n_seg, cap = 1, 320
     full = nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps,
                        variant=variant)
     full.rollout(steps, insert=False)
@@ -400,6 +402,70 @@ def test_memories_after_rollout_match_sequential_oracle(nb):
         got = sp.sl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
         assert int(sp.sl[p].total.item()) == total and np.array_equal(raw16(got), raw16(data))
     assert int(sp.counts.sum().item()) == 0
+
+
+def _rows(a):
+    return list(map(bytes, np.ascontiguousarray(a).view(np.uint8).reshape(-1, 16)))
+
+
+@pytest.mark.parametrize("variant", ["cuda", "sorted"])
+def test_direct_ring_append_equals_the_staged_insert(nb, variant):
+    """direct_rings: the rollout kernel writes the RL records into the rings itself (ticket = atomic add on the ring's
+    total, slot = ticket % capacity; replay_buffer.py:30-41).  Launch by launch the records are those the staged path
+    moves with nfsp_ring_insert (same seed, same games) and those of the oracle; after the rings have wrapped they hold
+    every record of the last launches and the most recent part of the launch the wrap cuts."""
+    from collections import Counter
+
+    n, steps, seed, launches = 3000, 4, 21, 11
+    cap = 2 * n * steps  # the smallest ring a launch may not lap: holds about 3.6 launches' worth of one player's records
+    mk = lambda direct: nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=cap, sl_capacity=1 << 12,  # noqa: E731
+                                    max_steps_per_call=steps, variant=variant, direct_rings=direct)
+    sd, ss = mk(True), mk(False)
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(0.3))
+    nets = oracle_nets(nb, nb.glorot_nets(seed, "cuda").cpu().numpy())
+    per_launch = [[], []]
+    for k in range(launches):
+        out = ss.rollout(steps, insert=False, debug=True)
+        rl, sl = ss.staged()
+        ref = b.rollout_act(1 + k * steps, steps, nets, orc.u32_frac(0.3), orc.u32_frac(0.1), forced_vec=out["vec"].cpu().numpy())
+        for p in range(2):
+            assert np.array_equal(canon(rl[p]), canon(ref["rl"][p]))
+            per_launch[p].append(_rows(rl[p]))
+        ss.flush()
+        before = [int(sd.rl[p].total.item()) for p in range(2)]
+        sd.rollout(steps)  # production kernel, rings written in place, flush() only moves the SL records
+        for p in range(2):
+            assert int(sd.rl[p].total.item()) - before[p] == len(rl[p]) and int(sd.rl[p].total.item()) == int(ss.rl[p].total.item())
+            if int(sd.rl[p].total.item()) <= cap:  # not wrapped yet: the same multiset in the same span of slots
+                t = int(sd.rl[p].total.item())
+                assert np.array_equal(canon(sd.rl[p].data[:t].cpu().numpy()), canon(ss.rl[p].data[:t].cpu().numpy()))
+    assert np.array_equal(sd.env.state_words().cpu().numpy(), ss.env.state_words().cpu().numpy())
+    assert sd.read_stats() == ss.read_stats() and int(sd.counts.sum().item()) == 0
+    for p in range(2):
+        assert int(sd.rl[p].total.item()) > 2 * cap  # wrapped at least twice
+        for q in range(2):  # the reservoirs went through the staged path in both objects, fed in different orders
+            assert int(sd.sl[q].total.item()) == int(ss.sl[q].total.item())
+        have = Counter(_rows(sd.rl[p].data.cpu().numpy()))
+        room = cap
+        for k in reversed(range(launches)):
+            want = Counter(per_launch[p][k])
+            if len(per_launch[p][k]) <= room:  # a launch the ring still holds completely
+                assert not (want - have), (p, k)
+                have -= want
+                room -= len(per_launch[p][k])
+            else:  # the launch the wrap cuts: what is left of the ring comes from it
+                assert sum(have.values()) == room and not (have - want), (p, k)
+                break
+
+
+def test_direct_ring_refuses_a_ring_one_launch_could_lap(nb):
+    with pytest.raises(ValueError):
+        nb.SelfPlay(3000, rl_capacity=2 * 3000 * 4 - 1, sl_capacity=1 << 12, max_steps_per_call=4, variant="sorted", direct_rings=True)
+    with pytest.raises(ValueError):
+        nb.SelfPlay(3000, rl_capacity=1 << 20, sl_capacity=1 << 12, max_steps_per_call=4, variant="tcgen05", direct_rings=True)
+    sp = nb.SelfPlay(3000, rl_capacity=1 << 20, sl_capacity=1 << 12, max_steps_per_call=4, direct_rings="auto")
+    assert sp.direct_rings and sp.stage_rl[0].shape[0] == 1
 
 
 def test_sample_minibatches_slab_equals_per_memory_samples(nb):
