@@ -108,10 +108,12 @@ rollout_kernel(const RolloutArgs A) {
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ FastLuts s_lut;
+    __shared__ uint32_t s_next;  // blocks of games this CTA has handed to its warps
     if (threadIdx.x < NFSP_STATS_FIELDS) s_stats[threadIdx.x] = 0ull;
     s_lut.fill();
     const uint32_t bar = smem_u32(&s_bar);
     if (threadIdx.x == 0) {
+        s_next = 0u;
         mbar_init(bar, 1);
         fence_mbar_init();
     }
@@ -129,12 +131,14 @@ rollout_kernel(const RolloutArgs A) {
     FastCounters c;
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const uint32_t lane = threadIdx.x & 31u;
-    // blocks of 32 consecutive games are handed out dynamically: one atomic per warp and block keeps the 148 x 24
-    // warps busy to the end (a static split of 2^15 blocks over 3552 warps leaves 8% of the last pass idle)
+    // blocks of 32 consecutive games: CTA c owns blocks c, c + grid, c + 2 grid, ... (every SM gets its share however
+    // few games there are -- with one global counter the first CTAs to start took all 2 048 blocks of a 64k-game
+    // launch and 84 SMs idled), and its warps take them dynamically through a shared-memory counter, which keeps the
+    // 32 warps busy to the end (a static split over the warps leaves 8% of the last pass idle)
     const int64_t n_blocks = (A.n + 31) >> 5;
     for (;;) {
         uint32_t blk = 0;
-        if (lane == 0) blk = atomicAdd(A.work, 1u);
+        if (lane == 0) blk = blockIdx.x + gridDim.x * atomicAdd(&s_next, 1u);
         blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
         if ((int64_t)blk >= n_blocks) break;
         const int64_t base = (int64_t)blk << 5;
@@ -293,8 +297,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         h->step += (uint64_t)n_steps;
         return NFSP_OK;
     }
-    NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    const int grid = grid_for(h->n, kRollThreads, h->sm_count - io->reserve_sms, 1);
+    const int grid = grid_for(h->n, 32, h->sm_count - io->reserve_sms, 1);  // at least one block of 32 games per CTA
     if (debug && direct) rollout_kernel<true, true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else if (debug) rollout_kernel<true, false><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);
     else if (direct) rollout_kernel<false, true><<<grid, kRollThreads, kTabImageBytes, (cudaStream_t)stream>>>(A);

@@ -352,8 +352,10 @@ __global__ void __launch_bounds__(kRowThreads, 1)
 learner_fit_rows_kernel(const FitArgs F) {
     extern __shared__ __align__(16) unsigned char fit_smem_raw[];
     RowFitSmem &S = *reinterpret_cast<RowFitSmem *>(fit_smem_raw);
+    __shared__ int s_peer_lost;  // a peer did not answer within the time limit of the gradient exchange
     const LearnerArgs &A = F.A;
     const int net = blockIdx.x, player = net >> 1, is_br = net & 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_peer_lost = 0;
     if (!((A.net_mask >> net) & 1)) {
         if (F.w_out != A.w)
             for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) F.w_out[net * NFSP_NET_PARAMS + e] = A.w[net * NFSP_NET_PARAMS + e];
@@ -515,12 +517,20 @@ learner_fit_rows_kernel(const FitArgs F) {
                 while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
                     if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; never hang the GPU
                         *F.err = 1u;
+                        s_peer_lost = 1;
                         break;
                     }
                     __nanosleep(64);
                 }
             }
             __syncthreads();
+            if (s_peer_lost) {
+                // a slot of a silent peer may be stale or half written: summing it would make the replicas differ
+                // silently.  Give up on this net instead: no further steps, NaN weights out (nobody can mistake them for a
+                // result), the error word set for Learner.check_peers()
+                for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) S.w[e] = __int_as_float(0x7FC00000);
+                break;
+            }
             const float scale = 1.0f / (float)F.world;
             for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
                 float g = 0.f;

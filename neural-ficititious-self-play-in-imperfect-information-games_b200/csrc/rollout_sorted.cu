@@ -32,7 +32,7 @@ struct __align__(16) GroupShared {
     uint32_t cnt[kSortG];   // per warp: decisions of sort key 0..3, one byte each
     uint32_t base[4];       // this step's first slot of the group in rl0, rl1, sl0, sl1
     uint32_t acc[2];        // records of the step so far: rl0 | rl1 << 16, sl0 | sl1 << 16
-    uint32_t arrive, blk;
+    uint32_t arrive, pad;
     uint32_t desc[kSortGT];  // sorted decisions: xrow | (yrow - 75) << 7 | net << 13
     float4 res[kSortGT];     // their scores
 };
@@ -79,11 +79,8 @@ rollout_sorted_kernel(const RolloutArgs A) {
     uint4 *const rl0 = kDirect ? A.ring[0] : A.rl[0], *const rl1 = kDirect ? A.ring[1] : A.rl[1];
     const uint32_t cap_rl = kDirect ? A.ring_cap : (uint32_t)A.cap_rl, cap_sl = (uint32_t)A.cap_sl;
     const int64_t n_blocks = (A.n + kSortGT - 1) / kSortGT;
-    for (;;) {
-        if (tig == 0) S.blk = atomicAdd(A.work, 1u);  // blocks of 128 consecutive games, handed out dynamically
-        group_bar(bar_id);
-        const uint32_t blk = S.blk;
-        if ((int64_t)blk >= n_blocks) break;
+    // blocks of 128 consecutive games, dealt round-robin to the chip's warp groups (every SM gets its share of a small batch)
+    for (uint32_t blk = blockIdx.x + gridDim.x * grp; (int64_t)blk < n_blocks; blk += gridDim.x * kSortGroups) {
         const int64_t i = (int64_t)blk * kSortGT + tig;
         const bool live = i < A.n;
         const uint64_t game = A.game0 + (uint64_t)i;
@@ -224,11 +221,9 @@ int nfsp_rollout_sorted_configure() {
 int nfsp_rollout_sorted_launch(nfsp_env_t h, const RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st) {
     NFSP_CHECK_ARG(io->n_segments == 1, "variant 4 appends through one cursor per memory: n_segments must be 1");
     const bool direct = A.ring[0] != nullptr;
-    NFSP_CUDA(cudaMemsetAsync(h->d_work, 0, sizeof(uint32_t), st));
     int grid = h->sm_count - io->reserve_sms;
-    const int64_t need = (A.n + kSortGT - 1) / kSortGT;
-    const int64_t ctas = (need + kSortGroups - 1) / kSortGroups;
-    if (ctas < grid) grid = (int)ctas;
+    const int64_t need = (A.n + kSortGT - 1) / kSortGT;  // at least one block of 128 games per CTA
+    if (need < grid) grid = (int)need;
     if (grid < 1) grid = 1;
     if (debug) return direct ? launch_sorted<true, true>(A, grid, st) : launch_sorted<true, false>(A, grid, st);
     return direct ? launch_sorted<false, true>(A, grid, st) : launch_sorted<false, false>(A, grid, st);

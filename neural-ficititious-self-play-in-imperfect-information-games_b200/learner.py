@@ -57,13 +57,9 @@ class Learner:
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
         self._peers = None
         if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
-            self._setup_peers()
             # every rank must take the same path (a rank in the peer exchange and one in an NCCL all-reduce would wait
-            # for each other forever): the exchange is used only if the set-up worked everywhere
-            ok = torch.tensor([1 if self._peers is not None else 0], dtype=torch.int32, device=self.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                self._peers = None
+            # for each other forever): _setup_peers agrees on every phase collectively
+            self._setup_peers()
         self.iteration = [0, 0]
         self.target_update_count = [0, 0]
         self.temp = [1.0, 1.0]
@@ -109,32 +105,63 @@ class Learner:
         return [self._pos[0], self._pos[2]], [self._pos[1], self._pos[3]]
 
     # ---- several GPUs of one box: the all-reduce of every SGD step inside the fit kernel, over peer memory ----
+    def _agree(self, ok: bool) -> bool:
+        """True iff every rank says ok: one MIN all-reduce, so that all ranks take the same branch."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(int(flag.item()))
+
+    def _no_peers(self, why):
+        self._peers = None
+        self._peer_note = "peer exchange unavailable: %s" % (why,)
+        import warnings
+
+        warnings.warn("nfsp_b200 learner: %s; using one NCCL all-reduce per SGD step" % self._peer_note, RuntimeWarning)
+
     def _setup_peers(self):
         """One exchange buffer per rank that every rank can address (torch symmetric memory: CUDA IPC under the hood).
-        Falls back to the NCCL path (one all-reduce per SGD step) if the ranks cannot map each other's memory."""
-        try:
+        Falls back to the NCCL path (one all-reduce per SGD step) if the ranks cannot map each other's memory.
+
+        Collective-safe: each phase that can fail on one rank only runs under its own try, and the ranks AGREE on its
+        outcome with an all-reduce before anybody enters the next collective -- no rank can sit in rendezvous / barrier
+        while another has already fallen back."""
+        symm_mem, buf, why = None, None, None
+        try:  # phase 1, local only: the import, the size limit, the allocation
             import torch.distributed._symmetric_memory as symm_mem
 
+            if dist.get_world_size() > _lib.MAX_PEERS:
+                raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
             buf = symm_mem.empty(_lib.PEER_BUF_FLOATS, dtype=torch.float32, device=self.device)
             buf.zero_()
-            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
             torch.cuda.synchronize(self.device)
-            dist.barrier()  # every buffer is zero before anybody's first flag can arrive
-            p = _lib.Peers()
-            p.world, p.rank = dist.get_world_size(), dist.get_rank()
-            if p.world > _lib.MAX_PEERS:
-                raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
-            for r in range(p.world):
-                p.d_buf[r] = int(hdl.buffer_ptrs[r])
-            self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            p.d_err = self._peer_err.data_ptr()
-            self._peers, self._peer_keep, self._epoch = p, (buf, hdl), 0
-        except Exception as e:  # noqa: BLE001  (no peer access: NCCL per step, same results up to summation order)
-            self._peers = None
-            self._peer_note = "peer exchange unavailable: %r" % (e,)
-            import warnings
+        except Exception as e:  # noqa: BLE001
+            why = repr(e)
+        if not self._agree(why is None):
+            return self._no_peers(why or "another rank could not allocate symmetric memory")
+        hdl = None
+        try:  # phase 2, collective: every rank is here
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        except Exception as e:  # noqa: BLE001
+            why = repr(e)
+        if not self._agree(why is None):
+            return self._no_peers(why or "another rank could not map the peers' buffers")
+        dist.barrier()  # every buffer is zero before anybody's first flag can arrive
+        p = _lib.Peers()
+        p.world, p.rank = dist.get_world_size(), dist.get_rank()
+        for r in range(p.world):
+            p.d_buf[r] = int(hdl.buffer_ptrs[r])
+        self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        p.d_err = self._peer_err.data_ptr()
+        self._peers, self._peer_keep, self._epoch = p, (buf, hdl), 0
 
-            warnings.warn("nfsp_b200 learner: %s; using one NCCL all-reduce per SGD step" % self._peer_note, RuntimeWarning)
+    def check_peers(self):
+        """Raises if a peer GPU failed to answer during any gradient exchange so far (the kernel then gave up after ~2 s,
+        skipped that net's remaining SGD steps and wrote NaN weights for it, so the failure cannot go unnoticed; the
+        replicas are no longer identical and the run must be restarted from a checkpoint).  Reads one device word (syncs):
+        called by update(sync=True), by PipelinedTrainer.finish() and every `peer_check_every` updates."""
+        if self._peers is not None and int(self._peer_err.item()):
+            raise RuntimeError("a peer GPU did not answer during the gradient exchange: the weights of this update are "
+                               "invalid (NaN) and the replicas have diverged")
 
     def _fit_peers(self, idx_rl, idx_sl, mask, w_in=None, w_out=None):
         io = self._io(idx_rl, idx_sl, 0, self.minibatch, mask, w_in)
@@ -217,8 +244,8 @@ class Learner:
                         stats = self.flat[GRAD:].clone()
         if sync:
             self._loss = stats.cpu().tolist()
-            if self._peers is not None and int(self._peer_err.item()):
-                raise RuntimeError("a peer GPU did not answer during the gradient exchange")
+        if sync or (self._peers is not None and (self.updates + 1) % self.peer_check_every == 0):
+            self.check_peers()
         s = getattr(self, "_loss", [0.0] * N_STATS)
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:
@@ -288,6 +315,7 @@ class PipelinedTrainer:
     def finish(self):
         """Wait for the last update and make its weights the acting nets; returns them."""
         torch.cuda.current_stream(self.sp.device).wait_stream(self.stream)
+        self.learner.check_peers()
         self.sp.set_weights(self.w[self.j % 2])
         return self.w[self.j % 2]
 
