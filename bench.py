@@ -2,7 +2,8 @@
 """Headline benchmark: Leduc transitions/sec of the fused NFSP rollout (env step + NFSP act + memories).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on all host threads
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the REFERENCE's own Python (leduc.newenv +
+                                                             # main.train + Agent.play + both memories) on all host cores
 
 One "step" = one pass of the hot path over one batch: `rollout(T)` (T decisions for every game: observe,
 remember, act with the eta-mixed nets, env.step, terminal observations, auto re-deal) followed by the
@@ -14,6 +15,8 @@ shard by global id with no data-path collective.
 Prints ONE JSON line (contract in the task statement).  `value` is device-timed with inputs resident in
 HBM; `e2e` adds, per step, the pinned-host -> device copy of the four nets' weights, the sampling of a
 256-row minibatch from all four memories and the device -> host read of those batches and the counters.
+Outside the timed region one shard of the workload (65 536 games x 8 decisions, same seed / eta / epsilon /
+nets) is replayed against the CPU oracle: `parity_checked`.
 """
 import argparse
 import gc
@@ -145,27 +148,86 @@ def cpu_rollout_rate(threads, games_per_thread, t_steps, reps):
     return trans, times
 
 
+REF_HANDS_PER_STEP = 1500  # hands per process and step of the reference arm (about 0.3 s of its Python per step)
+
+
+def reference_rates(procs, hands, kind="nfsp", reps=1):
+    """The reference's own code (oracle/ref_timing.py: /root/reference, or the verbatim copy under baseline/_ref that
+    travels to the GPU box) on `procs` processes; returns the list of per-repetition results."""
+    from oracle import ref_timing
+
+    return [ref_timing.run(kind, hands, procs) for _ in range(reps)]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import orc
+    from oracle import ref_timing
 
-    threads = max(1, os.cpu_count() or 1)
-    gpt = 8192
-    trans, times = cpu_rollout_rate(threads, gpt, T_PER_CALL, args.warmup + args.steps)
-    times = times[args.warmup:]
-    total = sum(times)
-    value = trans * len(times) / total
-    sample = "%d threads x %d games x %d decisions per step (oracle port of Agent.play + newenv + memories adds)" % (
-        threads, gpt, T_PER_CALL)
+    cores = max(1, os.cpu_count() or 1)
+    if ref_timing.reference_root() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no reference tree (neither /root/reference nor baseline/_ref)"}))
+        return
+    runs = reference_rates(cores, REF_HANDS_PER_STEP, "nfsp", args.warmup + args.steps)[args.warmup:]
+    trans = sum(r["transitions"] for r in runs)
+    secs = sum(r["seconds"] for r in runs)
+    value = trans / secs
+    sample = ("%d processes x %d hands per step of the reference's own leduc.newenv.Env + main.train + Agent.play + "
+              "ReplayBuffer / ReservoirBuffer (Keras nets replaced by np.random.rand(1,1,3): an upper bound of its rate)"
+              % (cores, REF_HANDS_PER_STEP))
     line = {"impl": "reference", "metric": "leduc_transitions_per_sec", "value": value, "unit": "transitions/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(),
-            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port", "sample": sample},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(runs),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "nfsp_rollout on the CPU: " + sample, "hands_per_step": cores * REF_HANDS_PER_STEP,
+                       "transitions_per_step": trans / len(runs), "cpu": runs[0]["cpu"],
+                       "baseline_config": "BASELINE.json configs[0] driver (reference path), NFSP loop of configs[2]"},
+            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "cpu": runs[0]["cpu"]},
             "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def parity_check(nfsp_b200, dev, game0):
+    """One shard of the benchmarked workload against the CPU oracle, outside every timed region: 65 536 games x 8
+    decisions with the bench's seed, eta, epsilon and nets (debug launch, teacher-forced on the kernel's own score
+    vectors) -- trace planes and record multisets bit for bit, score vectors within 1e-5 -- and the production launch
+    from the same start must leave the same game words, counters and records."""
+    import numpy as np
+    import torch
+
+    from oracle import orc
+
+    n, steps = 1 << 16, T_PER_CALL
+    mk = lambda: nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=1 << 21,  # noqa: E731
+                                    sl_capacity=1 << 18, max_steps_per_call=steps)
+    sp = mk()
+    out = sp.rollout(steps, insert=False, debug=True)
+    rl, sl = sp.staged()
+    vec = out["vec"].cpu().numpy()
+    tr = out["raw"].cpu().numpy().view(np.uint32)
+    w = sp.weights.cpu().numpy()
+    b = orc.NfspBatch(n, SEED, game0=game0)
+    b.reset(0, orc.u32_frac(ETA))
+    ref = b.rollout_act(1, steps, orc.Nets([nfsp_b200.split_net(w[k]) for k in range(4)]), orc.u32_frac(ETA),
+                        orc.u32_frac(EPS), forced_vec=vec)
+    canon = lambda a: (lambda v: v[np.lexsort(v.T[::-1])])(np.ascontiguousarray(a).view(np.uint32).reshape(-1, 4))  # noqa: E731
+    ok = (np.array_equal(tr[0], ref["trace"]["obs"]) and np.array_equal(tr[1].view(np.float32), ref["trace"]["reward"])
+          and np.array_equal(tr[2], ref["trace"]["misc"]))
+    err = float(np.abs(vec - ref["vec"]).max())
+    ok = ok and err <= 1e-5
+    for p in range(2):
+        ok = ok and np.array_equal(canon(rl[p]), canon(ref["rl"][p])) and np.array_equal(canon(sl[p]), canon(ref["sl"][p]))
+    prod = mk()
+    prod.rollout(steps, insert=False)
+    prl, psl = prod.staged()
+    ok = ok and np.array_equal(prod.env.state_words().cpu().numpy(), sp.env.state_words().cpu().numpy())
+    ok = ok and prod.read_stats() == sp.read_stats()
+    for p in range(2):
+        ok = ok and np.array_equal(canon(prl[p]), canon(rl[p])) and np.array_equal(canon(psl[p]), canon(sl[p]))
+    return bool(ok), {"games": n, "decisions": steps, "game0": int(game0), "max_abs_score_error": err,
+                      "what": "trace planes, RL/SL record multisets, counters and game words vs oracle/leduc_oracle.c; "
+                              "debug and production launch"}
 
 
 def workload_config():
@@ -173,6 +235,8 @@ def workload_config():
                         "ring %d + reservoir %d records per player, sample %d" %
                         (GAMES_PER_GPU, T_PER_CALL, ETA, EPS, RL_CAP, SL_CAP, BATCH),
             "games_per_gpu": GAMES_PER_GPU, "decisions_per_step": T_PER_CALL, "l2": "flushed between timed steps",
+            "records": "RL records written straight into the rings by the rollout kernel (direct_rings), SL records "
+                       "staged and moved into the reservoirs by one insert launch",
             "baseline_config": "BASELINE.json configs[4] per GPU (configs[2] at 1M games)"}
 
 
@@ -249,7 +313,8 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     game0, n = sharding.shard_games(GAMES_PER_GPU * world, rank, world)
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
-                            sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant)
+                            sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
+                            direct_rings=args.variant in ("default", "cuda"))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
     stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
@@ -354,6 +419,17 @@ def run_gpu(args):
         trainer.finish()
         torch.cuda.synchronize()
 
+    # after all those updates every rank must hold bit-identical nets (the gradient sum is taken in rank order everywhere)
+    chk = sp.weights.view(torch.int32).to(torch.int64).sum().reshape(1)
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        weights_same = bool(int(lo.item()) == int(hi.item()))
+    else:
+        weights_same = True
+    weights_same = weights_same and bool(torch.isfinite(sp.weights).all().item())
+
     # env-only K1 (BASELINE configs[1]) beside it, same games count, trace planes written
     env = nfsp_b200.BatchedNfspEnv(n, seed=SEED, game0=game0, device=dev)
     env.reset()
@@ -404,41 +480,52 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     buffers = buffer_kernels(nfsp_b200, dev, ev) if world == 1 else None
-    # the other first-layer variant, kernel only, for the record
-    other = "tcgen05" if args.variant in ("default", "cuda") else "cuda"
-    other_ms = 0.0
-    for k in range(3 + args.steps):
-        flush_buf.zero_()
-        a, b = ev(), ev()
-        a.record()
-        sp.rollout(T_PER_CALL, insert=False, variant=other)
-        b.record()
-        b.synchronize()
-        sp.counts.zero_()
-        if k >= 3:
-            other_ms += a.elapsed_time(b)
-    other_rate = n * T_PER_CALL * args.steps / (other_ms * 1e-3)
-    # BASELINE configs[2] as stated: 64k parallel games (latency-bound: 2 048 blocks of 32 games for 4 736 warps)
+    # the other variants of the rollout kernel, kernel only, for the record
+    others = {}
+    for other in ("sorted", "tcgen05", "tcgen05_ws"):
+        spo = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=1 << 16,
+                                 sl_capacity=1 << 16, max_steps_per_call=T_PER_CALL, variant=other)
+        other_ms = 0.0
+        for k in range(3 + args.steps):
+            flush_buf.zero_()
+            a, b = ev(), ev()
+            a.record()
+            spo.rollout(T_PER_CALL, insert=False)
+            b.record()
+            b.synchronize()
+            spo.counts.zero_()
+            if k >= 3:
+                other_ms += a.elapsed_time(b)
+        others[other] = {"kernel_transitions_per_sec": n * T_PER_CALL * args.steps / (other_ms * 1e-3),
+                         "kernel_ms_per_launch": other_ms / args.steps}
+        del spo
+    # BASELINE configs[2] + configs[3] as stated: 65 536 parallel games, ring of 200 000 + reservoir of 2 000 000 records per
+    # player, rollout(8) + the move of the records into the memories (a launch laps the ring: staged path) + 256-row sample
     sp64 = nfsp_b200.SelfPlay(1 << 16, seed=SEED, device=dev, eta=ETA, epsilon=EPS, rl_capacity=200000,
                               sl_capacity=2000000, max_steps_per_call=T_PER_CALL)
-    ms64 = 0.0
+    ms64, ms64s = 0.0, 0.0
     for k in range(3 + args.steps):
-        a, b = ev(), ev()
+        a, b, c = ev(), ev(), ev()
         a.record()
         sp64.rollout(T_PER_CALL)
         b.record()
-        b.synchronize()
+        sp64.sample_minibatches(BATCH)
+        c.record()
+        c.synchronize()
         if k >= 3:
             ms64 += a.elapsed_time(b)
+            ms64s += b.elapsed_time(c)
     rate64 = (1 << 16) * T_PER_CALL * args.steps / (ms64 * 1e-3)
     del sp64
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
-    roofline = {"bound": "hbm", "kernel": "rollout_tc_kernel" if args.variant == "tcgen05" else "rollout_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": {"tcgen05": "rollout_tc_kernel", "tcgen05_ws": "rollout_tq_kernel", "sorted": "rollout_sorted_kernel"}.get(args.variant, "rollout_kernel"), "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_transition": BYTES_PER_TRANSITION,
-                "kernel_ms_per_launch": ker_ms / args.steps, "useful_tflops": kernel_rate * 4224 / 1e12}
+                "kernel_ms_per_launch": ker_ms / args.steps,
+                # what a dense 30x64 + 64x3 evaluation would cost; the kernel's first layer is two row adds, not 1 920 MACs
+                "dense_equivalent_tflops": kernel_rate * 4224 / 1e12}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         tf = json.load(open(traffic_file))
@@ -448,14 +535,51 @@ def run_gpu(args):
             # first-layer rows and 768 B of second-layer weights from shared memory into registers
             roofline["limiter"] = "shared-memory register-fill bandwidth, not HBM"
             roofline["ncu"] = tf["rollout_kernel_ncu"]
-    cpu = None
+    cpu, cpu_extra = None, {}
     if world == 1:
+        cores = max(1, os.cpu_count() or 1)
+        try:  # the reference's own Python (a reported baseline, never the product): NFSP loop on all cores and on one core,
+            # and BASELINE configs[0] -- leduc.env.Env under the README driver, 100 000 hands -- on one core and on all cores
+            r_all = reference_rates(cores, 3000, "nfsp")[0]
+            cpu = {"value": r_all["transitions_per_sec"], "unit": "transitions/s", "cores": cores, "kind": "reference",
+                   "cpu": r_all["cpu"],
+                   "sample": "%d processes x 3000 hands: the reference's leduc.newenv.Env + main.train + Agent.play + both memories, "
+                             "Keras predict replaced by np.random.rand(1,1,3) (upper bound of its rate)" % cores}
+            r_one = reference_rates(1, 12000, "nfsp")[0]
+            l_one = reference_rates(1, 100000, "legacy")[0]
+            l_all = reference_rates(cores, max(1, 100000 // cores), "legacy")[0]
+            cpu_extra["reference_nfsp_1core"] = {"transitions_per_sec": r_one["transitions_per_sec"], "hands": 12000}
+            cpu_extra["reference_config1_env_100k_hands"] = {
+                "what": "BASELINE configs[0]: leduc.env.Env, README driver (reset; step(a0,0); step(a1,1); get_new_state x2), uniform-random actions",
+                "one_core": {"transitions_per_sec": l_one["transitions_per_sec"], "hands_per_sec": l_one["hands_per_sec"],
+                             "seconds": l_one["seconds"], "hands": 100000},
+                "all_cores": {"transitions_per_sec": l_all["transitions_per_sec"], "hands_per_sec": l_all["hands_per_sec"],
+                              "seconds": l_all["seconds"], "processes": cores, "hands_per_process": l_all["hands_per_proc"]},
+                "cpu": l_one["cpu"]}
+        except Exception as e:
+            cpu = {"value": None, "unit": "transitions/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
         try:
             trans, times = cpu_rollout_rate(1, 65536, T_PER_CALL, 3)
-            cpu = {"value": trans * len(times) / sum(times), "unit": "transitions/s", "cores": 1, "kind": "port",
-                   "sample": "65536 games x %d decisions x %d passes, oracle port, 1 thread" % (T_PER_CALL, len(times))}
-        except Exception as e:  # the oracle is a reported baseline, never the product
-            cpu = {"value": None, "unit": "transitions/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+            cpu_extra["port_1thread"] = {"transitions_per_sec": trans * len(times) / sum(times), "kind": "port",
+                                         "sample": "65536 games x %d decisions x %d passes, oracle/leduc_oracle.c, 1 thread" % (T_PER_CALL, len(times))}
+        except Exception as e:
+            cpu_extra["port_1thread"] = {"transitions_per_sec": None, "sample": "failed: %r" % (e,)}
+    parity_ok, parity_info = parity_check(nfsp_b200, dev, game0)
+    gpu_trans = GAMES_PER_GPU * world * T_PER_CALL
+    training = {"what": "rollout(8) + memory inserts + Learner.update(sync=False) per iteration; gradients of the 8 SGD steps "
+                        "exchanged inside the fit kernel over peer memory when n_gpus > 1",
+                "sequential_ms": train_ms, "sequential_transitions_per_sec": gpu_trans / (train_ms * 1e-3),
+                "pipelined_ms": pipe_ms, "pipelined_transitions_per_sec": (gpu_trans / (pipe_ms * 1e-3)) if pipe_ms else None,
+                "learner_update_ms": learner_ms, "gradient_exchange": "peer memory" if getattr(learner, "_peers", None) is not None else ("nccl" if world > 1 else "none")}
+    configs = [
+        {"config": "BASELINE configs[1]: batched Leduc env, %d games, uniform-random actions, env kernel only" % n,
+         "kernel": "nfsp_step_fsm_kernel", "transitions_per_sec": env_rate,
+         "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
+         "moved_frac_of_hbm_peak": env_rate * (12.0 + 16.0 / ENV_T_PER_CALL) / 1e9 / hbm},
+        {"config": "BASELINE configs[2]+[3]: NFSP rollout, 65536 games, eta 0.1, ring 200000 + reservoir 2000000 per player, insert + 256-batch sample per step",
+         "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps, "sample_us": 1e3 * ms64s / args.steps},
+        {"config": "BASELINE configs[4] per GPU: the headline line", "transitions_per_sec": value / world},
+    ]
     h2d = int(w_host.numel() * 4)
     d2h = int(2 * BATCH * (30 + 3 + 1 + 30 + 1) * 4 + 2 * BATCH * 33 * 4 + sp.stats.numel() * 8)
     line = {"metric": "leduc_transitions_per_sec", "value": value, "unit": "transitions/s", "n_gpus": world,
@@ -464,9 +588,13 @@ def run_gpu(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 6 * args.steps,  # rollout + (ring insert, commit) + (reservoir stamp, write, commit), both players per launch
+            "gpu_launches": 2 * args.steps,  # rollout_kernel (records into the rings in place) + insert_kernel (both reservoirs)
             "roofline": roofline, "cpu_baseline": cpu,
-            "extra": {"env_only": {"kernel": "nfsp_step_fsm_kernel", "transitions_per_sec": env_rate,
+            "parity_checked": parity_ok, "parity": parity_info,
+            # the iteration that communicates (BASELINE configs[4]): rollout + memories + update_strategy() of both agents
+            "training_step": training, "weights_identical_on_all_ranks": weights_same,
+            "configs": configs,
+            "extra": {"cpu": cpu_extra, "env_only": {"kernel": "nfsp_step_fsm_kernel", "transitions_per_sec": env_rate,
                                    "achieved_gbs": env_rate * ENV_BYTES_PER_TRANSITION / 1e9,
                                    "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
                                    "algorithmic_bytes_per_transition": ENV_BYTES_PER_TRANSITION,
@@ -482,16 +610,11 @@ def run_gpu(args):
                                           "moved_bytes_per_transition": 12.0 + 8.0 / leg_iters,
                                           "moved_gbs": legacy_rate * (12.0 + 8.0 / leg_iters) / 1e9,
                                           "moved_frac_of_hbm_peak": legacy_rate * (12.0 + 8.0 / leg_iters) / 1e9 / hbm},
-                      "variant": args.variant, "other_variant": {"name": other, "kernel_transitions_per_sec": other_rate,
-                                                                 "kernel_ms_per_launch": other_ms / args.steps},
-                      "rollout_64k_games": {"config": "BASELINE configs[2]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts",
-                                            "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps},
+                      "variant": args.variant, "other_variants": others,
+                      "rollout_64k_games": {"config": "BASELINE configs[2]+[3]: 65536 games, ring 200000 + reservoir 2000000, rollout(8) + memory inserts; then the 256-row sample of all four memories",
+                                            "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps,
+                                            "sample_256_all_memories_us": 1e3 * ms64s / args.steps},
                       "buffers": buffers,
-                      "training_step": {"what": "rollout(8) + memory inserts + Learner.update(sync=False) per iteration (BASELINE configs[4])",
-                                        "ms": train_ms, "transitions_per_sec": GAMES_PER_GPU * world * T_PER_CALL / (train_ms * 1e-3),
-                                        "pipelined_ms": pipe_ms,
-                                        "pipelined_transitions_per_sec": (GAMES_PER_GPU * world * T_PER_CALL / (pipe_ms * 1e-3)) if pipe_ms else None,
-                                        "pipelined": "update j beside rollout j+1 (acting nets one update behind), 4 SMs left to the learner"},
                       "learner": {"update_ms": learner_ms, "sgd_steps_per_update": 8, "allreduce_floats": 4 * 2179 + 8,
                                   "exploitability_proxy": lstats.get("exploitability"), "trained_mask": lstats.get("trained")},
                       "hands": int(st[10]), "transitions_counted": int(st[11]), "records_dropped": int(st[12])}}
@@ -506,8 +629,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="default", choices=["default", "cuda", "tcgen05"],
-                    help="first layer of the acting nets: CUDA-core row sums or tcgen05 tensor-core tiles")
+    ap.add_argument("--variant", default="default", choices=["default", "cuda", "sorted", "tcgen05", "tcgen05_ws"],
+                    help="rollout kernel: CUDA-core row sums (default), net-sorted warp groups, tcgen05 tensor-core tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -201,33 +201,45 @@ int nfsp_rollout_profile(nfsp_env_t h, uint64_t *out24);
 /* A staged batch is n_segments segments of seg_cap 16-byte slots with one device count each
  * (d_counts uint32[n_segments]); n_segments = 1 is a plain dense array.  Batch order = segment order, then
  * slot order.  The batch is consumed: on the stream, *d_total += records and the counts are zeroed.
+ * Every insert is ONE cooperative launch (segment prefixes, grid barrier, the moves, commit); d_scratch is
+ * uint64[n_segments + NFSP_INSERT_SCRATCH_WORDS] of device memory per memory, zeroed once by the caller and left to
+ * the library afterwards (barrier words + the prefix table); calls that share a scratch block must be stream-ordered.
  *
- * ReplayBuffer.add (replay_buffer.py:30-41) for a batch: FIFO ring, slot = ticket % cap where ticket counts
- * records ever inserted (*d_total); of a batch larger than the ring only the last `cap` survive. */
+ * ReplayBuffer.add (replay_buffer.py:30-41) for a batch: FIFO ring of cap 16-byte records, slot = ticket % cap where
+ * ticket counts records ever inserted (*d_total); of a batch larger than the ring only the last `cap` survive. */
+#define NFSP_INSERT_SCRATCH_WORDS 4
 int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
-                     int n_segments, int64_t seg_cap, void *stream);
+                     int n_segments, int64_t seg_cap, uint64_t *d_scratch, void *stream);
 /* ReservoirBuffer.add (ReservoirBuffer.py:18-28) for a batch.  mode 0 = Algorithm R (Vitter):
  * ticket t >= cap replaces slot j ~ U[0,t] iff j < cap; mode 1 = the reference's law
  * (j = randrange(1, cap+1), replace iff j < cap).  Same-slot collisions inside a batch are
- * resolved as in the sequential algorithm (largest ticket wins) via d_stamp uint64[cap]. */
-int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp, const void *d_recs,
-                          uint32_t *d_counts, int n_segments, int64_t seg_cap, uint64_t seed, int mode, void *stream);
-/* The same two calls for several memories at once (the two players' rings in one launch, their reservoirs in another):
- * request k is exactly nfsp_ring_insert / nfsp_reservoir_insert with these arguments.  d_stamp, seed, mode are read for
- * reservoirs only. */
+ * resolved as in the sequential algorithm (largest ticket wins).
+ * Storage: d_res is cap slots of NFSP_RESERVOIR_SLOT_BYTES = 32 bytes (one DRAM sector), zeroed once:
+ *   {16-byte SL record, uint64 stamp = ticket + 1 of the record that owns the slot, uint64 unused}
+ * so the stamp's atomic and the record's store touch the same sector.  Record j is at d_res + 32 * j. */
+#define NFSP_RESERVOIR_SLOT_BYTES 32
+int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
+                          int n_segments, int64_t seg_cap, uint64_t seed, int mode, uint64_t *d_scratch, void *stream);
+/* The same for several memories in one launch: request k is exactly nfsp_ring_insert (reservoir = 0) /
+ * nfsp_reservoir_insert (reservoir = 1) with these arguments; seed and mode are read for reservoirs only.
+ * nfsp_insert_multi takes any mix -- after a rollout both players' rings and reservoirs travel together --
+ * nfsp_ring_insert_multi / nfsp_reservoir_insert_multi insist on one kind.  The barrier words of request 0 serve
+ * the whole launch. */
 #define NFSP_MAX_INSERT_REQS 4
 typedef struct {
     void *d_mem;
     int64_t cap;
     uint64_t *d_total;
-    uint64_t *d_stamp;
+    uint64_t *d_scratch;
     const void *d_recs;
     uint32_t *d_counts;
     int32_t n_segments;
     int64_t seg_cap;
     uint64_t seed;
     int32_t mode;
+    int32_t reservoir;
 } nfsp_insert_req;
+int nfsp_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 int nfsp_reservoir_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 /* random.sample(buffer, batch) (replay_buffer.py:46-51, ReservoirBuffer.py:33-37): `batch`
@@ -245,7 +257,7 @@ int nfsp_sample_indices(uint64_t seed, uint64_t call_idx, const uint64_t *d_tota
  * positions in d_idx (the learner kernels read the packed records themselves). */
 #define NFSP_MAX_SAMPLE_REQS 8
 typedef struct {
-    const void *d_mem;        /* ring / reservoir storage, 16-byte records */
+    const void *d_mem;        /* ring (16-byte records) / reservoir (32-byte slots, the record first) storage */
     const uint64_t *d_total;  /* records ever inserted (device) */
     int64_t cap;
     uint64_t seed, call_idx;
@@ -258,7 +270,7 @@ int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, int batch, 
  * s [b][30], a [b][3] (one-hot of the stored argmax), r [b], s2 [b][30], t [b] */
 int nfsp_gather_rl(const void *d_ring, const int64_t *d_idx, int batch, float *d_s, float *d_a, float *d_r,
                    float *d_s2, float *d_t, void *stream);
-/* ReservoirBuffer.sample_batch (ReservoirBuffer.py:39-43): s [b][30], a [b][3] */
+/* ReservoirBuffer.sample_batch (ReservoirBuffer.py:39-43): s [b][30], a [b][3]; d_res = 32-byte slots */
 int nfsp_gather_sl(const void *d_res, const int64_t *d_idx, int batch, float *d_s, float *d_a, void *stream);
 
 /* ------------------------------------------------------------------ learner */
@@ -268,7 +280,7 @@ typedef struct {
     const float *d_target_weights; /* [2][NFSP_NET_PARAMS] target best-response nets (agent.py:70-72)         */
     const void *d_rl[2];           /* the players' rings and the sampled slots (nfsp_sample_indices)          */
     const int64_t *d_rl_idx[2];
-    const void *d_sl[2];           /* the players' reservoirs and the sampled slots                           */
+    const void *d_sl[2];           /* the players' reservoirs (32-byte slots) and the sampled slots           */
     const int64_t *d_sl_idx[2];
     int32_t row0, rows;            /* minibatch = sampled rows [row0, row0+rows) (Keras fit batches of 32)    */
     float gamma;                   /* config.ini Agent.Gamma                                                  */

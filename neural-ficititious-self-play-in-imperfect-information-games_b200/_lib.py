@@ -26,7 +26,7 @@ SYMBOLS = [
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_tune", "nfsp_rollout_profile",
-    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
+    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_insert_multi", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
 ]
 
@@ -39,9 +39,12 @@ class RolloutIO(C.Structure):
 
 
 class InsertReq(C.Structure):
-    _fields_ = [("d_mem", C.c_void_p), ("cap", C.c_int64), ("d_total", C.c_void_p), ("d_stamp", C.c_void_p),
+    _fields_ = [("d_mem", C.c_void_p), ("cap", C.c_int64), ("d_total", C.c_void_p), ("d_scratch", C.c_void_p),
                 ("d_recs", C.c_void_p), ("d_counts", C.c_void_p), ("n_segments", C.c_int32), ("seg_cap", C.c_int64),
-                ("seed", C.c_uint64), ("mode", C.c_int32)]
+                ("seed", C.c_uint64), ("mode", C.c_int32), ("reservoir", C.c_int32)]
+
+
+INSERT_SCRATCH_WORDS, RESERVOIR_SLOT_BYTES = 4, 32  # NFSP_INSERT_SCRATCH_WORDS, NFSP_RESERVOIR_SLOT_BYTES
 
 
 MAX_PEERS, PEER_BUF_FLOATS = 8, 17536  # NFSP_MAX_PEERS, NFSP_PEER_BUF_FLOATS
@@ -119,8 +122,9 @@ def lib():
     L.nfsp_act_forward.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_act_forward_tc.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
-    L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp]
-    L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp]
+    L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
+    L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp, vp]
+    L.nfsp_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_ring_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_reservoir_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]

@@ -236,14 +236,25 @@ SL_DT = np.dtype([("s", "<u4"), ("a", "<f4", (3,))])
 
 class _Memory:
     is_ring = True
+    slot_words = 4  # int32 words per storage slot
 
     def __init__(self, capacity: int, seed: int = 1234, device=None):
         self.device = _device(device)
         self.capacity = int(capacity)
         self.seed = int(seed) & (2 ** 64 - 1)
-        self.data = torch.zeros((self.capacity, 4), dtype=torch.int32, device=self.device)
+        self.store = torch.zeros((self.capacity, self.slot_words), dtype=torch.int32, device=self.device)
+        self.data = self.store[:, :4]  # the 16-byte records (a strided view for the reservoir's 32-byte slots)
         self.total = torch.zeros(1, dtype=torch.int64, device=self.device)  # records ever inserted
+        self._scratch = None
         self.sample_calls = 0
+
+    def scratch(self, n_seg: int) -> torch.Tensor:
+        """The insert kernel's barrier words + segment-prefix table (zeroed once, then the library's)."""
+        need = int(n_seg) + _lib.INSERT_SCRATCH_WORDS
+        if self._scratch is None or self._scratch.numel() < need:
+            torch.cuda.current_stream(self.device).synchronize()  # an insert that still uses the old block
+            self._scratch = torch.zeros(need, dtype=torch.int64, device=self.device)
+        return self._scratch
 
     def size(self) -> int:
         """count saturates at capacity (replay_buffer.py:36-44).  Reads one device word (syncs)."""
@@ -260,7 +271,7 @@ class _Memory:
     def records(self) -> np.ndarray:
         """Host copy of the stored records in storage-slot order (tests)."""
         dt = RL_DT if self.is_ring else SL_DT
-        return self.data.cpu().numpy().view(np.uint8).reshape(-1).view(dt)[: self.size()].copy()
+        return np.ascontiguousarray(self.data.cpu().numpy()).view(np.uint8).reshape(-1).view(dt)[: self.size()].copy()
 
     def clear(self):
         self.total.zero_()
@@ -276,8 +287,8 @@ class DeviceRing(_Memory):
         consumed: counts are zeroed).  A plain dense batch is n_seg = 1."""
         n_seg = counts.numel()
         seg_cap = recs.shape[0] // n_seg if seg_cap is None else seg_cap
-        check(lib().nfsp_ring_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(recs), _ptr(counts),
-                                     n_seg, int(seg_cap), _stream(self.device)))
+        check(lib().nfsp_ring_insert(_ptr(self.store), self.capacity, _ptr(self.total), _ptr(recs), _ptr(counts),
+                                     n_seg, int(seg_cap), _ptr(self.scratch(n_seg)), _stream(self.device)))
 
     def sample(self, batch: int):
         idx, n = self.sample_slots(batch)
@@ -287,7 +298,7 @@ class DeviceRing(_Memory):
         a = torch.empty((b, 3), dtype=torch.float32, device=self.device)
         r = torch.empty(b, dtype=torch.float32, device=self.device)
         t = torch.empty(b, dtype=torch.float32, device=self.device)
-        check(lib().nfsp_gather_rl(_ptr(self.data), _ptr(idx), b, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(t),
+        check(lib().nfsp_gather_rl(_ptr(self.store), _ptr(idx), b, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(t),
                                    _stream(self.device)))
         return s, a, r, s2, t, idx, n
 
@@ -297,31 +308,36 @@ class DeviceReservoir(_Memory):
     BASELINE.json's north_star specifies); mode "reference" = the reference's constant-probability law."""
 
     is_ring = False
+    slot_words = 8  # 32-byte slots: {record, int64 stamp = ticket + 1 of the owning record, int64 unused} = one DRAM sector
 
     def __init__(self, capacity, seed=1234, device=None, mode="R"):
         super().__init__(capacity, seed, device)
         if mode not in ("R", "reference"):
             raise ValueError("mode must be 'R' or 'reference'")
         self.mode = 0 if mode == "R" else 1
-        self.stamp = torch.zeros(self.capacity, dtype=torch.int64, device=self.device)
+
+    @property
+    def stamp(self) -> torch.Tensor:
+        """int64 [capacity] view of the slots' stamps."""
+        return self.store.view(torch.int64)[:, 2]
 
     def insert(self, recs, counts, seg_cap=None):
         n_seg = counts.numel()
         seg_cap = recs.shape[0] // n_seg if seg_cap is None else seg_cap
-        check(lib().nfsp_reservoir_insert(_ptr(self.data), self.capacity, _ptr(self.total), _ptr(self.stamp),
-                                          _ptr(recs), _ptr(counts), n_seg, int(seg_cap), self.seed, self.mode,
+        check(lib().nfsp_reservoir_insert(_ptr(self.store), self.capacity, _ptr(self.total), _ptr(recs), _ptr(counts),
+                                          n_seg, int(seg_cap), self.seed, self.mode, _ptr(self.scratch(n_seg)),
                                           _stream(self.device)))
 
     def sample(self, batch: int):
         idx, n = self.sample_slots(batch)
         s = torch.empty((batch, 30), dtype=torch.float32, device=self.device)
         a = torch.empty((batch, 3), dtype=torch.float32, device=self.device)
-        check(lib().nfsp_gather_sl(_ptr(self.data), _ptr(idx), batch, _ptr(s), _ptr(a), _stream(self.device)))
+        check(lib().nfsp_gather_sl(_ptr(self.store), _ptr(idx), batch, _ptr(s), _ptr(a), _stream(self.device)))
         return s, a, idx, n
 
     def clear(self):
         super().clear()
-        self.stamp.zero_()
+        self.store.zero_()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -436,7 +452,7 @@ class SelfPlay:
             io.d_counts, io.d_stats = self.counts.data_ptr(), self.stats.data_ptr()
             if self.direct_rings:
                 for p in range(2):
-                    io.d_ring[p], io.d_ring_total[p] = self.rl[p].data.data_ptr(), self.rl[p].total.data_ptr()
+                    io.d_ring[p], io.d_ring_total[p] = self.rl[p].store.data_ptr(), self.rl[p].total.data_ptr()
                 io.ring_cap = self.rl[0].capacity
             if not want_debug:
                 self._io = io
@@ -477,38 +493,24 @@ class SelfPlay:
         return rl, sl
 
     def flush(self):
-        """Move the staged records into the memories (stream-ordered, no host sync): both players' rings in one
-        insert + commit pair on the caller's stream, both reservoirs as stamp + write + commit -- latency-bound, 1/13 of
-        the records -- on a side stream beside them (different memories, different rows of the count array).  The side
-        stream starts after the rollout and joins the caller's stream before this returns, so whatever follows (the
-        next rollout overwrites the staging arrays) waits for both."""
-        main = torch.cuda.current_stream(self.device)
-        if not hasattr(self, "_side"):
-            self._side = torch.cuda.Stream(self.device)
-            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
-        self._fork.record(main)
-        self._side.wait_event(self._fork)
-
-        if not hasattr(self, "_flush_reqs"):  # pointers and geometry never change: the request blocks are built once
-            def reqs(mems, stages, rows, seg_cap):
-                arr = (_lib.InsertReq * 2)()
-                for p in range(2):
-                    r, mem = arr[p], mems[p]
-                    r.d_mem, r.cap, r.d_total = mem.data.data_ptr(), mem.capacity, mem.total.data_ptr()
-                    r.d_stamp = mem.stamp.data_ptr() if hasattr(mem, "stamp") else None
-                    r.d_recs, r.d_counts = stages[p].data_ptr(), self.counts[rows[p]].data_ptr()
-                    r.n_segments, r.seg_cap, r.seed, r.mode = self.n_seg, seg_cap, mem.seed, getattr(mem, "mode", 0)
-                return arr
-
-            self._flush_reqs = (reqs(self.sl, self.stage_sl, (2, 3), self.cap_sl), reqs(self.rl, self.stage_rl, (0, 1), self.cap_rl))
-        res_reqs, ring_reqs = self._flush_reqs
-        with torch.cuda.stream(self._side):  # both players' reservoirs: stamp, write, commit
-            check(lib().nfsp_reservoir_insert_multi(res_reqs, 2, _stream(self.device)))
-            self._join.record(self._side)
-        # both players' rings: insert, commit (nothing to move when the rollout kernel wrote the rings itself)
-        if not self.direct_rings:
-            check(lib().nfsp_ring_insert_multi(ring_reqs, 2, _stream(self.device)))
-        main.wait_event(self._join)
+        """Move the staged records into the memories (stream-ordered, no host sync): ONE cooperative launch for both
+        players' rings and reservoirs (`nfsp_insert_multi`: segment prefixes, ring copies beside the reservoirs' stamp
+        pass, their write pass, totals committed and counts cleared).  With direct_rings the rings were written by the
+        rollout kernel itself and only the two reservoirs travel."""
+        if not hasattr(self, "_flush_reqs"):  # pointers and geometry never change: the request block is built once
+            mems = [(self.sl[p], self.stage_sl[p], 2 + p, self.cap_sl) for p in range(2)]
+            if not self.direct_rings:
+                mems += [(self.rl[p], self.stage_rl[p], p, self.cap_rl) for p in range(2)]
+            arr = (_lib.InsertReq * len(mems))()
+            for r, (mem, stage, row, seg_cap) in zip(arr, mems):
+                r.d_mem, r.cap, r.d_total = mem.store.data_ptr(), mem.capacity, mem.total.data_ptr()
+                r.d_scratch = mem.scratch(self.n_seg).data_ptr()
+                r.d_recs, r.d_counts = stage.data_ptr(), self.counts[row].data_ptr()
+                r.n_segments, r.seg_cap, r.seed, r.mode = self.n_seg, seg_cap, mem.seed, getattr(mem, "mode", 0)
+                r.reservoir = 0 if mem.is_ring else 1
+            self._flush_reqs = (arr, len(mems))
+        arr, n = self._flush_reqs
+        check(lib().nfsp_insert_multi(arr, n, _stream(self.device)))
 
     def sample_minibatches(self, batch=256, to_host=False):
         """sample_batch(batch) of all four memories (replay_buffer.py:46-59, ReservoirBuffer.py:33-43) into ONE
@@ -546,7 +548,7 @@ class SelfPlay:
             for p in range(2):
                 for k, mem in ((0, self.rl[p]), (1, self.sl[p])):
                     r = reqs[2 * p + k]
-                    r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
+                    r.d_mem, r.d_total, r.cap = mem.store.data_ptr(), mem.total.data_ptr(), mem.capacity
                     r.seed, r.is_ring = mem.seed, int(mem.is_ring)
                     r.d_out = slab.data_ptr() + 4 * (p * per + k * 65 * b)
             views = {src is host: [{k: src[o:o + n].view(shape) for k, (o, n, shape) in spec.items()} for spec in layout]

@@ -3,6 +3,8 @@
 //   K4 reservoir insert        (utils/ReservoirBuffer.py:18-28) Philox Algorithm R, two passes
 //   K5 minibatch sample        (replay_buffer.py:46-59, ReservoirBuffer.py:33-43) Floyd + gather/expand
 // All counts live in device memory: no host synchronisation on the hot path.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -15,81 +17,113 @@ __device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) { return __u
 // ---- staged batches --------------------------------------------------------------------------------
 // A batch is n_seg segments of seg_cap slots with a device count each (n_seg = 1: a plain dense array).
 // Record i of segment s has batch index prefix(s) + i, where prefix(s) = sum of the counts of the segments
-// before s; its ticket is total + that index.  Each CTA row (blockIdx.y = segment) recomputes its prefix
-// with one block reduction over the <= 65536 counts.
+// before s; its ticket is total + that index.
 struct Batch {
     const uint4 *recs;
-    const uint32_t *counts;
+    uint32_t *counts;
     uint32_t n_seg;
     uint64_t seg_cap;
 };
 
-__device__ __forceinline__ void batch_prefix(const Batch &B, uint32_t seg, uint64_t &before, uint64_t &all) {
-    __shared__ unsigned long long s_before, s_all;
-    if (threadIdx.x == 0) { s_before = 0ull; s_all = 0ull; }
-    __syncthreads();
-    unsigned long long lb = 0ull, la = 0ull;
-    for (uint32_t k = threadIdx.x; k < B.n_seg; k += blockDim.x) {
-        unsigned long long cnt = B.counts[k];
-        if (cnt > B.seg_cap) cnt = B.seg_cap;
-        la += cnt;
-        if (k < seg) lb += cnt;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lb += __shfl_xor_sync(0xFFFFFFFFu, lb, o);
-        la += __shfl_xor_sync(0xFFFFFFFFu, la, o);
-    }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_before, lb); atomicAdd(&s_all, la); }
-    __syncthreads();
-    before = s_before;
-    all = s_all;
-}
-
 // ---- memories of one launch ----------------------------------------------------------------------
-// The insert kernels take up to NFSP_MAX_INSERT_REQS memories at once (blockIdx.z = memory): the two players' rings
-// travel in one launch, their reservoirs in another -- at 64k games the flush is launch latency, not bandwidth.
+// ONE cooperative launch moves the staged batches of up to NFSP_MAX_INSERT_REQS memories (both players' rings and
+// reservoirs after a rollout): segment prefixes -> grid barrier -> ring copies + reservoir stamps -> grid barrier ->
+// reservoir payloads -> totals and counts committed.  At 64k games the flush used to be five launches on two streams
+// (36 us of launch latency for 30 us of work).
 struct Mem {
-    uint4 *data;
-    unsigned long long *stamp;  // reservoirs only
+    uint4 *data;        // ring: 16-byte records; reservoir: 32-byte slots {record, u64 stamp, u64 unused}
     uint64_t cap;
     uint64_t *total;
+    uint64_t *scratch;  // [0] barrier arrivals, [1] barrier generation, [2 .. 2 + n_seg] exclusive prefix of the counts
     Batch B;
     uint64_t seed;
     int mode;
+    int reservoir;
 };
 struct MemSet {
     Mem m[NFSP_MAX_INSERT_REQS];
+    int n;
+    uint32_t gx;     // CTAs' worth of work items per segment
+    uint64_t chunk;  // records per stamp / write round of the reservoirs
 };
+constexpr int kScratchHead = 2;
+constexpr uint64_t kResChunk = 1ull << 21;  // records per stamp / write round: the 64 MB of slots they touch stay in L2
+
+// sense-reversing grid barrier on two words of device memory (all CTAs are co-resident: cooperative launch)
+__device__ __forceinline__ void grid_sync(uint64_t *ctrl) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(ctrl);
+        volatile unsigned long long *gen = reinterpret_cast<volatile unsigned long long *>(ctrl + 1);
+        const unsigned long long g = *gen;
+        __threadfence();
+        if (atomicAdd(cnt, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            *cnt = 0ull;
+            __threadfence();
+            atomicAdd(const_cast<unsigned long long *>(gen), 1ull);
+        } else {
+            while (*gen == g) __nanosleep(32);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// exclusive prefix of one memory's segment counts (clamped to the segment capacity), by one CTA
+__device__ __forceinline__ void scan_counts(const Mem &M) {
+    __shared__ unsigned long long s_warp[kBufThreads / 32];
+    __shared__ unsigned long long s_run;
+    if (threadIdx.x == 0) s_run = 0ull;
+    __syncthreads();
+    uint64_t *pre = M.scratch + kScratchHead;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t k0 = 0; k0 < M.B.n_seg; k0 += kBufThreads) {
+        const uint32_t k = k0 + threadIdx.x;
+        unsigned long long c = 0ull;
+        if (k < M.B.n_seg) {
+            c = M.B.counts[k];
+            if (c > M.B.seg_cap) c = M.B.seg_cap;
+        }
+        unsigned long long incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long before = s_run;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+        if (k < M.B.n_seg) pre[k] = before + incl - c;
+        __syncthreads();
+        if (threadIdx.x == kBufThreads - 1) s_run = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pre[M.B.n_seg] = s_run;
+}
 
 // ---- K3 ------------------------------------------------------------------------------------------
 constexpr int kRingUnroll = 4;
 // slot = ticket % cap; of a batch larger than the ring only the last `cap` records survive (the others
-// would be evicted by popleft(), replay_buffer.py:40).
-__global__ void __launch_bounds__(kBufThreads) ring_insert_kernel(const MemSet S) {
-    const Mem &M = S.m[blockIdx.z];
+// would be evicted by popleft(), replay_buffer.py:40).  Work item = (segment, x of gx): records x*256 + t, stride gx*256.
+__device__ __forceinline__ void ring_item(const Mem &M, uint64_t total, uint32_t seg, uint32_t x, uint32_t gx) {
     const Batch &B = M.B;
-    const uint32_t seg = blockIdx.y;
-    if (seg >= B.n_seg) return;
-    uint64_t before, m;
-    batch_prefix(B, seg, before, m);
-    const uint64_t total = *M.total, cap = M.cap;
+    const uint64_t *pre = M.scratch + kScratchHead;
+    const uint64_t before = __ldcg(pre + seg), cnt = __ldcg(pre + seg + 1) - before, m = __ldcg(pre + B.n_seg), cap = M.cap;
     const uint64_t first = m > cap ? m - cap : 0;
-    uint64_t cnt = B.counts[seg];
-    if (cnt > B.seg_cap) cnt = B.seg_cap;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
     uint4 *ring = M.data;
     // slot of batch index idx = (total + idx) % cap without a 64-bit division per record: head = total % cap once, then
     // one conditional subtraction (a second reduction only for batches larger than the ring).  kRingUnroll records per
     // thread and iteration, the loads issued before the first store, so several 16-byte reads are in flight per thread.
     const uint64_t head = total % cap;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kRingUnroll) {
+    const uint64_t stride = (uint64_t)gx * blockDim.x;
+    for (uint64_t i0 = x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kRingUnroll) {
         uint4 v[kRingUnroll];
 #pragma unroll
         for (int u = 0; u < kRingUnroll; ++u) {
             const uint64_t i = i0 + (uint64_t)u * stride;
-            if (i < cnt) v[u] = src[i];
+            if (i < cnt) v[u] = __ldcs(src + i);
         }
 #pragma unroll
         for (int u = 0; u < kRingUnroll; ++u) {
@@ -104,17 +138,6 @@ __global__ void __launch_bounds__(kBufThreads) ring_insert_kernel(const MemSet S
     }
 }
 
-// runs after the insert kernel(s) of a batch, one CTA per memory: total += n, staged counts cleared for the next rollout
-__global__ void __launch_bounds__(kBufThreads) commit_kernel(const MemSet S) {
-    const Mem &M = S.m[blockIdx.x];
-    uint64_t before, m;
-    batch_prefix(M.B, 0, before, m);
-    __syncthreads();
-    uint32_t *counts = const_cast<uint32_t *>(M.B.counts);
-    for (uint32_t k = threadIdx.x; k < M.B.n_seg; k += blockDim.x) counts[k] = 0;
-    if (threadIdx.x == 0) *M.total += m;
-}
-
 // ---- K4 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket, uint64_t cap, int mode) {
     if (ticket < cap) return (int64_t)ticket;  // fill phase, ReservoirBuffer.py:22-24
@@ -127,70 +150,103 @@ __device__ __forceinline__ int64_t reservoir_slot(uint64_t seed, uint64_t ticket
     return j < cap ? (int64_t)j : -1;
 }
 
-// Both passes are random 8/16-byte accesses whose latency (not bandwidth) is the bound with one access in flight
-// per thread, so each thread handles kResUnroll records per iteration: the slot draws are independent and the
-// atomics / loads of an iteration are all issued before the first result is needed.
+// A reservoir slot is 32 bytes = one DRAM sector: {record, stamp = ticket + 1 of the record that owns it, unused}.
+// Two passes over the batch, a grid barrier between them (ReservoirBuffer.py:18-28 for a whole batch at once):
+//   stamp  every accepted record raises its slot's stamp to its ticket + 1 (atomicMax keeps the latest)
+//   write  the record whose ticket owns the stamp writes the payload -- the outcome of the sequential adds.
+// The random 8-byte atomic brings the slot's sector into L2; the stamp check and the 16-byte payload store of the second
+// pass then hit that same sector (separate stamp and payload arrays moved four sectors per record: 163 bytes of DRAM
+// traffic for 40 algorithmic, ncu r01).  Batches are processed in rounds of kResChunk records so that the sectors of a
+// round are still in L2 when its second pass comes.  Both passes are latency-bound with one access in flight per
+// thread, so each thread handles kResUnroll records per iteration, all slot draws / atomics / loads issued before the
+// first result is needed.
 constexpr int kResUnroll = 4;
 
-// pass 1: every accepted record stamps its slot with ticket+1; atomicMax keeps the latest
-__global__ void __launch_bounds__(kBufThreads) reservoir_stamp_kernel(const MemSet S) {
-    const Mem &M = S.m[blockIdx.z];
+template <bool kWrite>
+__device__ __forceinline__ void reservoir_item(const Mem &M, uint64_t total, uint32_t seg, uint32_t x, uint32_t gx, uint64_t lo,
+                                               uint64_t hi) {
     const Batch &B = M.B;
-    const uint32_t seg = blockIdx.y;
-    if (seg >= B.n_seg) return;
-    uint64_t before, m;
-    batch_prefix(B, seg, before, m);
-    const uint64_t total = *M.total, cap = M.cap, seed = M.seed;
+    const uint64_t *pre = M.scratch + kScratchHead;
+    const uint64_t before = __ldcg(pre + seg), cnt = __ldcg(pre + seg + 1) - before;
+    if (before >= hi || before + cnt <= lo) return;  // no record of this segment in the round [lo, hi)
+    const uint64_t i_lo = lo > before ? lo - before : 0, i_hi = hi - before < cnt ? hi - before : cnt;
+    const uint64_t cap = M.cap, seed = M.seed;
     const int mode = M.mode;
-    unsigned long long *stamp = M.stamp;
-    uint64_t cnt = B.counts[seg];
-    if (cnt > B.seg_cap) cnt = B.seg_cap;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kResUnroll) {
+    uint4 *res = M.data;
+    const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
+    const uint64_t stride = (uint64_t)gx * blockDim.x;
+    for (uint64_t i0 = i_lo + x * (uint64_t)blockDim.x + threadIdx.x; i0 < i_hi; i0 += stride * kResUnroll) {
         int64_t slot[kResUnroll];
 #pragma unroll
         for (int u = 0; u < kResUnroll; ++u) {
             const uint64_t i = i0 + (uint64_t)u * stride;
-            slot[u] = i < cnt ? reservoir_slot(seed, total + before + i, cap, mode) : -1;
+            slot[u] = i < i_hi ? reservoir_slot(seed, total + before + i, cap, mode) : -1;
         }
+        if (!kWrite) {
 #pragma unroll
-        for (int u = 0; u < kResUnroll; ++u)
-            if (slot[u] >= 0) atomicMax(stamp + slot[u], (unsigned long long)(total + before + i0 + (uint64_t)u * stride + 1u));
+            for (int u = 0; u < kResUnroll; ++u)
+                if (slot[u] >= 0)
+                    atomicMax(reinterpret_cast<unsigned long long *>(res + 2 * slot[u] + 1),
+                              (unsigned long long)(total + before + i0 + (uint64_t)u * stride + 1u));
+        } else {
+            unsigned long long owner[kResUnroll];
+#pragma unroll
+            for (int u = 0; u < kResUnroll; ++u)
+                owner[u] = slot[u] >= 0 ? __ldcg(reinterpret_cast<const unsigned long long *>(res + 2 * slot[u] + 1)) : 0ull;
+#pragma unroll
+            for (int u = 0; u < kResUnroll; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (slot[u] >= 0 && owner[u] == (unsigned long long)(total + before + i + 1u)) res[2 * slot[u]] = __ldcs(src + i);
+            }
+        }
     }
 }
 
-// pass 2: the record whose ticket owns the stamp writes the payload (== sequential order of adds)
-__global__ void __launch_bounds__(kBufThreads) reservoir_write_kernel(const MemSet S) {
-    const Mem &M = S.m[blockIdx.z];
-    const Batch &B = M.B;
-    const uint32_t seg = blockIdx.y;
-    if (seg >= B.n_seg) return;
-    uint64_t before, m;
-    batch_prefix(B, seg, before, m);
-    const uint64_t total = *M.total, cap = M.cap, seed = M.seed;
-    const int mode = M.mode;
-    const unsigned long long *stamp = M.stamp;
-    uint4 *res = M.data;
-    uint64_t cnt = B.counts[seg];
-    if (cnt > B.seg_cap) cnt = B.seg_cap;
-    const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < cnt; i0 += stride * kResUnroll) {
-        int64_t slot[kResUnroll];
-        unsigned long long owner[kResUnroll];
+// work items of memory k: (segment, x) pairs, enumerated CTA-stride by all CTAs of the grid
+template <class F>
+__device__ __forceinline__ void for_items(const MemSet &S, int k, F f) {
+    const uint64_t items = (uint64_t)S.m[k].B.n_seg * S.gx;
+    for (uint64_t w = blockIdx.x; w < items; w += gridDim.x) f((uint32_t)(w / S.gx), (uint32_t)(w % S.gx));
+}
+
+__global__ void __launch_bounds__(kBufThreads) insert_kernel(const MemSet S) {
+    uint64_t *ctrl = S.m[0].scratch;
+    uint64_t total[NFSP_MAX_INSERT_REQS];
 #pragma unroll
-        for (int u = 0; u < kResUnroll; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * stride;
-            slot[u] = i < cnt ? reservoir_slot(seed, total + before + i, cap, mode) : -1;
+    for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) total[k] = k < S.n ? *S.m[k].total : 0ull;
+    for (int k = blockIdx.x; k < S.n; k += gridDim.x) scan_counts(S.m[k]);
+    grid_sync(ctrl);
+    uint64_t res_max = 0;  // records of the largest reservoir batch: the number of stamp / write rounds
+#pragma unroll
+    for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
+        if (k < S.n && S.m[k].reservoir) {
+            const uint64_t m = __ldcg(S.m[k].scratch + kScratchHead + S.m[k].B.n_seg);
+            res_max = m > res_max ? m : res_max;
         }
 #pragma unroll
-        for (int u = 0; u < kResUnroll; ++u) owner[u] = slot[u] >= 0 ? stamp[slot[u]] : 0ull;
+    for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
+        if (k < S.n && !S.m[k].reservoir)
+            for_items(S, k, [&](uint32_t seg, uint32_t x) { ring_item(S.m[k], total[k], seg, x, S.gx); });
+    for (uint64_t lo = 0; lo < res_max; lo += S.chunk) {
 #pragma unroll
-        for (int u = 0; u < kResUnroll; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * stride;
-            if (slot[u] >= 0 && owner[u] == (unsigned long long)(total + before + i + 1u)) res[slot[u]] = src[i];
-        }
+        for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
+            if (k < S.n && S.m[k].reservoir)
+                for_items(S, k, [&](uint32_t seg, uint32_t x) { reservoir_item<false>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk); });
+        grid_sync(ctrl);
+#pragma unroll
+        for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
+            if (k < S.n && S.m[k].reservoir)
+                for_items(S, k, [&](uint32_t seg, uint32_t x) { reservoir_item<true>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk); });
     }
+    // commit: total += records of the batch, staged counts cleared for the next rollout.  Nobody reads the counts after
+    // the first barrier or the totals after the kernel's first instructions, so no further barrier is needed.
+#pragma unroll
+    for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
+        if (k < S.n && (uint32_t)k % gridDim.x == blockIdx.x) {
+            const Mem &M = S.m[k];
+            for (uint32_t s = threadIdx.x; s < M.B.n_seg; s += blockDim.x) M.B.counts[s] = 0u;
+            if (threadIdx.x == 0) *M.total = total[k] + __ldcg(M.scratch + kScratchHead + M.B.n_seg);
+        }
 }
 
 // ---- K5 ------------------------------------------------------------------------------------------
@@ -302,7 +358,7 @@ sample_gather_kernel(const SampleReqs R, int batch, int64_t *__restrict__ idx_ou
     float *o = R.out[m];
     for (int k = row0 + threadIdx.x; k < row1; k += blockDim.x) {
         if (idx_out) idx_out[(int64_t)m * batch + k] = slot[k];
-        if (o) s_rec[k] = slot[k] >= 0 ? mem[slot[k]] : make_uint4(0, 0, 0, 0);
+        if (o) s_rec[k] = slot[k] >= 0 ? mem[slot[k] * (R.is_ring[m] ? 1 : 2)] : make_uint4(0, 0, 0, 0);  // reservoir slots are 32 bytes
     }
     if (!o) return;  // positions only (the learner reads the packed records itself)
     __syncthreads();
@@ -341,98 +397,113 @@ gather_sl_kernel(const uint4 *__restrict__ res, const int64_t *__restrict__ idx,
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int row = e / 33, col = e - row * 33;
         const int64_t slot = idx[row];
-        expand_sl(slot >= 0 ? res[slot] : make_uint4(0, 0, 0, 0), row, col, s, a);
+        expand_sl(slot >= 0 ? res[2 * slot] : make_uint4(0, 0, 0, 0), row, col, s, a);  // 32-byte slots, the record first
     }
-}
-
-static dim3 insert_grid(int64_t seg_cap, int n_seg, int n_mems) {
-    int64_t g = (seg_cap + kBufThreads - 1) / kBufThreads;
-    const int64_t rows = (int64_t)n_seg * n_mems;
-    const int64_t lim = rows >= 148 * 8 ? 1 : (148 * 8 + rows - 1) / rows;  // about 8 CTAs per SM in total
-    if (g > lim) g = lim;
-    if (g < 1) g = 1;
-    return dim3((unsigned)g, (unsigned)n_seg, (unsigned)n_mems);
 }
 
 }  // namespace nfsp
 
 using namespace nfsp;
 
-// validates the requests and fills the kernels' argument; *seg_cap_max / *n_seg_max size the grid
-static int make_memset(const nfsp_insert_req *reqs, int n, bool reservoir, MemSet &S, int64_t *seg_cap_max, int *n_seg_max) {
+// validates the requests and fills the kernel's argument
+static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet &S, int64_t *seg_cap_max) {
     NFSP_CHECK_ARG(reqs && n >= 1 && n <= NFSP_MAX_INSERT_REQS, "1..%d memories per call", NFSP_MAX_INSERT_REQS);
     *seg_cap_max = 0;
-    *n_seg_max = 0;
+    int64_t rows = 0;
     for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) S.m[k] = Mem{};
     for (int k = 0; k < n; ++k) {
         const nfsp_insert_req &r = reqs[k];
         NFSP_CHECK_ARG(r.d_mem && r.d_total && r.cap > 0, "bad memory %d", k);
-        NFSP_CHECK_ARG(r.d_recs && r.d_counts, "null staged batch %d", k);
+        NFSP_CHECK_ARG(r.d_recs && r.d_counts && r.d_scratch, "null staged batch or scratch %d", k);
         NFSP_CHECK_ARG(r.n_segments >= 1 && r.n_segments <= 65535 && r.seg_cap >= 0, "bad segment geometry %d", k);
-        if (reservoir) {
-            NFSP_CHECK_ARG(r.d_stamp, "reservoir %d has no stamp array", k);
-            NFSP_CHECK_ARG(r.mode == 0 || r.mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
-        }
+        NFSP_CHECK_ARG(r.reservoir == 0 || r.reservoir == 1, "reservoir must be 0 (ring) or 1 (reservoir)");
+        NFSP_CHECK_ARG(want_kind < 0 || r.reservoir == want_kind, "memory %d is of the other kind", k);
+        if (r.reservoir) NFSP_CHECK_ARG(r.mode == 0 || r.mode == 1, "mode must be 0 (Algorithm R) or 1 (reference law)");
         S.m[k].data = (uint4 *)r.d_mem;
-        S.m[k].stamp = (unsigned long long *)r.d_stamp;
         S.m[k].cap = (uint64_t)r.cap;
         S.m[k].total = r.d_total;
+        S.m[k].scratch = r.d_scratch;
         S.m[k].B = Batch{(const uint4 *)r.d_recs, r.d_counts, (uint32_t)r.n_segments, (uint64_t)r.seg_cap};
         S.m[k].seed = r.seed;
         S.m[k].mode = r.mode;
+        S.m[k].reservoir = r.reservoir;
         if (r.seg_cap > *seg_cap_max) *seg_cap_max = r.seg_cap;
-        if (r.n_segments > *n_seg_max) *n_seg_max = r.n_segments;
+        rows += r.n_segments;
+    }
+    S.n = n;
+    // work items per segment: about 8 CTAs' worth per SM in total, never more than a segment has 256-record slices
+    int64_t g = (*seg_cap_max + kBufThreads - 1) / kBufThreads;
+    const int64_t lim = rows >= 148 * 8 ? 1 : (148 * 8 + rows - 1) / rows;
+    if (g > lim) g = lim;
+    if (g < 1) g = 1;
+    S.gx = (uint32_t)g;
+    S.chunk = kResChunk;
+    if (const char *e = getenv("NFSP_RES_CHUNK")) {  // tuning hook (profiles/run_buffers.py)
+        const long long v = atoll(e);
+        if (v >= 1024) S.chunk = (uint64_t)v;
     }
     return NFSP_OK;
+}
+
+// one cooperative launch: every CTA must be resident for the grid barriers
+static int launch_insert(MemSet &S, cudaStream_t st) {
+    int dev = 0, sms = 0, per_sm = 0;
+    NFSP_CUDA(cudaGetDevice(&dev));
+    NFSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NFSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel, kBufThreads, 0));
+    if (per_sm < 1) return set_error(NFSP_E_CUDA, "insert_kernel does not fit an SM");
+    if (per_sm > 8) per_sm = 8;
+    int64_t items = 0;
+    for (int k = 0; k < S.n; ++k) items += (int64_t)S.m[k].B.n_seg * S.gx;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (items < grid) grid = items;
+    if (grid < S.n) grid = S.n;
+    void *args[] = {(void *)&S};
+    NFSP_CUDA(cudaLaunchCooperativeKernel((const void *)insert_kernel, dim3((unsigned)grid), dim3(kBufThreads), args, 0, st));
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
+    MemSet S;
+    int64_t seg_cap;
+    const int rc = make_memset(reqs, n, -1, S, &seg_cap);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
+    return launch_insert(S, (cudaStream_t)stream);
 }
 
 extern "C" int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
     MemSet S;
     int64_t seg_cap;
-    int n_seg;
-    const int rc = make_memset(reqs, n, false, S, &seg_cap, &n_seg);
+    const int rc = make_memset(reqs, n, 0, S, &seg_cap);
     if (rc != NFSP_OK) return rc;
     if (seg_cap == 0) return NFSP_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    ring_insert_kernel<<<insert_grid(seg_cap, n_seg, n), kBufThreads, 0, st>>>(S);
-    NFSP_LAUNCH_CHECK();
-    commit_kernel<<<n, kBufThreads, 0, st>>>(S);
-    NFSP_LAUNCH_CHECK();
-    return NFSP_OK;
+    return launch_insert(S, (cudaStream_t)stream);
 }
 
 extern "C" int nfsp_reservoir_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
     MemSet S;
     int64_t seg_cap;
-    int n_seg;
-    const int rc = make_memset(reqs, n, true, S, &seg_cap, &n_seg);
+    const int rc = make_memset(reqs, n, 1, S, &seg_cap);
     if (rc != NFSP_OK) return rc;
     if (seg_cap == 0) return NFSP_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid = insert_grid(seg_cap, n_seg, n);
-    reservoir_stamp_kernel<<<grid, kBufThreads, 0, st>>>(S);
-    NFSP_LAUNCH_CHECK();
-    reservoir_write_kernel<<<grid, kBufThreads, 0, st>>>(S);
-    NFSP_LAUNCH_CHECK();
-    commit_kernel<<<n, kBufThreads, 0, st>>>(S);
-    NFSP_LAUNCH_CHECK();
-    return NFSP_OK;
+    return launch_insert(S, (cudaStream_t)stream);
 }
 
 extern "C" int nfsp_ring_insert(void *d_ring, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
-                                int n_segments, int64_t seg_cap, void *stream) {
+                                int n_segments, int64_t seg_cap, uint64_t *d_scratch, void *stream) {
     nfsp_insert_req r{};
     r.d_mem = d_ring; r.cap = cap; r.d_total = d_total; r.d_recs = d_recs; r.d_counts = d_counts;
-    r.n_segments = n_segments; r.seg_cap = seg_cap;
+    r.n_segments = n_segments; r.seg_cap = seg_cap; r.d_scratch = d_scratch;
     return nfsp_ring_insert_multi(&r, 1, stream);
 }
 
-extern "C" int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, uint64_t *d_stamp,
-                                     const void *d_recs, uint32_t *d_counts, int n_segments, int64_t seg_cap,
-                                     uint64_t seed, int mode, void *stream) {
+extern "C" int nfsp_reservoir_insert(void *d_res, int64_t cap, uint64_t *d_total, const void *d_recs, uint32_t *d_counts,
+                                     int n_segments, int64_t seg_cap, uint64_t seed, int mode, uint64_t *d_scratch,
+                                     void *stream) {
     nfsp_insert_req r{};
-    r.d_mem = d_res; r.cap = cap; r.d_total = d_total; r.d_stamp = d_stamp; r.d_recs = d_recs; r.d_counts = d_counts;
-    r.n_segments = n_segments; r.seg_cap = seg_cap; r.seed = seed; r.mode = mode;
+    r.d_mem = d_res; r.cap = cap; r.d_total = d_total; r.d_recs = d_recs; r.d_counts = d_counts;
+    r.n_segments = n_segments; r.seg_cap = seg_cap; r.seed = seed; r.mode = mode; r.d_scratch = d_scratch; r.reservoir = 1;
     return nfsp_reservoir_insert_multi(&r, 1, stream);
 }
 

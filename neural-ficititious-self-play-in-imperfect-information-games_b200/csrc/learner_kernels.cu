@@ -115,7 +115,8 @@ __device__ __forceinline__ void prefetch_rows(const LearnerArgs &A, int net, int
     const int player = net >> 1;
     const uint4 *mem = (net & 1) ? A.rl[player] : A.sl[player];
     const int64_t *idx = (net & 1) ? A.rl_idx[player] : A.sl_idx[player];
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) s_rec[r] = mem[idx[base + r]];
+    const int stride = (net & 1) ? 1 : 2;  // a reservoir slot is 32 bytes, the record first (buffer_kernels.cu)
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) s_rec[r] = mem[idx[base + r] * stride];
     __syncthreads();
 }
 __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &N, int net, int row0, int rows,
@@ -161,7 +162,7 @@ __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &
 #pragma unroll
             for (int i = 0; i < 30; ++i) gw1[i] += ((s >> i) & 1u) ? dh : 0.f;
         } else {
-            const uint4 rec = s_rec ? s_rec[row - s_base] : A.sl[player][A.sl_idx[player][row]];
+            const uint4 rec = s_rec ? s_rec[row - s_base] : A.sl[player][2 * A.sl_idx[player][row]];
             s = rec.x;
             const float ya = __uint_as_float(rec.y), yb = __uint_as_float(rec.z), yc = __uint_as_float(rec.w);
             const float h = W.hidden(s);

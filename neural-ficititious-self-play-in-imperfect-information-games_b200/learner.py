@@ -56,6 +56,7 @@ class Learner:
         self.target = selfplay.weights[[1, 3]].clone().contiguous()   # agent.py:70-72
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
         self._peers = None
+        self.peer_check_every = 64  # updates between two reads of the peer-exchange error word when nothing else syncs
         if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
             # every rank must take the same path (a rank in the peer exchange and one in an NCCL all-reduce would wait
             # for each other forever): _setup_peers agrees on every phase collectively
@@ -77,8 +78,8 @@ class Learner:
         io = _lib.LearnerIO()
         io.d_weights, io.d_target_weights = (sp.weights if w_in is None else w_in).data_ptr(), self.target.data_ptr()
         for p in range(2):
-            io.d_rl[p], io.d_rl_idx[p] = sp.rl[p].data.data_ptr(), idx_rl[p].data_ptr()
-            io.d_sl[p], io.d_sl_idx[p] = sp.sl[p].data.data_ptr(), idx_sl[p].data_ptr()
+            io.d_rl[p], io.d_rl_idx[p] = sp.rl[p].store.data_ptr(), idx_rl[p].data_ptr()
+            io.d_sl[p], io.d_sl_idx[p] = sp.sl[p].store.data_ptr(), idx_sl[p].data_ptr()
         io.row0, io.rows, io.gamma, io.net_mask = row0, rows, self.gamma, mask
         io.terminal_bootstraps = int(self.terminal_bootstraps)
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
@@ -94,7 +95,7 @@ class Learner:
             for p in range(2):
                 for k, mem in ((0, sp.rl[p]), (1, sp.sl[p])):
                     r = reqs[2 * p + k]
-                    r.d_mem, r.d_total, r.cap = mem.data.data_ptr(), mem.total.data_ptr(), mem.capacity
+                    r.d_mem, r.d_total, r.cap = mem.store.data_ptr(), mem.total.data_ptr(), mem.capacity
                     r.seed, r.is_ring, r.d_out = mem.seed, int(mem.is_ring), None
             self._pos_reqs = reqs
         for p in range(2):
@@ -332,8 +333,8 @@ def _agent_fit(agent, net):
     idx = mem.sample_slots(agent.minibatch_size)[0]
     io = _lib.LearnerIO()
     io.d_weights, io.d_target_weights = w.data_ptr(), target.data_ptr()
-    io.d_rl[0], io.d_rl_idx[0] = agent._rl_memory.memory.data.data_ptr(), idx.data_ptr()
-    io.d_sl[0], io.d_sl_idx[0] = agent._sl_memory.memory.data.data_ptr(), idx.data_ptr()
+    io.d_rl[0], io.d_rl_idx[0] = agent._rl_memory.memory.store.data_ptr(), idx.data_ptr()
+    io.d_sl[0], io.d_sl_idx[0] = agent._sl_memory.memory.store.data_ptr(), idx.data_ptr()
     io.gamma, io.net_mask, io.terminal_bootstraps = agent.gamma, 1 << net, 0
     io.d_grad, io.d_stats = flat.data_ptr(), flat[GRAD:].data_ptr()
     lr = (C.c_float * 4)(agent.lr_ar, agent.lr_br_now, 0.0, 0.0)

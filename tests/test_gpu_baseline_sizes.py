@@ -197,7 +197,7 @@ def test_config4_memories_200k_ring_2m_reservoir_vs_oracle(nb):
     assert int(ring.total.item()) == total == steps * n_rl and ring.size() == count == cap_rl
     assert np.array_equal(raw16(got), raw16(data))
     data_s, count_s, total_s = orc.reservoir_insert_all(all_sl, cap_sl, res.seed)
-    got = res.data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+    got = np.ascontiguousarray(res.data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.SL_DT)
     assert int(res.total.item()) == total_s == steps * n_sl > cap_sl and res.size() == count_s == cap_sl
     assert np.array_equal(raw16(got), raw16(data_s))
     assert not np.array_equal(raw16(got), raw16(all_sl[:cap_sl]))  # replacement did happen
@@ -218,6 +218,32 @@ def test_config4_memories_200k_ring_2m_reservoir_vs_oracle(nb):
         assert np.array_equal(a_.cpu().numpy().view(np.uint32), rec["a"].view(np.uint32))
 
 
+def test_reservoir_batches_spanning_several_rounds_vs_oracle(nb):
+    """The insert kernel stamps and writes a batch in rounds of 2^21 records (so that a round's slots stay in L2); a later
+    round must override an earlier one exactly as the sequential adds do.  Three batches of 5 000 000 records (3 rounds
+    each, the first batch also crossing the end of the fill phase) into 3 000 000 slots, dense and as 64 ragged segments."""
+    cap, n, dev = 3_000_000, 5_000_000, torch.device("cuda")
+    rng = np.random.RandomState(9)
+    for n_seg in (1, 64):
+        res = nb.DeviceReservoir(cap, seed=31, device=dev, mode="R")
+        fed = []
+        for b in range(3):
+            recs = rng.randint(0, 1 << 30, size=(n, 4), dtype=np.uint32)
+            if n_seg == 1:
+                res.insert(torch.from_numpy(recs.view(np.int32)).to(dev), torch.tensor([n], dtype=torch.int32, device=dev))
+                fed.append(recs)
+            else:
+                seg_cap = n // n_seg
+                counts = rng.randint(seg_cap // 2, seg_cap + 1, n_seg).astype(np.int32)
+                res.insert(torch.from_numpy(recs[: n_seg * seg_cap].view(np.int32)).to(dev), torch.from_numpy(counts).to(dev), seg_cap)
+                fed.append(np.concatenate([recs[s * seg_cap: s * seg_cap + counts[s]] for s in range(n_seg)]))
+        allr = np.concatenate(fed).view(orc.SL_DT).reshape(-1)
+        data, count, total = orc.reservoir_insert_all(allr, cap, res.seed)
+        got = np.ascontiguousarray(res.data.cpu().numpy())
+        assert int(res.total.item()) == total == len(allr) and count == cap
+        assert np.array_equal(got.view(np.uint32), raw16(data)), n_seg
+
+
 def test_config4_memories_fed_by_the_rollout_vs_oracle(nb):
     """The same capacities fed by the fused rollout itself: 65 536 games, eta 0.1, one decision per step (about 65 k RL
     and 6.5 k SL records per step, the figures of configs[3]), 40 steps: the ring wraps 6 times.  Both players'
@@ -236,12 +262,12 @@ def test_config4_memories_fed_by_the_rollout_vs_oracle(nb):
     for p in range(2):
         recs = np.concatenate(rings[p])
         data, count, total = orc.ring_insert_all(recs, 200_000)
-        got = sp.rl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.RL_DT)
+        got = np.ascontiguousarray(sp.rl[p].data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.RL_DT)
         assert int(sp.rl[p].total.item()) == total > 5 * 200_000
         assert np.array_equal(raw16(got), raw16(data))
         recs = np.concatenate(ress[p])
         data, count, total = orc.reservoir_insert_all(recs, 2_000_000, sp.sl[p].seed)
-        got = sp.sl[p].data.cpu().numpy().view(np.uint8).reshape(-1).view(orc.SL_DT)
+        got = np.ascontiguousarray(sp.sl[p].data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.SL_DT)
         assert int(sp.sl[p].total.item()) == total and np.array_equal(raw16(got)[:count], raw16(data)[:count])
 
 
