@@ -98,6 +98,12 @@ int nfsp_fsm_image(uint32_t *out, int capacity_words);
 /* The same for the legacy rules (leduc/env.py README iteration; layout in csrc/legacy_fsm.cuh); *n_rows receives the
  * number of states a rollout can reach. */
 int nfsp_legacy_fsm_image(uint32_t *out, int capacity_words, int *n_rows);
+/* newenv.Env.do_action (newenv.py:131-178) called on its own, for callers that drive the pieces of step() themselves:
+ * raise->call coercions, history bit, round_raises, chips, last_action -- no snapshot, no round change, no showdown,
+ * `terminated` untouched.  d_actions int8[n]: np.argmax(action), 3 = all-zero vector (argmax 0 = fold), negative =
+ * no call for this game; d_players
+ * int8[n]; d_fold int8[n] or NULL receives the return value (1 = the player folded). */
+int nfsp_env_do_action(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int8_t *d_fold, void *stream);
 /* newenv.Env.get_state(p) (newenv.py:116-129), packed: player < 0 => per-game d_players.
  * Outputs (any may be NULL): d_s snapshot mask, d_s2 current observation mask, d_reward,
  * d_term, d_last_a (argmax of last_action[p], 3 if it was never set / all-zero). */

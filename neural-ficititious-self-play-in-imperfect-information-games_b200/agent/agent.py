@@ -76,7 +76,6 @@ class Agent:
         self.actions = np.zeros(3)
         self.played = 0
         self.reward = 0
-        self.test_reward = 0
         self.game_step = 0
 
     # ---- device plumbing
@@ -142,24 +141,6 @@ class Agent:
         return (e / e.sum()).reshape(1, 1, 3)
 
     # ---- agent.py:168-190 (evaluation hooks; their caller is commented out in main.py)
-    def play_test(self, policy, index, s2=None):
-        if s2 is None:
-            s, a, r, s2, t = self.env.get_state(index)
-            self.test_reward += r
-            if t:
-                return t
-        model = self.avg_strategy_model if policy == "a" else self.best_response_model
-        self.env.step(model.predict(np.reshape(s2, (1, 1, 30))), index)
-        return False
-
-    @property
-    def play_test_get_reward(self):
-        return self.test_reward
-
-    def play_test_init(self):
-        self.test_reward = 0
-
-    # ---- agent.py:192-207
     def update_strategy(self):
         self.update_avg_response_network()
         self.update_best_response_network()

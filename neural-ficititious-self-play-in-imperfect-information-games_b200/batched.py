@@ -144,6 +144,15 @@ class BatchedNfspEnv(_EnvBase):
                                   _stream(self.device)))
         return None if tr is None else decode_trace(tr)
 
+    def do_action(self, actions, players):
+        """newenv.Env.do_action (newenv.py:131-178) on its own: int8 codes as in step(), one player index per game.
+        Returns a bool tensor: the player folded."""
+        a = _as(actions, torch.int8, self.device, (self.n,))
+        p = _as(players, torch.int8, self.device, (self.n,))
+        fold = torch.empty(self.n, dtype=torch.int8, device=self.device)
+        check(lib().nfsp_env_do_action(self._h, _ptr(a), _ptr(p), _ptr(fold), _stream(self.device)))
+        return fold.bool()
+
     def get_state(self, player):
         """newenv.Env.get_state(p), packed: (s mask, last action id, reward, s2 mask, terminated)."""
         per_game = isinstance(player, (torch.Tensor, np.ndarray, list, tuple))

@@ -160,6 +160,23 @@ nfsp_observe_kernel(const uint64_t *__restrict__ state, int64_t n, const int8_t 
     }
 }
 
+// newenv.Env.do_action (newenv.py:131-178) called on its own: code 0..2 = np.argmax(action), 3 = the all-zero vector
+__global__ void __launch_bounds__(kThreads)
+nfsp_do_action_kernel(uint64_t *__restrict__ state, int64_t n, const int8_t *__restrict__ actions, const int8_t *__restrict__ players,
+                      int8_t *__restrict__ fold) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (actions[i] < 0) {  // negative code: this game makes no call
+            if (fold) fold[i] = 0;
+            continue;
+        }
+        NfspW g{state[i]};
+        const int code = actions[i] & 3;
+        const bool f = g.do_action(code == 3 ? 0 : code, code != 3, players[i] & 1);
+        state[i] = g.w;
+        if (fold) fold[i] = (int8_t)f;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 nfsp_export_kernel(const uint64_t *__restrict__ state, int64_t n, int32_t *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -455,6 +472,17 @@ extern "C" int nfsp_env_step(nfsp_env_t h, const int8_t *d_actions, const int8_t
                                                            d_actions, d_players, auto_reset, frac_u32(eta), nullptr);
     NFSP_LAUNCH_CHECK();
     h->step += (uint64_t)n_steps;
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_env_do_action(nfsp_env_t h, const int8_t *d_actions, const int8_t *d_players, int8_t *d_fold, void *stream) {
+    NFSP_CHECK_ARG(h != nullptr && d_actions != nullptr && d_players != nullptr, "null argument");
+    NFSP_CHECK_ARG(h->rules == NFSP_RULES_NFSP, "do_action is a method of leduc.newenv.Env (NFSP rules)");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
+    nfsp_do_action_kernel<<<grid_for(h->n, kThreads, h->sm_count, 8), kThreads, 0, (cudaStream_t)stream>>>(h->d_state, h->n, d_actions,
+                                                                                                        d_players, d_fold);
+    NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }
 

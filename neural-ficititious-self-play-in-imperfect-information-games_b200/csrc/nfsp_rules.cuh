@@ -140,6 +140,35 @@ struct NfspW {
         return av;
     }
 
+    // newenv.py:131-178 ALONE, as a caller of the bare method sees it: the coercions, the history bit, round_raises,
+    // the chips and last_action -- no snapshot, no round change, no showdown, and `terminated` is neither read nor set
+    // (step() does that with the return value).  Returns true for a fold.  A fold leaves no trace but last_action (the
+    // reference appends 'Fold' to actions_done, which only game_or_round_has_terminated reads, and it answers falsy
+    // either way); a fourth action in a round (history[p][round][3]: IndexError in the reference) sets the anomaly bit.
+    __device__ __forceinline__ bool do_action(int raw, bool nonzero, int p) {
+        const uint32_t r = round(), kk = k();
+        w = (w & ~((3ull << (46 + 2 * p)) | (1ull << (50 + p)))) | ((uint64_t)raw << (46 + 2 * p)) |
+            ((uint64_t)nonzero << (50 + p));
+        const uint32_t h = hist();
+        const uint32_t rnd = (h | (h >> 12)) >> (6u * r);
+        const bool p_raised = ((h >> (12u * p + 6u * r)) & 0x2Au) != 0u;
+        int av = raw;
+        if (av == A_RAISE && p_raised) av = A_CALL;
+        if (av == A_RAISE && kk == 2u && (rnd & 1u) && (rnd & 8u)) av = A_CALL;
+        if (av == A_FOLD) return true;
+        if (kk == 3u) {
+            w |= 1ull << 62;
+            return false;
+        }
+        const bool prev_raise = kk > 0u && ((rnd >> (2u * (kk - 1u) + 1u)) & 1u);
+        uint32_t add = (av == A_CALL) ? (prev_raise ? 2u : 0u) : (prev_raise ? 4u : 2u);
+        if (r == 0u && kk == 0u) add += 1u;
+        w |= 1ull << (12u * p + 6u * r + 2u * kk + (av == A_RAISE ? 1u : 0u));
+        w += (uint64_t)add << (34 + 4 * p);
+        w = (w & ~(3ull << 32)) | ((uint64_t)(kk + 1u) << 32);
+        return false;
+    }
+
     // 12-byte trace record, word 3 (layout: DESIGN.md "trace record")
     __device__ __forceinline__ uint32_t trace_misc(int raw, int eff, bool started) const {
         return (uint32_t)raw | ((uint32_t)eff << 2) | (round() << 4) | (dealer() << 5) | (card(0) << 6) |

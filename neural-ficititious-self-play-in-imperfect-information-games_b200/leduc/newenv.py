@@ -91,7 +91,14 @@ class Env:
         self.last_action[idx, pl[live]] = a[live]  # newenv.py:136 runs only on a live hand
 
     def do_action(self, action, p_index):
-        raise NotImplementedError("do_action is fused into step() on the device (newenv.py:131-178); call step()")
+        """newenv.py:131-178 on its own (step() runs it fused with the rest on the device): the raise->call coercions,
+        the history bit, round_raises, the chips and last_action; returns True when the player folds.  Like the
+        reference's method it neither reads nor sets `terminated`, takes no snapshot and never changes the round."""
+        a = np.asarray(action, dtype=np.float64).reshape(self.n_games, 3)
+        pl = np.broadcast_to(np.asarray(p_index, np.int8), (self.n_games,)).copy()
+        fold = self.batched.do_action(action_code(a), pl).cpu().numpy()
+        self.last_action[np.arange(self.n_games), pl] = a  # newenv.py:136
+        return bool(fold[0]) if self.n_games == 1 else fold
 
     def game_or_round_has_terminated(self):
         """newenv.py:180-190 on the current round's actions; None (falsy) where the reference returns None."""

@@ -470,6 +470,51 @@ class ScriptedBufRandom:
         return [population[i] for i in idx]
 
 
+def gen_do_action(mods, n_hands=1200, seed=20261018):
+    """newenv.Env.do_action (newenv.py:131-178) called on its own: a few step() calls bring the hand somewhere (possibly
+    into round 1), then up to three bare do_action calls by arbitrary players; after every call the return value and
+    everything the method touches (history, round_raises, overall_raises, last_action)."""
+    rng = pyrandom.Random(seed)
+    newenv = mods["newenv"]
+    newenv.print = lambda *a, **k: None
+    N, C = n_hands, 6
+    g = dict(dealer=np.zeros(N, np.int8), cards=np.zeros((N, 3), np.int8), op=np.full((N, C), -1, np.int8),
+             player=np.zeros((N, C), np.int8), vec=np.zeros((N, C, 3), np.float32), ret=np.zeros((N, C), np.int8),
+             hist=np.zeros((N, C), np.uint32), round=np.zeros((N, C), np.int8), round_raises=np.zeros((N, C), np.int8),
+             bets=np.zeros((N, C, 2), np.float32), terminated=np.zeros((N, C), np.int8),
+             last_action=np.zeros((N, C, 2, 3), np.float32))
+    env = newenv.Env()
+    deals = [(a, b, c) for a in range(3) for b in range(3) for c in range(3) if not (a == b == c)]
+    for i in range(N):
+        deal, dealer = rng.choice(deals), rng.randrange(2)
+        with rr.ScriptedShuffle(lambda: list(deal)):
+            env.reset(dealer)
+        g["dealer"][i], g["cards"][i] = dealer, deal
+        n_steps = rng.randrange(0, 4)
+        folded = False
+        for c in range(C):
+            # a bare fold ends the hand for the caller, as it does for step() (the reference appends 'Fold' to actions_done,
+            # a state no later call is meant to see); a fourth action in a round is an IndexError in the reference
+            if env.terminated or env.round_raises > 2 or folded:
+                break
+            p = rng.randrange(2)
+            v = KIND_VECS[rng.choice("FCCRRRZ")][rng.randrange(2)]
+            if c < n_steps:  # ops: 0 = step(vec, p), 1 = do_action(vec, p)
+                g["op"][i, c] = 0
+                env.step(v.copy(), p)
+            else:
+                g["op"][i, c] = 1
+                g["ret"][i, c] = int(bool(env.do_action(v.copy(), p)))
+                folded = bool(g["ret"][i, c])
+            g["player"][i, c], g["vec"][i, c] = p, v
+            g["hist"][i, c] = mask30(np.concatenate((env.history.flatten(), np.zeros(6)))) & 0xFFFFFF
+            g["round"][i, c], g["round_raises"][i, c] = env.round, env.round_raises
+            g["bets"][i, c], g["terminated"][i, c] = env.overall_raises, int(bool(env.terminated))
+            g["last_action"][i, c] = np.asarray(env.last_action, dtype=np.float64).reshape(2, 3)
+    np.savez_compressed(os.path.join(OUT, "do_action.npz"), **g)
+    print("do_action.npz: %d hands, %d bare do_action calls, %d folds" % (N, int((g["op"] == 1).sum()), int(g["ret"].sum())))
+
+
 def gen_buffers(mods, seed=7):
     rng = np.random.RandomState(seed)
     cap, n_add = 50, 173
@@ -554,6 +599,7 @@ def main():
     os.chdir(rr.REF_ROOT)
     mods = rr.load()
     gen_kat(mods)
+    gen_do_action(mods, n_hands=2400)
     gen_buffers(mods)
     gen_legacy(mods)
     gen_fuzz(mods)

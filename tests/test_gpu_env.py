@@ -88,6 +88,48 @@ def test_nfsp_env_golden_call_order_fuzz(nb, golden_dir):
         assert np.array_equal(rr[gs], g["gs_r"][gs, c])
 
 
+def test_nfsp_do_action_alone_golden(nb, golden_dir):
+    """newenv.Env.do_action (newenv.py:131-178) called on its own, against the reference's method: 2 400 hands brought
+    somewhere by step() calls, then bare do_action calls by arbitrary players (a hand ends with its first fold) -- return value, history, round_raises,
+    chips, `terminated` untouched, last_action -- and the single-game drop-in class on the first hands."""
+    g = load(golden_dir, "do_action.npz")
+    N, C = g["op"].shape
+    from nfsp_b200.leduc.newenv import Env, action_code
+
+    env = nb.BatchedNfspEnv(N, seed=1)
+    env.set_hands(g["dealer"], g["cards"])
+    n_calls = 0
+    for c in range(C):
+        op, pl = g["op"][:, c], g["player"][:, c].astype(np.int8)
+        code = action_code(g["vec"][:, c])
+        env.step(np.where(op == 0, code, 4).astype(np.int8)[None], pl[None], n_steps=1, auto_reset=False)
+        fold = env.do_action(np.where(op == 1, code, -1).astype(np.int8), pl).cpu().numpy()
+        e = _np(env.export())
+        live, bare = op >= 0, op == 1
+        n_calls += int(bare.sum())
+        assert np.array_equal(fold[bare], g["ret"][bare, c].astype(bool)), c
+        assert not fold[~bare].any()
+        assert np.array_equal(e["hist"][live].view(np.uint32), g["hist"][live, c]), c
+        assert np.array_equal(e["round"][live], g["round"][live, c]) and np.array_equal(e["k"][live], g["round_raises"][live, c])
+        assert np.array_equal(e["bets0"][live], (2 * g["bets"][live, c, 0]).astype(np.int32))
+        assert np.array_equal(e["bets1"][live], (2 * g["bets"][live, c, 1]).astype(np.int32))
+        assert np.array_equal(e["terminated"][live], g["terminated"][live, c]) and not e["anomaly"][live].any()
+        for q in (0, 1):  # last_action[q] (newenv.py:136): its argmax and whether it is the zero vector
+            la = g["last_action"][live, c, q]
+            assert np.array_equal(e["last_a%d" % q][live], np.argmax(la, axis=1))
+            assert np.array_equal(e["nz%d" % q][live].astype(bool), (la != 0).any(axis=1))
+    assert n_calls == int((g["op"] == 1).sum()) > 2000 and int(g["ret"].sum()) > 500
+    for i in range(40):  # the reference-shaped class, one game at a time
+        one = Env(n_games=1, seed=1, config_path=None)
+        one.load_hand(int(g["dealer"][i]), g["cards"][i])
+        for c in range(C):
+            if g["op"][i, c] == 0:
+                one.step(g["vec"][i, c].reshape(1, 1, 3), int(g["player"][i, c]))
+            elif g["op"][i, c] == 1:
+                assert one.do_action(g["vec"][i, c].reshape(1, 1, 3), int(g["player"][i, c])) is bool(g["ret"][i, c])
+                assert np.array_equal(one.last_action[0], g["last_action"][i, c])
+
+
 @pytest.mark.parametrize("n,steps", [(1, 40), (257, 33), (100_000, 24)])
 def test_nfsp_env_seeded_rollout_vs_oracle(nb, n, steps):
     """Philox deals + uniform-random actions + auto re-deal: trace planes bit-exact vs the oracle."""
