@@ -311,13 +311,14 @@ int nfsp_learner_fit(const nfsp_learner_io *io, int minibatch, int fit_batch, in
 /* The same fit when several GPUs of one box train together (SURVEY 8e, C1 + C2): the all-reduce of every SGD step runs
  * INSIDE the kernel over peer memory (NVLink).  Each rank owns an exchange buffer of NFSP_PEER_BUF_FLOATS floats, zeroed
  * once, that every other rank can address (CUDA IPC / torch symmetric memory); d_buf[r] is rank r's buffer as THIS
- * process sees it.  Per step a rank publishes its mean gradients and statistics in its own buffer, release-stores the
- * step's epoch into every peer's flag words, waits for the peers' flags and sums all buffers in rank order -- so the
- * weights stay bit-identical on every rank.  epoch0 = SGD steps exchanged through these buffers so far (the same on all
- * ranks; add the steps of this call afterwards).  *d_err becomes 1 if a peer did not answer within ~2 s (the kernel then
- * carries on instead of hanging the GPU; the result is invalid).  Every rank must make the same call. */
+ * process sees it.  Per step a rank pushes its mean gradients and statistics as 8-byte {value, epoch} words into its
+ * slot of EVERY rank's buffer and polls its own buffer until all slots carry the step's epoch (no flags, no fences, no
+ * round trip), then sums them in rank order -- so the weights stay bit-identical on every rank.  epoch0 = SGD steps
+ * exchanged through these buffers so far (the same on all ranks; add the steps of this call afterwards).  *d_err becomes
+ * 1 if a peer did not answer within ~2 s (the kernel then gives up on that net instead of hanging the GPU and writes NaN
+ * weights for it: the result is invalid and visibly so).  Every rank must make the same call. */
 #define NFSP_MAX_PEERS 8
-#define NFSP_PEER_BUF_FLOATS 17536
+#define NFSP_PEER_BUF_FLOATS 279552 /* 2 parities x 4 nets x NFSP_MAX_PEERS senders x 2184 words of 8 bytes */
 typedef struct {
     int32_t world, rank;
     void *d_buf[NFSP_MAX_PEERS];

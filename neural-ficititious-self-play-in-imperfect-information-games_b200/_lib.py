@@ -47,7 +47,7 @@ class InsertReq(C.Structure):
 INSERT_SCRATCH_WORDS, RESERVOIR_SLOT_BYTES = 4, 32  # NFSP_INSERT_SCRATCH_WORDS, NFSP_RESERVOIR_SLOT_BYTES
 
 
-MAX_PEERS, PEER_BUF_FLOATS = 8, 17536  # NFSP_MAX_PEERS, NFSP_PEER_BUF_FLOATS
+MAX_PEERS, PEER_BUF_FLOATS = 8, 279552  # NFSP_MAX_PEERS, NFSP_PEER_BUF_FLOATS
 
 
 class Peers(C.Structure):

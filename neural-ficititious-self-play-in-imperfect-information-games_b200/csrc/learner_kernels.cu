@@ -267,17 +267,37 @@ struct FitArgs {
     uint32_t *err;       // set to 1 if a peer did not answer in time
 };
 
-// exchange buffer of one rank, in floats: two parities x four nets x a slot of kPeerSlot floats (2179 mean gradients, then
-// loss sum, exploitability sum, rows), then world x 4 epoch flags written BY the peers
-constexpr int kPeerSlot = 2184, kPeerFlagOff = 2 * 4 * kPeerSlot;
-static_assert(kPeerFlagOff + NFSP_MAX_PEERS * 4 <= NFSP_PEER_BUF_FLOATS, "exchange buffer too small");
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Exchange buffer of one rank (the RECEIVER owns it): two parities x four nets x one slot per sending rank of kPeerSlot
+// 8-byte words {value, epoch} -- 2179 mean gradients, then loss sum, exploitability sum, rows.  A sender PUSHES its values
+// into the slot it has in every rank's buffer (its own included); a receiver polls its own memory until a word carries
+// the step's epoch.  The 8-byte store is atomic, so a word is either the old epoch's or complete: no flags, no fences,
+// no round trip (NCCL's LL protocol).  Round 1 published into the sender's buffer, fenced at system scope, flagged the
+// peers and had them read the values back over NVLink: ~15 us per SGD step at 8 GPUs.
+constexpr int kPeerSlot = 2184;
+static_assert(2 * 4 * NFSP_MAX_PEERS * kPeerSlot * 2 <= NFSP_PEER_BUF_FLOATS, "exchange buffer too small");
+__device__ __forceinline__ size_t ll_index(uint32_t parity, int net, int src, int e) {
+    return ((size_t)((parity * 4u + (uint32_t)net) * NFSP_MAX_PEERS + (uint32_t)src)) * kPeerSlot + (size_t)e;
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ll_store(float *buf, size_t idx, float v, uint32_t epoch) {
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2 *>(buf) + idx), "r"(__float_as_uint(v)),
+                 "r"(epoch)
+                 : "memory");
+}
+// spins until the word carries `epoch`; gives up after ~2 s (a peer is gone; never hang the GPU) and reports it in *lost
+__device__ __forceinline__ float ll_wait(const float *buf, size_t idx, uint32_t epoch, int *lost) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(buf) + idx;
+    uint32_t v, ep;
+    long long t0 = 0;
+    for (int spin = 0;; ++spin) {
+        asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(ep) : "l"(p) : "memory");
+        if (ep == epoch) break;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && clock64() - t0 > 4000000000ll) {
+            *lost = 1;
+            break;
+        }
+    }
+    return __uint_as_float(v);
 }
 __device__ __forceinline__ float ld_volatile_f32(const float *p) {
     float v;
@@ -454,12 +474,14 @@ learner_fit_rows_kernel(const FitArgs F) {
         // all ranks' buffers, read over NVLink in rank order: the all-reduce of the step, inside the kernel.
         const float inv_rows = 1.0f / (float)rows;
         const bool peers = F.world > 1;
-        const uint32_t epoch = F.epoch0 + (uint32_t)k + 1u;
-        const int slot = ((int)(epoch & 1u) * 4 + net) * kPeerSlot;
-        float *mine = peers ? F.peer[F.rank] + slot : nullptr;
+        const uint32_t epoch = F.epoch0 + (uint32_t)k + 1u, parity = epoch & 1u;
         auto apply = [&](int e, float g) {
-            if (peers) mine[e] = g * inv_rows;
-            else S.w[e] -= lr * 1.0f * (g * inv_rows);
+            if (peers) {
+                const float v = g * inv_rows;
+                for (int r = 0; r < F.world; ++r) ll_store(F.peer[r], ll_index(parity, net, F.rank, e), v, epoch);
+            } else {
+                S.w[e] -= lr * 1.0f * (g * inv_rows);
+            }
         };
         // W1: warp i owns input i and both halves of the hidden units.  Only ~30 % of the input bits are set: the rows
         // that have bit i come from one ballot (lane r tests row r) and only those are added, in row order -- adding the
@@ -498,55 +520,50 @@ learner_fit_rows_kernel(const FitArgs F) {
             float ls = 0.f, ex = 0.f;
             for (int r = 0; r < rows; ++r) { ls += S.loss[r]; ex += S.expl[r]; }
             if (peers) {
-                mine[2180] = ls; mine[2181] = ex; mine[2182] = (float)rows;
+                for (int r = 0; r < F.world; ++r) {
+                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2180), ls, epoch);
+                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2181), ex, epoch);
+                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2182), (float)rows, epoch);
+                }
             } else {
                 A.stats[4 + net] = ls;
                 if (is_br) { A.stats[player] = ex; A.stats[2 + player] = (float)rows; }
             }
         }
         if (peers) {
-            // this rank's slot must be complete before any peer sees the flag: the CTA barrier orders every thread's
-            // stores before the publishing threads, whose system-scope fence + release store make them visible
-            // (cumulativity) -- one fence per peer instead of one per thread
+            // every thread of this CTA has read S.w for this step's gradients: the update may begin.  Each thread sums its
+            // elements over the ranks' slots IN RANK ORDER as they arrive -- the same sum, and with it bit-identical
+            // weights, on every rank
             __syncthreads();
-            const int t = threadIdx.x;
-            if (t < F.world && t != F.rank) {
-                __threadfence_system();
-                st_release_sys(reinterpret_cast<uint32_t *>(F.peer[t] + kPeerFlagOff) + F.rank * 4 + net, epoch);
-                const uint32_t *flag = reinterpret_cast<const uint32_t *>(F.peer[F.rank] + kPeerFlagOff) + t * 4 + net;
-                const long long t0 = clock64();
-                while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
-                    if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; never hang the GPU
-                        *F.err = 1u;
-                        s_peer_lost = 1;
-                        break;
-                    }
-                    __nanosleep(64);
-                }
-            }
-            __syncthreads();
-            if (s_peer_lost) {
-                // a slot of a silent peer may be stale or half written: summing it would make the replicas differ
-                // silently.  Give up on this net instead: no further steps, NaN weights out (nobody can mistake them for a
-                // result), the error word set for Learner.check_peers()
-                for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) S.w[e] = __int_as_float(0x7FC00000);
-                break;
-            }
+            const float *mybuf = F.peer[F.rank];
             const float scale = 1.0f / (float)F.world;
+            int lost = 0;
             for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) {
                 float g = 0.f;
-                for (int r = 0; r < F.world; ++r) g += ld_volatile_f32(F.peer[r] + slot + e);
+                for (int r = 0; r < F.world; ++r) g += ll_wait(mybuf, ll_index(parity, net, r, e), epoch, &lost);
                 S.w[e] -= lr * scale * g;
             }
             if (k == 0 && threadIdx.x == 0) {
                 float ls = 0.f, ex = 0.f, rw = 0.f;
                 for (int r = 0; r < F.world; ++r) {
-                    ls += ld_volatile_f32(F.peer[r] + slot + 2180);
-                    ex += ld_volatile_f32(F.peer[r] + slot + 2181);
-                    rw += ld_volatile_f32(F.peer[r] + slot + 2182);
+                    ls += ll_wait(mybuf, ll_index(parity, net, r, 2180), epoch, &lost);
+                    ex += ll_wait(mybuf, ll_index(parity, net, r, 2181), epoch, &lost);
+                    rw += ll_wait(mybuf, ll_index(parity, net, r, 2182), epoch, &lost);
                 }
                 A.stats[4 + net] = ls;
                 if (is_br) { A.stats[player] = ex; A.stats[2 + player] = rw; }
+            }
+            if (lost) {
+                *F.err = 1u;
+                s_peer_lost = 1;
+            }
+            __syncthreads();
+            if (s_peer_lost) {
+                // a silent peer's slot is stale: summing it would make the replicas differ silently.  Give up on this net
+                // instead: no further steps, NaN weights out (nobody can mistake them for a result), the error word set for
+                // Learner.check_peers()
+                for (int e = threadIdx.x; e < NFSP_NET_PARAMS; e += kRowThreads) S.w[e] = __int_as_float(0x7FC00000);
+                break;
             }
         }
         __syncthreads();

@@ -5,7 +5,7 @@
 tag=${1:-r01}
 out=gpurun_out
 mkdir -p $out
-K='regex:rollout_kernel|rollout_tc_kernel|nfsp_step|legacy_rollout_kernel|ring_insert_kernel|reservoir_stamp_kernel|reservoir_write_kernel'
+K='regex:rollout_kernel|nfsp_step|legacy_rollout_kernel|insert_kernel'
 python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_plain.json 2> $out/${tag}_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 3 --warmup 3 > $out/${tag}_bench_under_ncu.log 2>&1

@@ -15,7 +15,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "all"
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n, T = 1 << 20, 8
 if what in ("rollout", "all"):
-    sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T)
+    sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T, direct_rings=True)
     for _ in range(passes):
         sp.rollout(T)
     torch.cuda.synchronize()
