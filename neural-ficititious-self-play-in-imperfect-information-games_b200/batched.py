@@ -404,7 +404,10 @@ class SelfPlay:
         # player, game and step: 2 RL records (previous + terminal) and 1 SL record.
         blocks = (self.n + 31) // 32
         self.n_seg = 1
-        while not sorted_variant and self.n_seg * 2 <= min(blocks, 1024):
+        # with direct_rings the only staged records are the SL ones (1/13 of all): 16 cursors per player keep the atomics
+        # apart, and a batch of <= 32 segments spares the insert launch its prefix scan and one grid barrier
+        max_seg = 16 if self.direct_rings else 1024
+        while not sorted_variant and self.n_seg * 2 <= min(blocks, max_seg):
             self.n_seg *= 2
         per_seg = ((blocks + self.n_seg - 1) // self.n_seg) * 32   # games that can map to one segment
         self.cap_rl = 2 * per_seg * self.max_steps

@@ -48,9 +48,11 @@ __device__ __forceinline__ float pack_weights_value(const float *__restrict__ w,
 }
 
 // both images in one launch: pack = [batched-forward image (kPackFloats) | rollout table image (kTabImageFloats)]
+// ... followed by a plain copy of the four nets (what the tensor-core variants' images are built from, on demand)
 __global__ void pack_images_kernel(const float *__restrict__ w, float *__restrict__ pack) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kPackFloats + kTabImageFloats; e += gridDim.x * blockDim.x)
-        pack[e] = e < kPackFloats ? pack_weights_value(w, e) : pack_tables_value(w, e - kPackFloats);
+    constexpr int kImages = kPackFloats + kTabImageFloats;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kImages + 4 * NFSP_NET_PARAMS; e += gridDim.x * blockDim.x)
+        pack[e] = e < kPackFloats ? pack_weights_value(w, e) : (e < kImages ? pack_tables_value(w, e - kPackFloats) : w[e - kImages]);
 }
 
 // forward of one net on one observation mask; sw = packed image in shared memory.  The first layer is the sum of the
@@ -185,7 +187,8 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     if (!h->d_wpack) {
-        NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats)));
+        NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS)));
+        h->d_wcopy = h->d_wpack + kPackFloats + kTabImageFloats;
         NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
         NFSP_CUDA(cudaFuncSetAttribute(act_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackFloats * sizeof(float))));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
@@ -195,13 +198,24 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         const int rc = nfsp_rollout_sorted_configure();
         if (rc != NFSP_OK) return rc;
     }
-    pack_images_kernel<<<(kPackFloats + kTabImageFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
+    pack_images_kernel<<<(kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
     NFSP_LAUNCH_CHECK();
-    int rc = nfsp_pack_tc_image(h, d_weights, (cudaStream_t)stream);
-    if (rc != NFSP_OK) return rc;
-    rc = nfsp_tq_set_weights(h, d_weights, (cudaStream_t)stream);
-    if (rc != NFSP_OK) return rc;
+    h->tc_dirty = h->tq_dirty = true;
     h->has_weights = true;
+    return NFSP_OK;
+}
+
+int nfsp_ensure_tc_images(nfsp_env_t h, bool tq, cudaStream_t st) {
+    if (h->tc_dirty) {
+        const int rc = nfsp_pack_tc_image(h, h->d_wcopy, st);
+        if (rc != NFSP_OK) return rc;
+        h->tc_dirty = false;
+    }
+    if (tq && h->tq_dirty) {
+        const int rc = nfsp_tq_set_weights(h, h->d_wcopy, st);
+        if (rc != NFSP_OK) return rc;
+        h->tq_dirty = false;
+    }
     return NFSP_OK;
 }
 
@@ -284,6 +298,10 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         if (rc != NFSP_OK) return rc;
         h->step += (uint64_t)n_steps;
         return NFSP_OK;
+    }
+    if (variant == 2 || variant == 3) {
+        const int rc = nfsp_ensure_tc_images(h, variant == 3, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
     }
     if (variant == 3) {
         const int rc = nfsp_rollout_tq_launch(h, A, debug, io->reserve_sms, (cudaStream_t)stream);

@@ -429,11 +429,15 @@ using namespace nfsp;
 extern "C" int nfsp_act_forward_tc(nfsp_env_t h, const uint32_t *d_obs, const int8_t *d_net, int64_t n, float *d_out,
                                    void *stream) {
     NFSP_CHECK_ARG(h != nullptr && d_obs && d_net && d_out && n >= 0, "bad arguments");
-    if (!h->has_weights || !h->d_wtc_wide) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
+    if (!h->has_weights) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
     if (n == 0) return NFSP_OK;
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = nfsp_ensure_tc_images(h, false, st);
+        if (rc != NFSP_OK) return rc;
+    }
     const int64_t ctas = (n + kFwdThreads - 1) / kFwdThreads;
     const int grid = (int)(ctas < h->sm_count ? ctas : h->sm_count);
     act_forward_tc_kernel<<<grid, kFwdThreads, kTcSmemBytes, st>>>((const uint8_t *)h->d_wtc_wide, d_obs, d_net, n, d_out);

@@ -45,6 +45,7 @@ struct MemSet {
     int n;
     uint32_t gx;     // CTAs' worth of work items per segment
     uint64_t chunk;  // records per stamp / write round of the reservoirs
+    int small;       // every memory's batch has at most kSmallSegs segments
 };
 constexpr int kScratchHead = 2;
 constexpr uint64_t kResChunk = 1ull << 21;  // records per stamp / write round: the 64 MB of slots they touch stay in L2
@@ -106,10 +107,10 @@ __device__ __forceinline__ void scan_counts(const Mem &M) {
 constexpr int kRingUnroll = 4;
 // slot = ticket % cap; of a batch larger than the ring only the last `cap` records survive (the others
 // would be evicted by popleft(), replay_buffer.py:40).  Work item = (segment, x of gx): records x*256 + t, stride gx*256.
-__device__ __forceinline__ void ring_item(const Mem &M, uint64_t total, uint32_t seg, uint32_t x, uint32_t gx) {
+__device__ __forceinline__ void ring_item(const Mem &M, uint64_t total, uint32_t seg, uint32_t x, uint32_t gx, uint64_t before,
+                                          uint64_t cnt, uint64_t m) {
     const Batch &B = M.B;
-    const uint64_t *pre = M.scratch + kScratchHead;
-    const uint64_t before = __ldcg(pre + seg), cnt = __ldcg(pre + seg + 1) - before, m = __ldcg(pre + B.n_seg), cap = M.cap;
+    const uint64_t cap = M.cap;
     const uint64_t first = m > cap ? m - cap : 0;
     const uint4 *src = B.recs + (uint64_t)seg * B.seg_cap;
     uint4 *ring = M.data;
@@ -164,10 +165,8 @@ constexpr int kResUnroll = 4;
 
 template <bool kWrite>
 __device__ __forceinline__ void reservoir_item(const Mem &M, uint64_t total, uint32_t seg, uint32_t x, uint32_t gx, uint64_t lo,
-                                               uint64_t hi) {
+                                               uint64_t hi, uint64_t before, uint64_t cnt) {
     const Batch &B = M.B;
-    const uint64_t *pre = M.scratch + kScratchHead;
-    const uint64_t before = __ldcg(pre + seg), cnt = __ldcg(pre + seg + 1) - before;
     if (before >= hi || before + cnt <= lo) return;  // no record of this segment in the round [lo, hi)
     const uint64_t i_lo = lo > before ? lo - before : 0, i_hi = hi - before < cnt ? hi - before : cnt;
     const uint64_t cap = M.cap, seed = M.seed;
@@ -202,50 +201,94 @@ __device__ __forceinline__ void reservoir_item(const Mem &M, uint64_t total, uin
     }
 }
 
-// work items of memory k: (segment, x) pairs, enumerated CTA-stride by all CTAs of the grid
+// work items of memory k: (segment, x) pairs, enumerated CTA-stride by all CTAs of the grid; f(seg, x, before, cnt).
+// pre = the memory's exclusive prefix table (n_seg + 1 entries), in global or in shared memory
 template <class F>
-__device__ __forceinline__ void for_items(const MemSet &S, int k, F f) {
+__device__ __forceinline__ void for_items(const MemSet &S, int k, const uint64_t *pre, bool in_smem, F f) {
     const uint64_t items = (uint64_t)S.m[k].B.n_seg * S.gx;
-    for (uint64_t w = blockIdx.x; w < items; w += gridDim.x) f((uint32_t)(w / S.gx), (uint32_t)(w % S.gx));
+    for (uint64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const uint32_t seg = (uint32_t)(w / S.gx), x = (uint32_t)(w % S.gx);
+        // the table in global memory was written by another CTA before the grid barrier: read it past L1
+        const uint64_t before = in_smem ? pre[seg] : __ldcg(pre + seg), next = in_smem ? pre[seg + 1] : __ldcg(pre + seg + 1);
+        f(seg, x, before, next - before);
+    }
 }
 
-__global__ void __launch_bounds__(kBufThreads) insert_kernel(const MemSet S) {
+constexpr int kSmallSegs = 32;  // up to this many segments per memory every CTA scans the counts itself (one warp each)
+
+__global__ void __launch_bounds__(kBufThreads, 4) insert_kernel(const MemSet S) {
+    __shared__ uint64_t s_pre[NFSP_MAX_INSERT_REQS][kSmallSegs + 1];
     uint64_t *ctrl = S.m[0].scratch;
-    uint64_t total[NFSP_MAX_INSERT_REQS];
+    uint64_t total[NFSP_MAX_INSERT_REQS], m_all[NFSP_MAX_INSERT_REQS];
+    const uint64_t *pre[NFSP_MAX_INSERT_REQS];
+    const bool small = S.small != 0;
 #pragma unroll
     for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) total[k] = k < S.n ? *S.m[k].total : 0ull;
-    for (int k = blockIdx.x; k < S.n; k += gridDim.x) scan_counts(S.m[k]);
-    grid_sync(ctrl);
+    if (small) {  // few segments: every CTA scans the counts itself -- no scan CTA, no grid barrier before the first pass
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        if (warp < (uint32_t)S.n) {
+            const Mem &M = S.m[warp];
+            unsigned long long c = lane < M.B.n_seg ? (unsigned long long)__ldcg(M.B.counts + lane) : 0ull;
+            if (c > M.B.seg_cap) c = M.B.seg_cap;
+            unsigned long long incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            s_pre[warp][lane + 1] = incl;
+            if (lane == 0) s_pre[warp][0] = 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) {
+            pre[k] = s_pre[k];
+            m_all[k] = k < S.n ? s_pre[k][S.m[k].B.n_seg] : 0ull;
+        }
+    } else {
+        for (int k = blockIdx.x; k < S.n; k += gridDim.x) scan_counts(S.m[k]);
+        grid_sync(ctrl);
+#pragma unroll
+        for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k) {
+            pre[k] = k < S.n ? S.m[k].scratch + kScratchHead : nullptr;
+            m_all[k] = k < S.n ? __ldcg(pre[k] + S.m[k].B.n_seg) : 0ull;
+        }
+    }
     uint64_t res_max = 0;  // records of the largest reservoir batch: the number of stamp / write rounds
 #pragma unroll
     for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
-        if (k < S.n && S.m[k].reservoir) {
-            const uint64_t m = __ldcg(S.m[k].scratch + kScratchHead + S.m[k].B.n_seg);
-            res_max = m > res_max ? m : res_max;
-        }
+        if (k < S.n && S.m[k].reservoir) res_max = m_all[k] > res_max ? m_all[k] : res_max;
 #pragma unroll
     for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
         if (k < S.n && !S.m[k].reservoir)
-            for_items(S, k, [&](uint32_t seg, uint32_t x) { ring_item(S.m[k], total[k], seg, x, S.gx); });
+            for_items(S, k, pre[k], small, [&](uint32_t seg, uint32_t x, uint64_t before, uint64_t cnt) {
+                ring_item(S.m[k], total[k], seg, x, S.gx, before, cnt, m_all[k]);
+            });
     for (uint64_t lo = 0; lo < res_max; lo += S.chunk) {
 #pragma unroll
         for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
             if (k < S.n && S.m[k].reservoir)
-                for_items(S, k, [&](uint32_t seg, uint32_t x) { reservoir_item<false>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk); });
+                for_items(S, k, pre[k], small, [&](uint32_t seg, uint32_t x, uint64_t before, uint64_t cnt) {
+                    reservoir_item<false>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk, before, cnt);
+                });
         grid_sync(ctrl);
 #pragma unroll
         for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
             if (k < S.n && S.m[k].reservoir)
-                for_items(S, k, [&](uint32_t seg, uint32_t x) { reservoir_item<true>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk); });
+                for_items(S, k, pre[k], small, [&](uint32_t seg, uint32_t x, uint64_t before, uint64_t cnt) {
+                    reservoir_item<true>(S.m[k], total[k], seg, x, S.gx, lo, lo + S.chunk, before, cnt);
+                });
     }
-    // commit: total += records of the batch, staged counts cleared for the next rollout.  Nobody reads the counts after
-    // the first barrier or the totals after the kernel's first instructions, so no further barrier is needed.
+    // commit: total += records of the batch, staged counts cleared for the next rollout.  The totals are read in the
+    // kernel's first instructions and the counts before the first pass; with few segments a CTA could still be reading
+    // the counts when another one is done (no barrier so far if there is no reservoir), hence one more barrier there.
+    if (small && res_max == 0) grid_sync(ctrl);
 #pragma unroll
     for (int k = 0; k < NFSP_MAX_INSERT_REQS; ++k)
         if (k < S.n && (uint32_t)k % gridDim.x == blockIdx.x) {
             const Mem &M = S.m[k];
             for (uint32_t s = threadIdx.x; s < M.B.n_seg; s += blockDim.x) M.B.counts[s] = 0u;
-            if (threadIdx.x == 0) *M.total = total[k] + __ldcg(M.scratch + kScratchHead + M.B.n_seg);
+            if (threadIdx.x == 0) *M.total = total[k] + m_all[k];
         }
 }
 
@@ -437,6 +480,9 @@ static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet
     if (g > lim) g = lim;
     if (g < 1) g = 1;
     S.gx = (uint32_t)g;
+    S.small = 1;
+    for (int k = 0; k < n; ++k)
+        if (reqs[k].n_segments > 32) S.small = 0;
     S.chunk = kResChunk;
     if (const char *e = getenv("NFSP_RES_CHUNK")) {  // tuning hook (profiles/run_buffers.py)
         const long long v = atoll(e);

@@ -20,6 +20,10 @@ struct nfsp_env_s {
     uint32_t *d_work;    // dynamic work counter of the fused rollout
     void *d_wtc_wide;    // tensor-core operand image of layer 1, the four nets side by side along N (act_tc_kernels.cu)
     bool has_weights;
+    // the tensor-core variants' weight images are built from the handle's own copy of the nets (behind the packed images
+    // in d_wpack) the first time one of them runs after nfsp_act_set_weights: the default path pays for one pack launch
+    bool tc_dirty = false, tq_dirty = false;
+    const float *d_wcopy = nullptr;
     // warp-specialised tcgen05 rollout (rollout_tq.cu)
     int w2_slot = -1;         // this handle's slot of the constant-bank image of the second layers, -1 = none yet
     void *d_w2img = nullptr;  // device copy of that image
@@ -32,6 +36,8 @@ int nfsp_fsm_upload(nfsp_env_t h);
 
 // builds the tensor-core operand image of the acting nets (act_tc_kernels.cu)
 int nfsp_pack_tc_image(nfsp_env_t h, const float *d_weights, cudaStream_t st);
+// brings the lazily built images of the tensor-core variants up to date on `st` (act_kernels.cu)
+int nfsp_ensure_tc_images(nfsp_env_t h, bool tq, cudaStream_t st);
 // second-layer image of the warp-specialised rollout: constant-bank slot of the handle (rollout_tq.cu)
 int nfsp_tq_set_weights(nfsp_env_t h, const float *d_weights, cudaStream_t st);
 void nfsp_tq_release(nfsp_env_t h);
