@@ -501,22 +501,28 @@ def run_gpu(args):
         del spo
     # BASELINE configs[2] + configs[3] as stated: 65 536 parallel games, ring of 200 000 + reservoir of 2 000 000 records per
     # player, rollout(8) + the move of the records into the memories (a launch laps the ring: staged path) + 256-row sample
-    sp64 = nfsp_b200.SelfPlay(1 << 16, seed=SEED, device=dev, eta=ETA, epsilon=EPS, rl_capacity=200000,
-                              sl_capacity=2000000, max_steps_per_call=T_PER_CALL)
-    ms64, ms64s = 0.0, 0.0
-    for k in range(3 + args.steps):
-        a, b, c = ev(), ev(), ev()
-        a.record()
-        sp64.rollout(T_PER_CALL)
-        b.record()
-        sp64.sample_minibatches(BATCH)
-        c.record()
-        c.synchronize()
-        if k >= 3:
-            ms64 += a.elapsed_time(b)
-            ms64s += b.elapsed_time(c)
+    def time_64k(rl_cap, direct):
+        s64 = nfsp_b200.SelfPlay(1 << 16, seed=SEED, device=dev, eta=ETA, epsilon=EPS, rl_capacity=rl_cap,
+                                 sl_capacity=2000000, max_steps_per_call=T_PER_CALL, direct_rings=direct)
+        ms, ms_s = 0.0, 0.0
+        for k in range(3 + args.steps):
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            s64.rollout(T_PER_CALL)
+            b.record()
+            s64.sample_minibatches(BATCH)
+            c.record()
+            c.synchronize()
+            if k >= 3:
+                ms += a.elapsed_time(b)
+                ms_s += b.elapsed_time(c)
+        return ms, ms_s
+
+    ms64, ms64s = time_64k(200000, False)
     rate64 = (1 << 16) * T_PER_CALL * args.steps / (ms64 * 1e-3)
-    del sp64
+    # the same with rings one launch cannot lap (2 * 65536 * 8 <= 2^21): the rollout kernel writes them in place
+    ms64d, _ = time_64k(1 << 21, True)
+    rate64d = (1 << 16) * T_PER_CALL * args.steps / (ms64d * 1e-3)
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
@@ -577,7 +583,10 @@ def run_gpu(args):
          "frac_of_hbm_peak": env_rate * ENV_BYTES_PER_TRANSITION / 1e9 / hbm,
          "moved_frac_of_hbm_peak": env_rate * (12.0 + 16.0 / ENV_T_PER_CALL) / 1e9 / hbm},
         {"config": "BASELINE configs[2]+[3]: NFSP rollout, 65536 games, eta 0.1, ring 200000 + reservoir 2000000 per player, insert + 256-batch sample per step",
-         "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps, "sample_us": 1e3 * ms64s / args.steps},
+         "transitions_per_sec": rate64, "ms_per_step": ms64 / args.steps, "sample_us": 1e3 * ms64s / args.steps,
+         "note": "one launch of 8 decisions laps a 200000-record ring: staged records + insert launch"},
+        {"config": "the same 65536 games with rings of 2^21 records (a launch cannot lap them: RL records written in place)",
+         "transitions_per_sec": rate64d, "ms_per_step": ms64d / args.steps},
         {"config": "BASELINE configs[4] per GPU: the headline line", "transitions_per_sec": value / world},
     ]
     h2d = int(w_host.numel() * 4)

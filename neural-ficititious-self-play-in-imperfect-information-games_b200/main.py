@@ -37,11 +37,16 @@ def sampled_actions(stats, player):
 
 
 def train(sp: SelfPlay, learner: Learner, episodes: int, steps_per_call: int = 8, report_every: int = 100,
-          world: int = 1, log=print, true_exploitability: bool = True, pipelined: bool = False):
+          world: int = 1, log=print, true_exploitability: bool = True, pipelined: bool = False, updates_per_call: int = 1):
     """main.train (main.py:21-124).  Plays until `episodes` hands have finished over all games and ranks.
     Returns the list of reported rows (the reference's `plotter`, main.py:75, plus what it prints).
     pipelined: the learner's update runs beside the next rollout (learner.PipelinedTrainer: acting nets one update
-    behind, the learner's time hidden)."""
+    behind, the learner's time hidden).
+    updates_per_call: update_strategy() calls per rollout call.  The reference updates an agent every 128 of ITS decisions
+    (agent.py:153-154); a rollout call is n_games * steps_per_call / 2 decisions per agent, so the reference's cadence is
+    updates_per_call = n_games * steps_per_call / 256 (sequential loop only)."""
+    if pipelined and updates_per_call != 1:
+        raise ValueError("the pipelined trainer runs one update beside each rollout")
     rows, calls, t0 = [], 0, time.time()
     trainer = PipelinedTrainer(sp, learner) if pipelined else None
     while True:
@@ -49,6 +54,8 @@ def train(sp: SelfPlay, learner: Learner, episodes: int, steps_per_call: int = 8
         report = calls % report_every == 0 or calls == 1
         if trainer is None:
             sp.rollout(steps_per_call)            # main.py:27-67 for every game, T decisions each
+            for _ in range(updates_per_call - 1):
+                learner.update(sync=False, pack=False)
             st = learner.update(sync=report)      # agent.py:153-154 -> 192-194 -> 209-264; host reads only when reporting
         else:
             st = trainer.step(steps_per_call, sync=report)
@@ -87,6 +94,8 @@ def main(argv=None):
     ap.add_argument("--report-every", type=int, default=100)
     ap.add_argument("--no-true-exploitability", action="store_true")
     ap.add_argument("--pipelined", action="store_true", help="run the learner's update beside the next rollout")
+    ap.add_argument("--updates-per-call", type=int, default=1,
+                    help="update_strategy() calls per rollout call (the reference's cadence: games * steps / 256)")
     args = ap.parse_args(argv)
     cfg = load_config(args.config)
     rank, world, local = sharding.env_rank_world()
@@ -105,7 +114,8 @@ def main(argv=None):
     episodes = args.episodes if args.episodes is not None else cfg.getint("Common", "Episodes")
     rows = train(sp, learner, episodes, args.steps_per_call, args.report_every, world,
                  log=print if rank == 0 else (lambda *a, **k: None),
-                 true_exploitability=not args.no_true_exploitability, pipelined=args.pipelined)
+                 true_exploitability=not args.no_true_exploitability, pipelined=args.pipelined,
+                 updates_per_call=args.updates_per_call)
     if world > 1:
         dist.destroy_process_group()
     return rows
