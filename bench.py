@@ -536,10 +536,10 @@ def run_gpu(args):
     if os.path.exists(traffic_file):
         tf = json.load(open(traffic_file))
         roofline["traffic"] = tf.get("rollout_kernel_bytes_per_launch")
-        if args.variant != "tcgen05" and "rollout_kernel_ncu" in tf:
+        if args.variant in ("default", "cuda") and "rollout_kernel_ncu" in tf:
             # what really bounds the kernel (ncu, not measured in this run): each decision has to bring 2 x 256 B of
             # first-layer rows and 768 B of second-layer weights from shared memory into registers
-            roofline["limiter"] = "shared-memory register-fill bandwidth, not HBM"
+            roofline["limiter"] = "shared memory -> register bandwidth (LDS.128 instructions), not HBM"
             roofline["ncu"] = tf["rollout_kernel_ncu"]
     cpu, cpu_extra = None, {}
     if world == 1:
