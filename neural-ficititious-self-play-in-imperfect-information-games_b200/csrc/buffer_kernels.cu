@@ -484,10 +484,12 @@ static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet
     for (int k = 0; k < n; ++k)
         if (reqs[k].n_segments > 32) S.small = 0;
     S.chunk = kResChunk;
-    if (const char *e = getenv("NFSP_RES_CHUNK")) {  // tuning hook (profiles/run_buffers.py)
+#ifdef NFSP_TUNING_HOOKS  // profiles/run_buffers.py with a library built with -DNFSP_TUNING_HOOKS
+    if (const char *e = getenv("NFSP_RES_CHUNK")) {
         const long long v = atoll(e);
         if (v >= 1024) S.chunk = (uint64_t)v;
     }
+#endif
     return NFSP_OK;
 }
 
