@@ -64,6 +64,56 @@ def test_gradients_match_float64_oracle(nb):
     assert float(np.abs(flat[:GRAD]).max()) > 1e-4  # not vacuous
 
 
+def test_gradients_match_torch_autograd(nb):
+    """The same gradients against torch.autograd in float64 on the CPU: the backward pass is DERIVED by autograd from the
+    forward definition (Dense-relu-Dense with a relu head and the Huber loss of agent.py:91-99 averaged over the three
+    outputs as Keras does, resp. a softmax head with categorical cross-entropy), so nothing of the hand-written backward --
+    kernel or numpy restatement -- is shared."""
+    import torch.nn.functional as F
+
+    from nfsp_b200.learner import GRAD, Learner
+
+    sp = _filled_selfplay(nb)
+    L = Learner(sp, minibatch=128, gamma=0.95)
+    L.target = (sp.weights[[1, 3]] * 0.9 + 0.01).contiguous()
+    idx_rl = [sp.rl[p].sample_slots(128)[0] for p in range(2)]
+    idx_sl = [sp.sl[p].sample_slots(128)[0] for p in range(2)]
+    L.lr_br, L.lr_ar = [0.0, 0.0], 0.0
+    row0, rows = 32, 64
+    L._step(idx_rl, idx_sl, row0, rows, 0xF)
+    flat = L.flat.cpu().double()
+    W, T = sp.weights.cpu().double(), L.target.cpu().double()
+
+    def parts(w):
+        return w[:1920].reshape(30, 64), w[1920:1984], w[1984:2176].reshape(64, 3), w[2176:2179]
+
+    def bits(m):
+        return torch.from_numpy(((np.asarray(m, np.uint32)[:, None] >> np.arange(30)) & 1).astype(np.float64))
+
+    def net(w, x):
+        W1, b1, W2, b2 = parts(w)
+        return F.relu(x @ W1 + b1) @ W2 + b2
+
+    for p in range(2):
+        rl = np.ascontiguousarray(sp.rl[p].data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.RL_DT)[idx_rl[p].cpu().numpy()][row0:row0 + rows]
+        w = W[2 * p + 1].clone().requires_grad_(True)
+        q = F.relu(net(w, bits(rl["s"])))
+        with torch.no_grad():
+            qn = F.relu(net(T[p], bits(rl["s2"]))).max(1).values
+            y = torch.from_numpy(rl["r"].astype(np.float64)) + 0.95 * (1.0 - torch.from_numpy(rl["t"].astype(np.float64))) * qn
+        err = y - q[torch.arange(rows), torch.from_numpy(rl["a"].astype(np.int64))]
+        huber = torch.where(err.abs() > 1, err.abs() - 0.5, 0.5 * err * err)   # agent.py:91-99
+        (huber / 3.0).mean().backward()                                          # Keras: mean over the 3 outputs, mean over rows
+        got = flat[(2 * p + 1) * 2179:(2 * p + 2) * 2179]
+        assert float((got - w.grad).abs().max()) < 1e-5 and float(w.grad.abs().max()) > 1e-4
+        sl = np.ascontiguousarray(sp.sl[p].data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.SL_DT)[idx_sl[p].cpu().numpy()][row0:row0 + rows]
+        w = W[2 * p].clone().requires_grad_(True)
+        logp = F.log_softmax(net(w, bits(sl["s"])), dim=1)
+        (-(torch.from_numpy(sl["a"].astype(np.float64)) * logp).sum(1)).mean().backward()   # categorical cross-entropy, target as is
+        got = flat[(2 * p) * 2179:(2 * p + 1) * 2179]
+        assert float((got - w.grad).abs().max()) < 1e-5 and float(w.grad.abs().max()) > 1e-4
+
+
 def test_sgd_apply_and_net_mask(nb):
     from nfsp_b200.learner import GRAD, Learner
 
