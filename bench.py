@@ -384,11 +384,12 @@ def run_gpu(args):
     barrier()
     a, b = ev(), ev()
     a.record()
-    for _ in range(5):
-        lstats = learner.update()
+    for _ in range(10):  # device time of an update: nothing read back in between (as in the training loop)
+        learner.update(sync=False)
     b.record()
     b.synchronize()
-    learner_ms = sharding.max_over_ranks(a.elapsed_time(b) / 5, dev)
+    learner_ms = sharding.max_over_ranks(a.elapsed_time(b) / 10, dev)
+    lstats = learner.update()  # one synchronised update for the statistics
     # the full self-play iteration of BASELINE configs[4]: rollout(8) + memory inserts + update_strategy() of both agents
     # (with its all-reduces when world > 1), nothing read back between iterations
     barrier()
