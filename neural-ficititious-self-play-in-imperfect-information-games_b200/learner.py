@@ -73,13 +73,29 @@ class Learner:
         and PipelinedTrainer need.  The same on every rank (the peer set-up is collective)."""
         return self.fused and (_world() == 1 or self._peers is not None)
 
+    def _gather(self, idx_rl, idx_sl):
+        """Copies of the sampled records (4 x minibatch rows, 24 KB): once they exist the update no longer reads the
+        memories, so a rollout that writes the rings in place, or the next insert, may run beside the fit."""
+        sp, b = self.sp, self.minibatch
+        if not hasattr(self, "_gath"):
+            self._gath = ([torch.empty((b, 4), dtype=torch.int32, device=self.device) for _ in range(2)],
+                          [torch.empty((b, 8), dtype=torch.int32, device=self.device) for _ in range(2)],
+                          torch.arange(b, dtype=torch.int64, device=self.device))
+        g_rl, g_sl, rows = self._gath
+        for p in range(2):  # a slot of -1 (memory not filled yet) belongs to a net the mask leaves out: any row does
+            torch.index_select(sp.rl[p].store, 0, idx_rl[p].clamp(min=0), out=g_rl[p])
+            torch.index_select(sp.sl[p].store, 0, idx_sl[p].clamp(min=0), out=g_sl[p])
+        self._mems = (g_rl, g_sl)
+        return [rows, rows], [rows, rows]
+
     def _io(self, idx_rl, idx_sl, row0, rows, mask, w_in=None):
         sp = self.sp
         io = _lib.LearnerIO()
         io.d_weights, io.d_target_weights = (sp.weights if w_in is None else w_in).data_ptr(), self.target.data_ptr()
+        mem_rl, mem_sl = getattr(self, "_mems", None) or ([m.store for m in sp.rl], [m.store for m in sp.sl])
         for p in range(2):
-            io.d_rl[p], io.d_rl_idx[p] = sp.rl[p].store.data_ptr(), idx_rl[p].data_ptr()
-            io.d_sl[p], io.d_sl_idx[p] = sp.sl[p].store.data_ptr(), idx_sl[p].data_ptr()
+            io.d_rl[p], io.d_rl_idx[p] = mem_rl[p].data_ptr(), idx_rl[p].data_ptr()
+            io.d_sl[p], io.d_sl_idx[p] = mem_sl[p].data_ptr(), idx_sl[p].data_ptr()
         io.row0, io.rows, io.gamma, io.net_mask = row0, rows, self.gamma, mask
         io.terminal_bootstraps = int(self.terminal_bootstraps)
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
@@ -210,12 +226,14 @@ class Learner:
         self._all_ready = mask == 15
         return mask
 
-    def update(self, sync=True, weights_in=None, weights_out=None, pack=True):
+    def update(self, sync=True, weights_in=None, weights_out=None, pack=True, on_gathered=None):
         """update_strategy() of both agents.  Returns a dict of statistics; with sync=False nothing is read back
         from the device (the loss / exploitability-proxy entries are then the previous synchronised values).
         weights_in / weights_out (float32 [4, 2179] device tensors): train FROM / INTO these instead of the acting
         weights of the SelfPlay object, and with pack=False leave the acting nets alone -- what PipelinedTrainer needs
-        to run this update beside the next rollout.  Only the one-launch fit supports it."""
+        to run this update beside the next rollout.  Only the one-launch fit supports it.
+        on_gathered: a callable; the sampled records are first copied out of the memories and the callable is invoked
+        right after that copy is enqueued (PipelinedTrainer records an event there: from then on the memories may change)."""
         sp = self.sp
         mask = self._ready_mask()
         if (weights_in is not None or weights_out is not None) and not self.one_launch:
@@ -229,6 +247,10 @@ class Learner:
             if (mask >> (2 * p + 1)) & 1:
                 self.iteration[p] += 1          # agent.py:216
         idx_rl, idx_sl = self._sample_positions()
+        self._mems = None
+        if on_gathered is not None:
+            idx_rl, idx_sl = self._gather(idx_rl, idx_sl)
+            on_gathered()
         stats = None
         if self.fused and (_world() == 1 or self._peers is not None):
             # one launch for the 8 SGD steps; with peers the per-step all-reduce happens inside it over NVLink
@@ -279,8 +301,9 @@ class PipelinedTrainer:
     (every 128 decisions of a batch-1 game) -- and in exchange the learner's time (and, with several GPUs, its gradient
     exchange) disappears behind the rollout.  Mechanics: the fit trains from one weight tensor into another
     (two tensors, alternating), so the acting images can be rebuilt from W_j while update j reads it; the rollout's
-    persistent grid leaves `reserve_sms` SMs free (the fit is four CTAs that need an SM each); events order
-    memories-written -> update -> memories-written-again.  Deterministic: the same weights, memories and games as the
+    persistent grid leaves `reserve_sms` SMs free (the fit is four CTAs that need an SM each); the update first copies
+    its sampled records out of the memories (24 KB) and an event after that copy lets the next rollout -- which writes the
+    rings in place with direct_rings -- and the next insert go ahead while the fit runs.  Deterministic: the same weights, memories and games as the
     sequential loop run with that lag (tests/test_gpu_train.py)."""
 
     def __init__(self, selfplay, learner, reserve_sms=4):
@@ -291,6 +314,7 @@ class PipelinedTrainer:
         self.w = [selfplay.weights.clone(), selfplay.weights.clone()]  # W_j lives in w[j % 2]
         self.stream = torch.cuda.Stream(selfplay.device)
         self.flushed = torch.cuda.Event()
+        self.gathered = torch.cuda.Event()                             # update j has copied its sampled records
         self.updated = [torch.cuda.Event(), torch.cuda.Event()]        # update j records updated[j % 2]
         self.j = 0
 
@@ -301,14 +325,17 @@ class PipelinedTrainer:
         if j >= 2:
             main.wait_event(self.updated[j % 2])          # update j-2 wrote W_{j-1}
         sp.set_weights(self.w[(j - 1) % 2] if j >= 1 else self.w[0])   # acting nets: W_{j-1} (W_0 for the first two steps)
-        sp.rollout(n_steps, insert=False, reserve_sms=self.reserve_sms)
         if j >= 1:
-            main.wait_event(self.updated[(j - 1) % 2])    # update j-1 has read its records: the memories may change
+            # update j-1 works on a copy of its sampled records: once that copy exists the memories may change -- the
+            # rollout writes the rings in place with direct_rings, the insert launch writes the reservoirs (and the rings)
+            main.wait_event(self.gathered)
+        sp.rollout(n_steps, insert=False, reserve_sms=self.reserve_sms)
         sp.flush()
         self.flushed.record(main)
         self.stream.wait_event(self.flushed)
         with torch.cuda.stream(self.stream):
-            out = self.learner.update(sync=sync, weights_in=self.w[j % 2], weights_out=self.w[(j + 1) % 2], pack=False)
+            out = self.learner.update(sync=sync, weights_in=self.w[j % 2], weights_out=self.w[(j + 1) % 2], pack=False,
+                                      on_gathered=lambda: self.gathered.record(self.stream))
             self.updated[j % 2].record(self.stream)
         self.j = j + 1
         return out

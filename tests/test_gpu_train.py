@@ -118,3 +118,25 @@ def test_pipelined_trainer_equals_the_sequential_loop_run_with_one_update_of_lag
         assert int(a.rl[p].total.item()) == int(b.rl[p].total.item()) and torch.equal(a.rl[p].data, b.rl[p].data)
         assert int(a.sl[p].total.item()) == int(b.sl[p].total.item()) and torch.equal(a.sl[p].data, b.sl[p].data)
     assert La.iteration == Lb.iteration and abs(a.epsilon - b.epsilon) < 1e-15
+
+
+def test_pipelined_trainer_with_direct_rings(nb):
+    """The production combination of bench.py: the rollout writes the rings in place while the previous update is still
+    running.  The update works on a copy of its sampled records taken before the rollout may start (the `gathered`
+    event), so nothing it reads can change under it: nets stay finite and move, every record is accounted for."""
+    from nfsp_b200.learner import Learner, PipelinedTrainer
+
+    sp = nb.SelfPlay(8192, seed=3, eta=0.3, epsilon=0.2, rl_capacity=1 << 18, sl_capacity=1 << 16, max_steps_per_call=8,
+                     direct_rings=True)
+    for _ in range(3):
+        sp.rollout(8)
+    w0 = sp.weights.clone()
+    T = PipelinedTrainer(sp, Learner(sp, cfg=nb.load_config(None)))
+    for _ in range(12):
+        assert T.step(8)["trained"] == 0xF
+    w = T.finish()
+    torch.cuda.synchronize()
+    st = sp.read_stats()
+    assert torch.isfinite(w).all() and not torch.equal(w, w0)
+    assert st["transitions"] == 15 * 8 * 8192 and st["dropped"] == 0
+    assert int(sp.counts.sum().item()) == 0 and all(int(sp.rl[p].total.item()) > 8192 for p in range(2))
