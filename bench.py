@@ -341,9 +341,9 @@ def run_gpu(args):
             flush_buf.zero_()  # L2 flush, outside the timed events
             a, b, c = ev(), ev(), ev()
             a.record()
-            if e2e:
-                sp.set_weights(w_host)  # pinned host -> device copy inside, then the kernels' weight images are rebuilt
-            sp.rollout(T_PER_CALL, insert=False)
+            # e2e: pinned host -> device copy of the four nets and the rebuild of the kernels' weight image, in the same
+            # library call that launches the rollout
+            sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None)
             b.record()
             sp.flush()
             if e2e:  # the learner's four minibatches and the counters come back to the host: one slab, one copy each

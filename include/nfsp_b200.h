@@ -196,6 +196,10 @@ typedef struct {
  * with auto re-deal.  Records are appended to the segmented staging arrays with warp-aggregated
  * atomics; move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
 int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io, void *stream);
+/* The learner -> actor hand-over and the rollout in one call (one trip through the binding instead of two at the head of
+ * every step): nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream) followed by nfsp_rollout(...). */
+int nfsp_rollout_with_weights(nfsp_env_t h, const float *h_weights, float *d_weights, int n_steps, double eta, double epsilon,
+                              const nfsp_rollout_io *io, void *stream);
 /* Tuning of variant 3: SM cycles a partly filled tile of an average-policy / a best-response net may wait for more rows
  * before its MMAs are issued anyway (defaults 1500 / 700). */
 int nfsp_rollout_tune(nfsp_env_t h, int patience_avg, int patience_br);
@@ -269,6 +273,9 @@ typedef struct {
     uint64_t seed, call_idx;
     int32_t is_ring;
     float *d_out;
+    void *d_rec_out;          /* or NULL: packed copies of the sampled slots, row k at the memory's slot size (16 bytes for a
+                                 ring, 32 for a reservoir, the record first) -- a snapshot the learner kernels can read in
+                                 place of the memory (slots 0 .. batch-1) while the memory itself moves on */
 } nfsp_sample_req;
 int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, int batch, int64_t *d_idx, uint32_t *d_n_out,
                             void *stream);

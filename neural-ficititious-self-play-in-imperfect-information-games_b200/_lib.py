@@ -25,7 +25,7 @@ SYMBOLS = [
     "nfsp_legacy_reset", "nfsp_legacy_set_hands", "nfsp_legacy_step", "nfsp_legacy_get_new_state",
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
-    "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_tune", "nfsp_rollout_profile",
+    "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_with_weights", "nfsp_rollout_tune", "nfsp_rollout_profile",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_insert_multi", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
 ]
@@ -57,7 +57,7 @@ class Peers(C.Structure):
 
 class SampleReq(C.Structure):
     _fields_ = [("d_mem", C.c_void_p), ("d_total", C.c_void_p), ("cap", C.c_int64), ("seed", C.c_uint64),
-                ("call_idx", C.c_uint64), ("is_ring", C.c_int32), ("d_out", C.c_void_p)]
+                ("call_idx", C.c_uint64), ("is_ring", C.c_int32), ("d_out", C.c_void_p), ("d_rec_out", C.c_void_p)]
 
 
 class LearnerIO(C.Structure):
@@ -123,6 +123,7 @@ def lib():
     L.nfsp_act_forward.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_act_forward_tc.argtypes = [vp, vp, i8p, C.c_int64, vp, vp]
     L.nfsp_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
+    L.nfsp_rollout_with_weights.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_double, C.POINTER(RolloutIO), vp]
     L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
     L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp, vp]
     L.nfsp_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]

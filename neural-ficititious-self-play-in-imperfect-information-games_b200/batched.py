@@ -447,11 +447,13 @@ class SelfPlay:
 
     VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4}
 
-    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0):
+    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None):
         """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
         net), "tcgen05" / "tcgen05_ws" (first layer as tensor-core tiles with the accumulator in TMEM) or None =
         self.variant.  reserve_sms: SMs the persistent rollout grid
-        leaves to kernels of other streams (the learner beside it, PipelinedTrainer)."""
+        leaves to kernels of other streams (the learner beside it, PipelinedTrainer).  weights_host: a pinned float32
+        [4, 2179] host tensor with new acting nets -- copied to the device and packed by the same library call that launches
+        the rollout (`set_weights(host tensor)` + `rollout()` in one trip through the binding)."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
         want_debug = debug or forced_vec is not None
@@ -482,7 +484,18 @@ class SelfPlay:
             io.d_trace, io.d_vec = tr.data_ptr(), vec.data_ptr()
             io.d_forced_vec = None if fv is None else fv.data_ptr()
             dbg = (tr, vec, fv)
-        check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilon, C.byref(io), _stream(self.device)))
+        if weights_host is not None and not getattr(self, "_own_weights", False):
+            self.set_weights(weights_host)  # first hand-over: the device tensor becomes this object's own
+            weights_host = None
+        if weights_host is not None:
+            if not (weights_host.dtype == torch.float32 and weights_host.is_contiguous() and not weights_host.is_cuda
+                    and tuple(weights_host.shape) == tuple(self.weights.shape)):
+                raise ValueError("weights_host must be a contiguous float32 [4, 2179] host tensor")
+            self._host_src = weights_host  # the copy is asynchronous: keep the source alive until the next hand-over
+            check(lib().nfsp_rollout_with_weights(self.env._h, C.c_void_p(weights_host.data_ptr()), _ptr(self.weights), n_steps,
+                                                  self.eta, self.epsilon, C.byref(io), _stream(self.device)))
+        else:
+            check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilon, C.byref(io), _stream(self.device)))
         out = None
         if dbg is not None:
             out = decode_trace(dbg[0])

@@ -383,6 +383,7 @@ struct SampleReqs {
     const uint64_t *total[NFSP_MAX_SAMPLE_REQS];
     uint64_t cap[NFSP_MAX_SAMPLE_REQS], seed[NFSP_MAX_SAMPLE_REQS], call_idx[NFSP_MAX_SAMPLE_REQS];
     float *out[NFSP_MAX_SAMPLE_REQS];
+    uint4 *rec_out[NFSP_MAX_SAMPLE_REQS];  // packed copies of the sampled slots (ring: 16 bytes, reservoir: 32), or null
     int is_ring[NFSP_MAX_SAMPLE_REQS];
 };
 __global__ void __launch_bounds__(kBufThreads)
@@ -399,9 +400,15 @@ sample_gather_kernel(const SampleReqs R, int batch, int64_t *__restrict__ idx_ou
     if (threadIdx.x == 0 && blockIdx.y == 0 && n_out) n_out[m] = (uint32_t)b;
     const uint4 *mem = R.mem[m];
     float *o = R.out[m];
+    uint4 *ro = R.rec_out[m];
+    const int stride = R.is_ring[m] ? 1 : 2;  // reservoir slots are 32 bytes
     for (int k = row0 + threadIdx.x; k < row1; k += blockDim.x) {
         if (idx_out) idx_out[(int64_t)m * batch + k] = slot[k];
-        if (o) s_rec[k] = slot[k] >= 0 ? mem[slot[k] * (R.is_ring[m] ? 1 : 2)] : make_uint4(0, 0, 0, 0);  // reservoir slots are 32 bytes
+        if (o || ro) {
+            const uint4 rec = slot[k] >= 0 ? mem[slot[k] * stride] : make_uint4(0, 0, 0, 0);
+            if (o) s_rec[k] = rec;
+            if (ro) ro[k * stride] = rec;  // same slot geometry as the memory: the learner kernels read either
+        }
     }
     if (!o) return;  // positions only (the learner reads the packed records itself)
     __syncthreads();
@@ -572,13 +579,14 @@ extern "C" int nfsp_sample_minibatches(const nfsp_sample_req *reqs, int n_reqs, 
     SampleReqs R;
     for (int m = 0; m < n_reqs; ++m) {
         NFSP_CHECK_ARG(reqs[m].d_mem && reqs[m].d_total && reqs[m].cap > 0, "bad request %d", m);
-        NFSP_CHECK_ARG(reqs[m].d_out || d_idx, "request %d has neither an output block nor an index array", m);
+        NFSP_CHECK_ARG(reqs[m].d_out || reqs[m].d_rec_out || d_idx, "request %d has neither an output block nor an index array", m);
         R.mem[m] = (const uint4 *)reqs[m].d_mem;
         R.total[m] = reqs[m].d_total;
         R.cap[m] = (uint64_t)reqs[m].cap;
         R.seed[m] = reqs[m].seed;
         R.call_idx[m] = reqs[m].call_idx;
         R.out[m] = reqs[m].d_out;
+        R.rec_out[m] = (uint4 *)reqs[m].d_rec_out;
         R.is_ring[m] = reqs[m].is_ring;
     }
     sample_gather_kernel<<<dim3((unsigned)n_reqs, 8u, 1u), kBufThreads, 0, (cudaStream_t)stream>>>(R, batch, d_idx, d_n_out);

@@ -73,20 +73,16 @@ class Learner:
         and PipelinedTrainer need.  The same on every rank (the peer set-up is collective)."""
         return self.fused and (_world() == 1 or self._peers is not None)
 
-    def _gather(self, idx_rl, idx_sl):
-        """Copies of the sampled records (4 x minibatch rows, 24 KB): once they exist the update no longer reads the
-        memories, so a rollout that writes the rings in place, or the next insert, may run beside the fit."""
-        sp, b = self.sp, self.minibatch
+    def _snapshot_buffers(self):
+        """Where the sampling launch leaves packed copies of the sampled records (4 x minibatch rows, 24 KB): once they
+        exist the update no longer reads the memories, so a rollout that writes the rings in place, or the next insert,
+        may run beside the fit."""
+        b = self.minibatch
         if not hasattr(self, "_gath"):
-            self._gath = ([torch.empty((b, 4), dtype=torch.int32, device=self.device) for _ in range(2)],
-                          [torch.empty((b, 8), dtype=torch.int32, device=self.device) for _ in range(2)],
+            self._gath = ([torch.zeros((b, 4), dtype=torch.int32, device=self.device) for _ in range(2)],
+                          [torch.zeros((b, 8), dtype=torch.int32, device=self.device) for _ in range(2)],
                           torch.arange(b, dtype=torch.int64, device=self.device))
-        g_rl, g_sl, rows = self._gath
-        for p in range(2):  # a slot of -1 (memory not filled yet) belongs to a net the mask leaves out: any row does
-            torch.index_select(sp.rl[p].store, 0, idx_rl[p].clamp(min=0), out=g_rl[p])
-            torch.index_select(sp.sl[p].store, 0, idx_sl[p].clamp(min=0), out=g_sl[p])
-        self._mems = (g_rl, g_sl)
-        return [rows, rows], [rows, rows]
+        return self._gath
 
     def _io(self, idx_rl, idx_sl, row0, rows, mask, w_in=None):
         sp = self.sp
@@ -101,25 +97,44 @@ class Learner:
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
         return io
 
-    def _sample_positions(self):
+    def _sample_positions(self, snapshot=False, which="both"):
         """sample_batch positions of the four memories (agent.py:217,260) in one launch; the same draws as four
-        sample_slots() calls.  Returns ([rl0, rl1], [sl0, sl1]) index tensors of `minibatch` storage slots."""
+        sample_slots() calls.  Returns ([rl0, rl1], [sl0, sl1]) index tensors of `minibatch` storage slots.
+        snapshot: the launch also copies the sampled slots out of the memories; the fit then reads those copies.
+        which = "rl" / "sl": only the two rings / the two reservoirs (the pipelined trainer samples the rings as soon as
+        the rollout has written them and the reservoirs after the insert launch); "rl" returns nothing."""
         sp, b = self.sp, self.minibatch
         if not hasattr(self, "_pos"):
-            self._pos = torch.empty((4, b), dtype=torch.int64, device=self.device)
+            self._pos = torch.empty((4, b), dtype=torch.int64, device=self.device)   # rows: rl0, rl1, sl0, sl1
             reqs = (_lib.SampleReq * 4)()
-            for p in range(2):
-                for k, mem in ((0, sp.rl[p]), (1, sp.sl[p])):
-                    r = reqs[2 * p + k]
-                    r.d_mem, r.d_total, r.cap = mem.store.data_ptr(), mem.total.data_ptr(), mem.capacity
-                    r.seed, r.is_ring, r.d_out = mem.seed, int(mem.is_ring), None
+            for k, mem in enumerate((sp.rl[0], sp.rl[1], sp.sl[0], sp.sl[1])):
+                r = reqs[k]
+                r.d_mem, r.d_total, r.cap = mem.store.data_ptr(), mem.total.data_ptr(), mem.capacity
+                r.seed, r.is_ring, r.d_out = mem.seed, int(mem.is_ring), None
             self._pos_reqs = reqs
-        for p in range(2):
-            for k, mem in ((0, sp.rl[p]), (1, sp.sl[p])):
-                self._pos_reqs[2 * p + k].call_idx = mem.sample_calls
+        g_rl, g_sl, rows = self._snapshot_buffers() if snapshot else (None, None, None)
+        lo, hi = {"both": (0, 4), "rl": (0, 2), "sl": (2, 4)}[which]
+        for k, mem in enumerate((sp.rl[0], sp.rl[1], sp.sl[0], sp.sl[1])):
+            if lo <= k < hi:
+                r = self._pos_reqs[k]
+                r.call_idx = mem.sample_calls
+                r.d_rec_out = None if not snapshot else (g_rl[k] if k < 2 else g_sl[k - 2]).data_ptr()
                 mem.sample_calls += 1
-        check(lib().nfsp_sample_minibatches(self._pos_reqs, 4, b, _ptr(self._pos), None, _stream(self.device)))
-        return [self._pos[0], self._pos[2]], [self._pos[1], self._pos[3]]
+        first = C.cast(C.byref(self._pos_reqs, lo * C.sizeof(_lib.SampleReq)), C.POINTER(_lib.SampleReq))
+        check(lib().nfsp_sample_minibatches(first, hi - lo, b, _ptr(self._pos[lo:]), None, _stream(self.device)))
+        if which == "rl":
+            return None
+        if snapshot:  # the sampled slots are rows 0 .. b-1 of the snapshots
+            self._mems = (g_rl, g_sl)
+            return [rows, rows], [rows, rows]
+        self._mems = None
+        return [self._pos[0], self._pos[1]], [self._pos[2], self._pos[3]]
+
+    def presample_rings(self):
+        """First half of an update for the pipelined trainer: draw the RL minibatches of both players and snapshot their
+        records (what update(presampled_rings=True) then trains on).  With direct_rings this is all of an update that
+        reads the rings, so the next rollout -- which writes them in place -- only waits for this launch."""
+        self._sample_positions(snapshot=True, which="rl")
 
     # ---- several GPUs of one box: the all-reduce of every SGD step inside the fit kernel, over peer memory ----
     def _agree(self, ok: bool) -> bool:
@@ -226,14 +241,15 @@ class Learner:
         self._all_ready = mask == 15
         return mask
 
-    def update(self, sync=True, weights_in=None, weights_out=None, pack=True, on_gathered=None):
+    def update(self, sync=True, weights_in=None, weights_out=None, pack=True, on_gathered=None, presampled_rings=False):
         """update_strategy() of both agents.  Returns a dict of statistics; with sync=False nothing is read back
         from the device (the loss / exploitability-proxy entries are then the previous synchronised values).
         weights_in / weights_out (float32 [4, 2179] device tensors): train FROM / INTO these instead of the acting
         weights of the SelfPlay object, and with pack=False leave the acting nets alone -- what PipelinedTrainer needs
         to run this update beside the next rollout.  Only the one-launch fit supports it.
         on_gathered: a callable; the sampled records are first copied out of the memories and the callable is invoked
-        right after that copy is enqueued (PipelinedTrainer records an event there: from then on the memories may change)."""
+        right after that copy is enqueued (PipelinedTrainer records an event there: from then on the memories may change).
+        presampled_rings: presample_rings() has already drawn and copied the RL minibatches of this update."""
         sp = self.sp
         mask = self._ready_mask()
         if (weights_in is not None or weights_out is not None) and not self.one_launch:
@@ -246,10 +262,10 @@ class Learner:
         for p in range(2):
             if (mask >> (2 * p + 1)) & 1:
                 self.iteration[p] += 1          # agent.py:216
-        idx_rl, idx_sl = self._sample_positions()
-        self._mems = None
+        if presampled_rings and on_gathered is None:
+            raise ValueError("presampled_rings belongs to the snapshot path (on_gathered)")
+        idx_rl, idx_sl = self._sample_positions(snapshot=on_gathered is not None, which="sl" if presampled_rings else "both")
         if on_gathered is not None:
-            idx_rl, idx_sl = self._gather(idx_rl, idx_sl)
             on_gathered()
         stats = None
         if self.fused and (_world() == 1 or self._peers is not None):
@@ -315,6 +331,7 @@ class PipelinedTrainer:
         self.stream = torch.cuda.Stream(selfplay.device)
         self.flushed = torch.cuda.Event()
         self.gathered = torch.cuda.Event()                             # update j has copied its sampled records
+        self.rolled, self.rings_sampled = torch.cuda.Event(), torch.cuda.Event()
         self.updated = [torch.cuda.Event(), torch.cuda.Event()]        # update j records updated[j % 2]
         self.j = 0
 
@@ -325,17 +342,29 @@ class PipelinedTrainer:
         if j >= 2:
             main.wait_event(self.updated[j % 2])          # update j-2 wrote W_{j-1}
         sp.set_weights(self.w[(j - 1) % 2] if j >= 1 else self.w[0])   # acting nets: W_{j-1} (W_0 for the first two steps)
-        if j >= 1:
-            # update j-1 works on a copy of its sampled records: once that copy exists the memories may change -- the
-            # rollout writes the rings in place with direct_rings, the insert launch writes the reservoirs (and the rings)
-            main.wait_event(self.gathered)
+        # update j-1 works on snapshots of its sampled records: once they exist the memories may change.  The rings'
+        # snapshot is taken right after rollout j-1 wrote them (beside the insert launch), so with direct_rings the next
+        # rollout -- which writes the rings in place -- finds it done; the reservoirs' snapshot gates the next insert
+        if j >= 1 and sp.direct_rings:
+            main.wait_event(self.rings_sampled)
         sp.rollout(n_steps, insert=False, reserve_sms=self.reserve_sms)
+        early = sp.direct_rings and self.learner._ready_mask() == 15
+        if early:
+            self.rolled.record(main)
+            self.stream.wait_event(self.rolled)
+            with torch.cuda.stream(self.stream):
+                self.learner.presample_rings()
+                self.rings_sampled.record(self.stream)
+        if j >= 1:
+            main.wait_event(self.gathered)
         sp.flush()
         self.flushed.record(main)
         self.stream.wait_event(self.flushed)
         with torch.cuda.stream(self.stream):
             out = self.learner.update(sync=sync, weights_in=self.w[j % 2], weights_out=self.w[(j + 1) % 2], pack=False,
-                                      on_gathered=lambda: self.gathered.record(self.stream))
+                                      on_gathered=lambda: self.gathered.record(self.stream), presampled_rings=early)
+            if not early:
+                self.rings_sampled.record(self.stream)
             self.updated[j % 2].record(self.stream)
         self.j = j + 1
         return out

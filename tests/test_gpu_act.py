@@ -579,3 +579,21 @@ def test_dropin_agent_play_flow(nb):
     pi = players[0].avg_strategy_model.predict(np.zeros((1, 1, 30)))
     assert q.shape == pi.shape == (1, 1, 3) and abs(pi.sum() - 1) < 1e-5 and (q >= 0).all()
     assert hasattr(players[0], "act") and hasattr(players[0], "remember_opponent_behaviour")
+
+
+def test_rollout_with_weights_from_host_equals_set_weights_then_rollout(nb):
+    """nfsp_rollout_with_weights (hand-over + rollout in one library call) against the two calls.  4096 games = one block
+    of 32 games per staging segment: the order of the staged records, and with it the reservoirs' contents, is fixed."""
+    n, steps = 4096, 6
+    mk = lambda: nb.SelfPlay(n, seed=9, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps)  # noqa: E731
+    a, b = mk(), mk()
+    for k in range(3):
+        w = torch.from_numpy(random_nets(20 + k)).pin_memory()
+        a.set_weights(w)
+        a.rollout(steps)
+        b.rollout(steps, weights_host=w)
+    torch.cuda.synchronize()
+    assert torch.equal(a.weights, b.weights) and torch.equal(a.env.state_words(), b.env.state_words())
+    assert a.read_stats() == b.read_stats()
+    for p in range(2):
+        assert torch.equal(a.rl[p].data, b.rl[p].data) and torch.equal(a.sl[p].data, b.sl[p].data)
