@@ -331,6 +331,8 @@ typedef struct {
     void *d_buf[NFSP_MAX_PEERS];
     uint32_t epoch0;
     uint32_t *d_err;
+    void *d_mc;   /* or NULL: a multicast mapping of the SAME buffers (NVLS: one store through it lands in every rank's
+                     buffer at that offset); the pushes then leave the SM once instead of `world` times */
 } nfsp_peers;
 int nfsp_learner_fit_peers(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
                            float *d_weights_out, const nfsp_peers *peers, void *stream);

@@ -52,7 +52,7 @@ MAX_PEERS, PEER_BUF_FLOATS = 8, 279552  # NFSP_MAX_PEERS, NFSP_PEER_BUF_FLOATS
 
 class Peers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d_buf", C.c_void_p * MAX_PEERS), ("epoch0", C.c_uint32),
-                ("d_err", C.c_void_p)]
+                ("d_err", C.c_void_p), ("d_mc", C.c_void_p)]
 
 
 class SampleReq(C.Structure):

@@ -265,6 +265,7 @@ struct FitArgs {
     float *peer[NFSP_MAX_PEERS];
     uint32_t epoch0;     // SGD steps exchanged through these buffers so far
     uint32_t *err;       // set to 1 if a peer did not answer in time
+    float *mc;           // multicast mapping of all ranks' buffers (NVLS), or null
 };
 
 // Exchange buffer of one rank (the RECEIVER owns it): two parities x four nets x one slot per sending rank of kPeerSlot
@@ -477,8 +478,12 @@ learner_fit_rows_kernel(const FitArgs F) {
         const uint32_t epoch = F.epoch0 + (uint32_t)k + 1u, parity = epoch & 1u;
         auto apply = [&](int e, float g) {
             if (peers) {
+                // one store through the multicast mapping reaches every rank's buffer (the switch replicates it); without
+                // NVLS the SM sends `world` copies itself
                 const float v = g * inv_rows;
-                for (int r = 0; r < F.world; ++r) ll_store(F.peer[r], ll_index(parity, net, F.rank, e), v, epoch);
+                if (F.mc) ll_store(F.mc, ll_index(parity, net, F.rank, e), v, epoch);
+                else
+                    for (int r = 0; r < F.world; ++r) ll_store(F.peer[r], ll_index(parity, net, F.rank, e), v, epoch);
             } else {
                 S.w[e] -= lr * 1.0f * (g * inv_rows);
             }
@@ -520,10 +525,11 @@ learner_fit_rows_kernel(const FitArgs F) {
             float ls = 0.f, ex = 0.f;
             for (int r = 0; r < rows; ++r) { ls += S.loss[r]; ex += S.expl[r]; }
             if (peers) {
-                for (int r = 0; r < F.world; ++r) {
-                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2180), ls, epoch);
-                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2181), ex, epoch);
-                    ll_store(F.peer[r], ll_index(parity, net, F.rank, 2182), (float)rows, epoch);
+                for (int r = 0; r < (F.mc ? 1 : F.world); ++r) {
+                    float *dst = F.mc ? F.mc : F.peer[r];
+                    ll_store(dst, ll_index(parity, net, F.rank, 2180), ls, epoch);
+                    ll_store(dst, ll_index(parity, net, F.rank, 2181), ex, epoch);
+                    ll_store(dst, ll_index(parity, net, F.rank, 2182), (float)rows, epoch);
                 }
             } else {
                 A.stats[4 + net] = ls;
@@ -648,10 +654,11 @@ static int learner_fit_impl(const nfsp_learner_io *io, int minibatch, int fit_ba
             ++F.n_steps;
         }
     for (int k = 0; k < 4; ++k) F.lr[k] = lr[k];
-    F.world = 1; F.rank = 0; F.epoch0 = 0u; F.err = nullptr;
+    F.world = 1; F.rank = 0; F.epoch0 = 0u; F.err = nullptr; F.mc = nullptr;
     for (int r = 0; r < NFSP_MAX_PEERS; ++r) F.peer[r] = nullptr;
     if (peers) {
         F.world = peers->world; F.rank = peers->rank; F.epoch0 = peers->epoch0; F.err = peers->d_err;
+        F.mc = (float *)peers->d_mc;
         for (int r = 0; r < peers->world; ++r) F.peer[r] = (float *)peers->d_buf[r];
     }
     if (minibatch <= kMaxFitRows && fit_batch <= kMaxStepRows) {  // one warp per row, weights in shared memory

@@ -39,7 +39,7 @@ def _world():
 
 class Learner:
     def __init__(self, selfplay, cfg=None, minibatch=128, fit_batch=32, epochs=2, lr_br=0.05, lr_ar=0.1, gamma=0.95,
-                 target_update_rate=150, terminal_bootstraps=False, fused=True):
+                 target_update_rate=150, terminal_bootstraps=False, fused=True, use_multicast=True):
         if cfg is not None:
             minibatch = cfg.getint("Agent", "MiniBatchSize")
             lr_br, lr_ar = cfg.getfloat("Agent", "LearningRateBR"), cfg.getfloat("Agent", "LearningRateAR")
@@ -57,6 +57,7 @@ class Learner:
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
         self._peers = None
         self.peer_check_every = 64  # updates between two reads of the peer-exchange error word when nothing else syncs
+        self.use_multicast = use_multicast
         if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
             # every rank must take the same path (a rank in the peer exchange and one in an NCCL all-reduce would wait
             # for each other forever): _setup_peers agrees on every phase collectively
@@ -184,6 +185,12 @@ class Learner:
             p.d_buf[r] = int(hdl.buffer_ptrs[r])
         self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
         p.d_err = self._peer_err.data_ptr()
+        # NVLS: a multicast mapping of the same buffers, when the fabric has one -- a push then leaves the SM once.  Every
+        # rank must decide alike (a rank that multicasts while another unicasts is still correct, but keep them uniform)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.use_multicast else 0
+        mc_ok = mc != 0 and buf.data_ptr() == int(hdl.buffer_ptrs[p.rank])
+        p.d_mc = mc if self._agree(mc_ok) else None
+        self._multicast = bool(p.d_mc)
         self._peers, self._peer_keep, self._epoch = p, (buf, hdl), 0
 
     def check_peers(self):

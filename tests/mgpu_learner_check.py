@@ -36,11 +36,14 @@ def filled():
     return sp
 
 
-a, b = filled(), filled()
-La, Lb = Learner(a, fused=True), Learner(b, fused=False)
+a, b, c = filled(), filled(), filled()
+La, Lb, Lc = Learner(a, fused=True), Learner(b, fused=False), Learner(c, fused=True, use_multicast=False)
 assert La._peers is not None, getattr(La, "_peer_note", "no peers")
+if rank == 0:
+    print("multicast (NVLS) pushes:", La._multicast)
 for k in range(4):
-    ra, rb = La.update(), Lb.update()
+    ra, rb, rc = La.update(), Lb.update(), Lc.update()
+    assert torch.equal(a.weights, c.weights), "multicast and unicast pushes must give identical weights"
     assert ra["trained"] == rb["trained"] == 0xF, (ra, rb)
     assert np.allclose(ra["loss"], rb["loss"], rtol=1e-5, atol=1e-5), (ra["loss"], rb["loss"])
     assert abs(ra["exploitability"] - rb["exploitability"]) < 1e-5
@@ -51,7 +54,7 @@ for k in range(4):
     dist.broadcast(ref, 0)
     assert torch.equal(mine, ref), "peer path: weights differ between ranks"
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-for name, L in (("peer exchange", La), ("nccl per step", Lb)):
+for name, L in (("peer exchange", La), ("peer, unicast pushes", Lc), ("nccl per step", Lb)):
     dist.barrier()
     s, e = ev(), ev()
     s.record()
@@ -60,8 +63,8 @@ for name, L in (("peer exchange", La), ("nccl per step", Lb)):
     e.record()
     e.synchronize()
     if rank == 0:
-        print("%-14s %.1f us per update" % (name, s.elapsed_time(e) * 100))
-assert int(La._peer_err.item()) == 0
+        print("%-22s %.1f us per update" % (name, s.elapsed_time(e) * 100))
+assert int(La._peer_err.item()) == 0 and int(Lc._peer_err.item()) == 0
 if rank == 0:
     print("mgpu learner check ok: world", world)
 dist.destroy_process_group()
