@@ -381,10 +381,13 @@ class SelfPlay:
 
     def __init__(self, n_games, weights=None, seed=1234, game0=0, device=None, eta=0.1, epsilon=0.06,
                  rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R",
-                 variant="default", direct_rings=False):
+                 variant="default", direct_rings=False, deterministic=False):
         """direct_rings: the rollout kernel writes the RL records straight into the players' rings (variants "cuda" and
         "sorted"; needs 2 * n_games * max_steps_per_call <= rl_capacity so that one launch cannot lap a ring): no staging
-        copy, `flush()` then only moves the SL records into the reservoirs.  "auto" = on when that condition holds."""
+        copy, `flush()` then only moves the SL records into the reservoirs.  "auto" = on when that condition holds.
+        deterministic: every block of 32 games stages into a segment of its own, so the order in which the records reach
+        the memories -- ring slots, reservoir tickets, the rows a minibatch draws -- is the same in every run (up to
+        1 048 576 games per GPU; staged records only, the warp-per-block variants only)."""
         self.variant = variant
         self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
         self.device, self.n = self.env.device, self.env.n
@@ -409,6 +412,13 @@ class SelfPlay:
         max_seg = 16 if self.direct_rings else 1024
         while not sorted_variant and self.n_seg * 2 <= min(blocks, max_seg):
             self.n_seg *= 2
+        self.deterministic = bool(deterministic)
+        if self.deterministic:
+            if self.direct_rings or sorted_variant or blocks > 32768:
+                raise ValueError("deterministic needs staged records (direct_rings=False), a warp-per-block variant and "
+                                 "at most 1 048 576 games")
+            while self.n_seg < blocks:  # one segment per block of 32 games: a single warp appends to it, in step order
+                self.n_seg *= 2
         per_seg = ((blocks + self.n_seg - 1) // self.n_seg) * 32   # games that can map to one segment
         self.cap_rl = 2 * per_seg * self.max_steps
         self.cap_sl = per_seg * self.max_steps

@@ -597,3 +597,25 @@ def test_rollout_with_weights_from_host_equals_set_weights_then_rollout(nb):
     assert a.read_stats() == b.read_stats()
     for p in range(2):
         assert torch.equal(a.rl[p].data, b.rl[p].data) and torch.equal(a.sl[p].data, b.sl[p].data)
+
+
+def test_deterministic_record_order_above_one_warp_per_segment(nb):
+    """deterministic=True: one staging segment per block of 32 games, so two runs of one seed leave bit-identical
+    memories even where the default layout (1 024 segments shared by several warps) does not fix the order."""
+    n, steps = 100_000, 8
+    runs = []
+    for _ in range(2):
+        sp = nb.SelfPlay(n, seed=4, eta=0.3, epsilon=0.1, rl_capacity=150_000, sl_capacity=20_000, max_steps_per_call=steps,
+                         deterministic=True)
+        assert sp.n_seg >= (n + 31) // 32
+        for _ in range(3):
+            sp.rollout(steps)
+        torch.cuda.synchronize()
+        runs.append(sp)
+    a, b = runs
+    assert a.read_stats() == b.read_stats() and a.read_stats()["dropped"] == 0
+    for p in range(2):
+        assert int(a.rl[p].total.item()) > 150_000 and int(a.sl[p].total.item()) > 20_000   # wrapped / replacing
+        assert torch.equal(a.rl[p].store, b.rl[p].store) and torch.equal(a.sl[p].store, b.sl[p].store)
+    with pytest.raises(ValueError):
+        nb.SelfPlay(4096, rl_capacity=1 << 20, max_steps_per_call=8, direct_rings=True, deterministic=True)
