@@ -532,6 +532,9 @@ class SelfPlay:
         players' rings and reservoirs (`nfsp_insert_multi`: segment prefixes, ring copies beside the reservoirs' stamp
         pass, their write pass, totals committed and counts cleared).  With direct_rings the rings were written by the
         rollout kernel itself and only the two reservoirs travel."""
+        mems_now = self.sl if self.direct_rings else self.sl + self.rl
+        if hasattr(self, "_flush_reqs") and any(m._scratch is None or m._scratch.data_ptr() != p_ for m, p_ in zip(mems_now, self._flush_scratch)):
+            del self._flush_reqs  # somebody inserted into a memory with a larger geometry: its scratch block moved
         if not hasattr(self, "_flush_reqs"):  # pointers and geometry never change: the request block is built once
             mems = [(self.sl[p], self.stage_sl[p], 2 + p, self.cap_sl) for p in range(2)]
             if not self.direct_rings:
@@ -544,6 +547,7 @@ class SelfPlay:
                 r.n_segments, r.seg_cap, r.seed, r.mode = self.n_seg, seg_cap, mem.seed, getattr(mem, "mode", 0)
                 r.reservoir = 0 if mem.is_ring else 1
             self._flush_reqs = (arr, len(mems))
+            self._flush_scratch = [m[0]._scratch.data_ptr() for m in mems]
         arr, n = self._flush_reqs
         check(lib().nfsp_insert_multi(arr, n, _stream(self.device)))
 
