@@ -26,7 +26,7 @@ n, steps = 4096, 8
 
 def filled():
     sp = nfsp_b200.SelfPlay(n, seed=5, game0=rank * n, device=dev, eta=0.3, epsilon=0.2, rl_capacity=1 << 16,
-                            sl_capacity=1 << 16, max_steps_per_call=steps)
+                            sl_capacity=1 << 16, max_steps_per_call=steps, deterministic=True)
     w = sp.weights.clone()
     w[:, 1920:1984] = 0.05
     w[:, 2176:] = 0.1

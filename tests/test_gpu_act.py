@@ -582,10 +582,11 @@ def test_dropin_agent_play_flow(nb):
 
 
 def test_rollout_with_weights_from_host_equals_set_weights_then_rollout(nb):
-    """nfsp_rollout_with_weights (hand-over + rollout in one library call) against the two calls.  4096 games = one block
-    of 32 games per staging segment: the order of the staged records, and with it the reservoirs' contents, is fixed."""
-    n, steps = 4096, 6
-    mk = lambda: nb.SelfPlay(n, seed=9, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps)  # noqa: E731
+    """nfsp_rollout_with_weights (hand-over + rollout in one library call) against the two calls (deterministic=True: one
+    staging segment per block of 32 games, so the order of the records, and with it the reservoirs' contents, is fixed)."""
+    n, steps = 5000, 6
+    mk = lambda: nb.SelfPlay(n, seed=9, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps,  # noqa: E731
+                             deterministic=True)
     a, b = mk(), mk()
     for k in range(3):
         w = torch.from_numpy(random_nets(20 + k)).pin_memory()

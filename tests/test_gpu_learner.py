@@ -21,6 +21,7 @@ def nb():
 
 
 def _filled_selfplay(nb, n=4096, steps=8, rounds=4, **kw):
+    kw.setdefault("deterministic", True)  # several tests hold two such objects against each other: same record order
     sp = nb.SelfPlay(n, seed=5, eta=0.3, epsilon=0.2, rl_capacity=1 << 16, sl_capacity=1 << 16,
                      max_steps_per_call=steps, **kw)
     w = sp.weights.clone()

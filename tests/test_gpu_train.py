@@ -86,12 +86,13 @@ def test_train_loop_runs_and_reports(nb, pipelined):
 def test_pipelined_trainer_equals_the_sequential_loop_run_with_one_update_of_lag(nb):
     """PipelinedTrainer (update j on its own stream beside rollout j+1, the rollout grid four SMs short) against the
     plain loop made to act with the same nets (rollout j with W_{j-1}): the events must order everything, so weights,
-    game words and memories come out bit-identical.  4096 games = one 32-game block per staging segment, so the order
-    of the staged records does not depend on how the blocks were scheduled."""
+    game words and memories come out bit-identical (deterministic=True: one staging segment per block of 32 games, so the
+    order of the staged records does not depend on how the blocks were scheduled)."""
     from nfsp_b200.learner import Learner, PipelinedTrainer
 
     def make():
-        sp = nb.SelfPlay(4096, seed=21, eta=0.3, epsilon=0.2, rl_capacity=1 << 15, sl_capacity=1 << 15, max_steps_per_call=8)
+        sp = nb.SelfPlay(4096, seed=21, eta=0.3, epsilon=0.2, rl_capacity=1 << 15, sl_capacity=1 << 15, max_steps_per_call=8,
+                         deterministic=True)
         for _ in range(3):
             sp.rollout(8)
         return sp
