@@ -13,7 +13,7 @@ import torch  # noqa: E402
 import nfsp_b200  # noqa: E402
 
 n, T = 1 << 20, 8
-sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T)
+sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T, direct_rings=True)
 w_host = sp.weights.cpu().pin_memory()
 stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
