@@ -171,11 +171,12 @@ typedef struct {
                              shared-memory gathers), 2 = tensor cores, one mixed-net tile per 128-thread group,
                              3 = tensor cores, warp-specialised: env warps -> per-net tile queues -> tcgen05.mma on
                              net-homogeneous M128 N64 tiles -> epilogue warpgroups (TMEM -> relu -> 64x3 with W2 from
-                             the constant bank), 4 = CUDA cores with net-sorted warp groups (see below),
-                             0 = library default */
-    int32_t reserve_sms;  /* variants 1, 3 and 4: SMs left free for kernels of other streams (the learner's fit running
+                             the constant bank), 4 = CUDA cores with net-sorted warp groups (see below), 5 = CUDA cores, two
+                             games per lane, the second layer's weights loaded once for a pair of same-net decisions
+                             (csrc/rollout_pairs.cu), 0 = library default */
+    int32_t reserve_sms;  /* variants 1, 3, 4 and 5: SMs left free for kernels of other streams (the learner's fit running
                              beside the rollout); the persistent grid is sm_count - reserve_sms CTAs.  0 = use them all */
-    /* variants 1 and 4, all NULL / 0 otherwise: the RL records go straight into the players' rings instead of d_rl
+    /* variants 1, 4 and 5, all NULL / 0 otherwise: the RL records go straight into the players' rings instead of d_rl
      * (ReplayBuffer.add, replay_buffer.py:30-41, done by the rollout kernel itself): ticket = atomic add on
      * *d_ring_total[p] (records ever inserted, advanced by the kernel), slot = ticket % ring_cap.  d_rl is not
      * written and needs no nfsp_ring_insert afterwards.  Requires 2 * n * n_steps <= ring_cap: the records of one

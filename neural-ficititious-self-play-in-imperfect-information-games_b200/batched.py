@@ -405,7 +405,7 @@ class SelfPlay:
         self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
         self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
         sorted_variant = self.VARIANTS[variant] == 4
-        can_direct = self.VARIANTS[variant] in (0, 1, 4) and 2 * self.n * self.max_steps <= int(rl_capacity)
+        can_direct = self.VARIANTS[variant] in (0, 1, 4, 5) and 2 * self.n * self.max_steps <= int(rl_capacity)
         if direct_rings == "auto":
             direct_rings = can_direct
         if direct_rings and not can_direct:
@@ -466,7 +466,7 @@ class SelfPlay:
         check(fn(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
         return out
 
-    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4}
+    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4, "pairs": 5}
 
     def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None):
         """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
@@ -492,7 +492,7 @@ class SelfPlay:
             if not want_debug:
                 self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
-        if self.direct_rings and io.variant not in (0, 1, 4):
+        if self.direct_rings and io.variant not in (0, 1, 4, 5):
             raise ValueError("this SelfPlay was built with direct_rings: only the CUDA-core variants can run on it")
         if (io.variant == 4) != (self.VARIANTS[self.variant] == 4):
             raise ValueError("variant 'sorted' appends through one cursor per memory: build the SelfPlay with variant='sorted'")

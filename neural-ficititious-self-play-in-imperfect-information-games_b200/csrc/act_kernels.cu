@@ -195,7 +195,9 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
-        const int rc = nfsp_rollout_sorted_configure();
+        int rc = nfsp_rollout_sorted_configure();
+        if (rc != NFSP_OK) return rc;
+        rc = nfsp_rollout_pairs_configure();
         if (rc != NFSP_OK) return rc;
     }
     pack_images_kernel<<<(kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
@@ -283,8 +285,9 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.work = h->d_work;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
-    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 4,
-                   "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group), 3 (tcgen05, warp-specialised) or 4 (CUDA cores, net-sorted groups)");
+    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 5,
+                   "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group), 3 (tcgen05, warp-specialised), "
+                   "4 (CUDA cores, net-sorted groups) or 5 (CUDA cores, two games per lane)");
     const int variant = io->variant == 0 ? NFSP_ROLLOUT_DEFAULT_VARIANT : io->variant;
     NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
     bool direct = false;
@@ -292,7 +295,13 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         const int rc = nfsp_rollout_direct_args(io, A, &direct);
         if (rc != NFSP_OK) return rc;
     }
-    NFSP_CHECK_ARG(!direct || variant == 1 || variant == 4, "the direct ring append (d_ring) exists in variants 1 and 4 only");
+    NFSP_CHECK_ARG(!direct || variant == 1 || variant == 4 || variant == 5, "the direct ring append (d_ring) exists in variants 1, 4 and 5 only");
+    if (variant == 5) {
+        const int rc = nfsp_rollout_pairs_launch(h, A, io, debug, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        h->step += (uint64_t)n_steps;
+        return NFSP_OK;
+    }
     if (variant == 4) {
         const int rc = nfsp_rollout_sorted_launch(h, A, io, debug, (cudaStream_t)stream);
         if (rc != NFSP_OK) return rc;

@@ -51,7 +51,11 @@ struct Layer2Acc {
 
     // + b2, then relu head (best response, agent.py:103) or softmax head (average policy, agent.py:112)
     __device__ __forceinline__ void head(const float4 &b2, bool is_br, float &o0, float &o1, float &o2) const {
-        const float y0 = hsum2(z0) + b2.x, y1 = hsum2(z1) + b2.y, y2 = hsum2(z2) + b2.z;
+        head_of_sums(hsum2(z0), hsum2(z1), hsum2(z2), b2, is_br, o0, o1, o2);
+    }
+    __device__ __forceinline__ static void head_of_sums(float s0, float s1, float s2, const float4 &b2, bool is_br, float &o0,
+                                                        float &o1, float &o2) {
+        const float y0 = s0 + b2.x, y1 = s1 + b2.y, y2 = s2 + b2.z;
         if (is_br) {
             o0 = fmaxf(y0, 0.f); o1 = fmaxf(y1, 0.f); o2 = fmaxf(y2, 0.f);
         } else {

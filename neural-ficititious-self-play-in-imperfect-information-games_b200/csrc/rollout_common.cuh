@@ -18,6 +18,9 @@ int nfsp_rollout_sorted_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, const n
 // validates nfsp_rollout_io.d_ring* and fills the direct-ring fields of A; *direct = the call appends directly
 int nfsp_rollout_direct_args(const nfsp_rollout_io *io, nfsp::RolloutArgs &A, bool *direct);
 int nfsp_rollout_sorted_configure();
+// launches the two-games-per-lane CUDA-core rollout (rollout_pairs.cu)
+int nfsp_rollout_pairs_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st);
+int nfsp_rollout_pairs_configure();
 
 namespace nfsp {
 

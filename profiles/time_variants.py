@@ -13,7 +13,7 @@ import nfsp_b200  # noqa: E402
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 n, T = 1 << 20, 8
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ("cuda", "cuda+direct", "sorted", "sorted+direct", "tcgen05", "tcgen05_ws")
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ("cuda", "cuda+direct", "pairs", "pairs+direct", "sorted", "tcgen05", "tcgen05_ws")
 tune = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
 for variant in variants:
     direct = variant.endswith("+direct")
