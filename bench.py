@@ -314,7 +314,7 @@ def run_gpu(args):
     game0, n = sharding.shard_games(GAMES_PER_GPU * world, rank, world)
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
                             sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
-                            direct_rings=args.variant in ("default", "cuda"))
+                            direct_rings=args.variant in ("default", "cuda", "pairs"))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
     stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
@@ -483,7 +483,7 @@ def run_gpu(args):
     buffers = buffer_kernels(nfsp_b200, dev, ev) if world == 1 else None
     # the other variants of the rollout kernel, kernel only, for the record
     others = {}
-    for other in ("sorted", "tcgen05", "tcgen05_ws"):
+    for other in ("pairs", "sorted", "tcgen05", "tcgen05_ws"):
         spo = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=1 << 16,
                                  sl_capacity=1 << 16, max_steps_per_call=T_PER_CALL, variant=other)
         other_ms = 0.0
@@ -527,7 +527,7 @@ def run_gpu(args):
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
-    roofline = {"bound": "hbm", "kernel": {"tcgen05": "rollout_tc_kernel", "tcgen05_ws": "rollout_tq_kernel", "sorted": "rollout_sorted_kernel"}.get(args.variant, "rollout_kernel"), "achieved": achieved, "peak": hbm, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": {"tcgen05": "rollout_tc_kernel", "tcgen05_ws": "rollout_tq_kernel", "sorted": "rollout_sorted_kernel", "pairs": "rollout_pairs_kernel"}.get(args.variant, "rollout_kernel"), "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_transition": BYTES_PER_TRANSITION,
                 "kernel_ms_per_launch": ker_ms / args.steps,
@@ -639,7 +639,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="default", choices=["default", "cuda", "sorted", "tcgen05", "tcgen05_ws"],
+    ap.add_argument("--variant", default="default", choices=["default", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
                     help="rollout kernel: CUDA-core row sums (default), net-sorted warp groups, tcgen05 tensor-core tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
