@@ -160,3 +160,14 @@ def test_ctypes_mirrors_match_the_header(nb, tmp_path):
             assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, (name, field)
     for name, value in consts.items():
         assert int(got[name]) == value, name
+
+
+def test_every_entry_point_is_mapped_in_integration_md():
+    """INTEGRATION.md must name the reference interface every exported entry replaces (or say that there is none)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "nfsp_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(s for s in set(re.findall(r"\b(nfsp_[a-z0-9_]+)\s*\(", hdr)) if s not in doc)
+    assert not missing, missing
