@@ -184,6 +184,10 @@ typedef struct {
     void *d_ring[2];
     uint64_t *d_ring_total[2];
     int64_t ring_cap;
+    /* each Agent of the reference decays its own epsilon (agent.py:253): with epsilon_per_player != 0 the `epsilon`
+     * argument of nfsp_rollout is player 0's and epsilon_p1 player 1's; otherwise both use `epsilon` */
+    int32_t epsilon_per_player;
+    double epsilon_p1;
 } nfsp_rollout_io;
 /* 4 = CUDA cores, the decisions of a four-warp group sorted by net so that warps are net-homogeneous, records appended
  * with one set of atomics per group: n_segments must be 1 (csrc/rollout_sorted.cu).  An experiment kept for the record:
@@ -300,6 +304,9 @@ typedef struct {
     float gamma;                   /* config.ini Agent.Gamma                                                  */
     int32_t net_mask;              /* bit k: net k trains (its memory holds > MiniBatchSize, agent.py:215,259) */
     int32_t terminal_bootstraps;   /* 1 = reference quirk agent.py:227 (terminal transitions bootstrap too)   */
+    int32_t others_to_target;      /* 1 = the two Q outputs of a row that were not taken regress to the target net's
+                                      predictions on s, as `target = target_br_model.predict(s_batch)` makes them
+                                      (agent.py:220,243); 0 = they have zero error                                */
     float *d_grad;                 /* out [4][NFSP_NET_PARAMS] mean gradients: the flat all-reduce buffer ... */
     float *d_stats;                /* out [NFSP_LEARNER_STATS], laid out right behind it by the host:
                                       expl_sum_p0, expl_sum_p1, rows_p0, rows_p1, loss sums of the 4 nets      */

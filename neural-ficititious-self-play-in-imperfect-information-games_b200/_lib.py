@@ -35,7 +35,8 @@ class RolloutIO(C.Structure):
     _fields_ = [("d_rl", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("cap_rl", C.c_int64), ("cap_sl", C.c_int64),
                 ("n_segments", C.c_int32), ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
                 ("d_forced_vec", C.c_void_p), ("variant", C.c_int32), ("reserve_sms", C.c_int32),
-                ("d_ring", C.c_void_p * 2), ("d_ring_total", C.c_void_p * 2), ("ring_cap", C.c_int64)]
+                ("d_ring", C.c_void_p * 2), ("d_ring_total", C.c_void_p * 2), ("ring_cap", C.c_int64),
+                ("epsilon_per_player", C.c_int32), ("epsilon_p1", C.c_double)]
 
 
 class InsertReq(C.Structure):
@@ -64,7 +65,7 @@ class LearnerIO(C.Structure):
     _fields_ = [("d_weights", C.c_void_p), ("d_target_weights", C.c_void_p), ("d_rl", C.c_void_p * 2),
                 ("d_rl_idx", C.c_void_p * 2), ("d_sl", C.c_void_p * 2), ("d_sl_idx", C.c_void_p * 2),
                 ("row0", C.c_int32), ("rows", C.c_int32), ("gamma", C.c_float), ("net_mask", C.c_int32),
-                ("terminal_bootstraps", C.c_int32), ("d_grad", C.c_void_p), ("d_stats", C.c_void_p)]
+                ("terminal_bootstraps", C.c_int32), ("others_to_target", C.c_int32), ("d_grad", C.c_void_p), ("d_stats", C.c_void_p)]
 
 
 class NfspError(RuntimeError):

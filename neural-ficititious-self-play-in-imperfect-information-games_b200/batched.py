@@ -400,7 +400,9 @@ class SelfPlay:
         self.variant = variant
         self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
         self.device, self.n = self.env.device, self.env.n
-        self.eta, self.epsilon = float(eta), float(epsilon)
+        self.eta = float(eta)
+        # one epsilon per player (each Agent of the reference decays its own, agent.py:253); a scalar sets both
+        self.epsilons = [float(e) for e in epsilon] if isinstance(epsilon, (list, tuple)) else [float(epsilon)] * 2
         self.max_steps = int(max_steps_per_call)
         self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
         self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
@@ -440,6 +442,15 @@ class SelfPlay:
         self.stats = torch.zeros(_lib.STATS_FIELDS, dtype=torch.int64, device=self.device)
         self.set_weights(glorot_nets(seed, self.device) if weights is None else weights)
         self.env.reset()
+
+    @property
+    def epsilon(self):
+        """Player 0's epsilon (both players' while they are equal); assigning a number sets both."""
+        return self.epsilons[0]
+
+    @epsilon.setter
+    def epsilon(self, value):
+        self.epsilons = [float(value)] * 2
 
     def set_weights(self, weights):
         """The four acting nets, float32 [4, 2179] (avg0, br0, avg1, br1).  A host tensor (pinned for an asynchronous
@@ -492,6 +503,7 @@ class SelfPlay:
             if not want_debug:
                 self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
+        io.epsilon_per_player, io.epsilon_p1 = int(self.epsilons[0] != self.epsilons[1]), self.epsilons[1]
         if self.direct_rings and io.variant not in (0, 1, 4, 5):
             raise ValueError("this SelfPlay was built with direct_rings: only the CUDA-core variants can run on it")
         if (io.variant == 4) != (self.VARIANTS[self.variant] == 4):
@@ -514,9 +526,9 @@ class SelfPlay:
                 raise ValueError("weights_host must be a contiguous float32 [4, 2179] host tensor")
             self._host_src = weights_host  # the copy is asynchronous: keep the source alive until the next hand-over
             check(lib().nfsp_rollout_with_weights(self.env._h, C.c_void_p(weights_host.data_ptr()), _ptr(self.weights), n_steps,
-                                                  self.eta, self.epsilon, C.byref(io), _stream(self.device)))
+                                                  self.eta, self.epsilons[0], C.byref(io), _stream(self.device)))
         else:
-            check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilon, C.byref(io), _stream(self.device)))
+            check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilons[0], C.byref(io), _stream(self.device)))
         out = None
         if dbg is not None:
             out = decode_trace(dbg[0])

@@ -279,7 +279,9 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     RolloutArgs A;
     A.keys = philox_keys(h->seed);
     A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
-    A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon); A.pack = h->d_wpack + kPackFloats;
+    A.eta_u32 = frac_u32(eta); A.eps_u32 = frac_u32(epsilon);
+    A.eps1_u32 = io->epsilon_per_player ? frac_u32(io->epsilon_p1) : A.eps_u32;
+    A.pack = h->d_wpack + kPackFloats;
     for (int q = 0; q < 2; ++q) { A.rl[q] = (uint4 *)io->d_rl[q]; A.sl[q] = (uint4 *)io->d_sl[q]; }
     A.cap_rl = io->cap_rl; A.cap_sl = io->cap_sl; A.n_seg = (uint32_t)io->n_segments; A.counts = io->d_counts;
     A.work = h->d_work;

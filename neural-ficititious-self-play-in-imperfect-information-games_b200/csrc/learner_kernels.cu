@@ -30,6 +30,7 @@ struct LearnerArgs {
     float gamma;
     int net_mask;            // bit k set = net k takes part (memory large enough, agent.py:215,259)
     int terminal_bootstraps; // reference quirk agent.py:227: `t is True` never holds, terminals bootstrap too
+    int others_to_target;    // the two outputs not taken regress to the target net's predictions (agent.py:220,243)
     float *grad;             // [4][2179] mean gradients (+= nothing: overwritten)
     float *stats;            // [NFSP_LEARNER_STATS]
 };
@@ -119,6 +120,27 @@ __device__ __forceinline__ void prefetch_rows(const LearnerArgs &A, int net, int
     for (int r = threadIdx.x; r < rows; r += blockDim.x) s_rec[r] = mem[idx[base + r] * stride];
     __syncthreads();
 }
+// Huber loss (agent.py:91-99) of the best-response net on one row, averaged over the three outputs as Keras does, and its
+// derivative w.r.t. the pre-activations z.  The taken action regresses to the TD target; the other two outputs have zero
+// error by default, or -- `others_to_target`, what agent.py:220-243 does with `target = target_br_model.predict(s_batch)`
+// -- regress to the target net's own predictions qt on s.
+__device__ __forceinline__ float br_loss(float z0, float z1, float z2, float qt0, float qt1, float qt2, uint32_t a, float td,
+                                         int others_to_target, float &dz0, float &dz1, float &dz2) {
+    const float z[3] = {z0, z1, z2}, qt[3] = {qt0, qt1, qt2};
+    float dz[3], loss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const bool taken = (uint32_t)c == a;
+        const float err = (taken ? td : qt[c]) - fmaxf(z[c], 0.f);
+        const float ae = fabsf(err);
+        const bool on = taken || others_to_target;
+        loss += on ? (ae > 1.f ? ae - 0.5f : 0.5f * err * err) * (1.0f / 3.0f) : 0.f;
+        dz[c] = on ? -(ae > 1.f ? copysignf(1.f, err) : err) * (1.0f / 3.0f) * (z[c] > 0.f ? 1.f : 0.f) : 0.f;
+    }
+    dz0 = dz[0]; dz1 = dz[1]; dz2 = dz[2];
+    return loss;
+}
+
 __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &N, int net, int row0, int rows,
                                           float (*red_all)[4][2][4], float (*part)[40][64], const uint4 *s_rec, int s_base) {
     const int player = net >> 1, is_br = net & 1, group = threadIdx.x >> 6, j = threadIdx.x & 63;
@@ -145,16 +167,12 @@ __device__ __forceinline__ void step_sums(const LearnerArgs &A, const NetState &
             cta_sum9(v, red, group);
             float z0 = v[0], z1 = v[1], z2 = v[2];
             const float y0 = v[3], y1 = v[4], y2 = v[5], e0 = v[6], e1 = v[7], e2 = v[8];
-            expl += fmaxf(fmaxf(fmaxf(e0 + t2_0, 0.f), fmaxf(e1 + t2_1, 0.f)), fmaxf(e2 + t2_2, 0.f));
+            const float qt0 = fmaxf(e0 + t2_0, 0.f), qt1 = fmaxf(e1 + t2_1, 0.f), qt2 = fmaxf(e2 + t2_2, 0.f);
+            expl += fmaxf(fmaxf(qt0, qt1), qt2);
             const float qn = fmaxf(fmaxf(fmaxf(y0 + t2_0, 0.f), fmaxf(y1 + t2_1, 0.f)), fmaxf(y2 + t2_2, 0.f));
             const float target = rew + ((term && !A.terminal_bootstraps) ? 0.f : A.gamma * qn);
             z0 += b2_0; z1 += b2_1; z2 += b2_2;
-            const float za = a == 0 ? z0 : (a == 1 ? z1 : z2);
-            const float err = target - fmaxf(za, 0.f);                     // y - Q(s,a), other outputs have zero error
-            const float ae = fabsf(err);
-            loss += (ae > 1.f ? ae - 0.5f : 0.5f * err * err) * (1.0f / 3.0f);
-            const float dq = -(ae > 1.f ? copysignf(1.f, err) : err) * (1.0f / 3.0f) * (za > 0.f ? 1.f : 0.f);
-            dz0 = a == 0 ? dq : 0.f; dz1 = a == 1 ? dq : 0.f; dz2 = a == 2 ? dq : 0.f;
+            loss += br_loss(z0, z1, z2, qt0, qt1, qt2, a, target, A.others_to_target, dz0, dz1, dz2);
             group_sync(group);  // red[] slots are reused by the next row
             const float dh = (h > 0.f) ? (W.w2[0] * dz0 + W.w2[1] * dz1 + W.w2[2] * dz2) : 0.f;
             gw2[0] += h * dz0; gw2[1] += h * dz1; gw2[2] += h * dz2;
@@ -433,16 +451,12 @@ learner_fit_rows_kernel(const FitArgs F) {
                 }
                 warp_sum9(v);
                 const float t2_0 = S.wt[2176], t2_1 = S.wt[2177], t2_2 = S.wt[2178];
-                expl = fmaxf(fmaxf(fmaxf(v[6] + t2_0, 0.f), fmaxf(v[7] + t2_1, 0.f)), fmaxf(v[8] + t2_2, 0.f));  // agent.py:234-238
+                const float qt0 = fmaxf(v[6] + t2_0, 0.f), qt1 = fmaxf(v[7] + t2_1, 0.f), qt2 = fmaxf(v[8] + t2_2, 0.f);
+                expl = fmaxf(fmaxf(qt0, qt1), qt2);  // agent.py:234-238
                 const float qn = fmaxf(fmaxf(fmaxf(v[3] + t2_0, 0.f), fmaxf(v[4] + t2_1, 0.f)), fmaxf(v[5] + t2_2, 0.f));
                 const float target = rew + ((term && !A.terminal_bootstraps) ? 0.f : A.gamma * qn);
                 const float z0 = v[0] + S.w[2176], z1 = v[1] + S.w[2177], z2 = v[2] + S.w[2178];
-                const float za = a == 0 ? z0 : (a == 1 ? z1 : z2);
-                const float err = target - fmaxf(za, 0.f);  // y - Q(s,a), the other outputs have zero error
-                const float ae = fabsf(err);
-                loss = (ae > 1.f ? ae - 0.5f : 0.5f * err * err) * (1.0f / 3.0f);
-                const float dq = -(ae > 1.f ? copysignf(1.f, err) : err) * (1.0f / 3.0f) * (za > 0.f ? 1.f : 0.f);
-                dz0 = a == 0 ? dq : 0.f; dz1 = a == 1 ? dq : 0.f; dz2 = a == 2 ? dq : 0.f;
+                loss = br_loss(z0, z1, z2, qt0, qt1, qt2, a, target, A.others_to_target, dz0, dz1, dz2);
             } else {
                 const float ya = __uint_as_float(rec.y), yb = __uint_as_float(rec.z), yc = __uint_as_float(rec.w);
                 float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -601,7 +615,8 @@ static int make_learner_args(const nfsp_learner_io *io, LearnerArgs &A) {
         if ((io->net_mask >> (2 * p)) & 1) NFSP_CHECK_ARG(A.sl[p] && A.sl_idx[p], "missing SL batch of player %d", p);
     }
     A.row0 = io->row0; A.rows = io->rows; A.gamma = io->gamma; A.net_mask = io->net_mask;
-    A.terminal_bootstraps = io->terminal_bootstraps; A.grad = io->d_grad; A.stats = io->d_stats;
+    A.terminal_bootstraps = io->terminal_bootstraps; A.others_to_target = io->others_to_target;
+    A.grad = io->d_grad; A.stats = io->d_stats;
     return NFSP_OK;
 }
 

@@ -36,7 +36,7 @@ struct RolloutArgs {
     uint64_t seed, game0, step0;
     PhiloxKeys keys;         // round keys of `seed` (constant-bank operands of the lean kernels)
     int n_steps;
-    uint32_t eta_u32, eps_u32;
+    uint32_t eta_u32, eps_u32, eps1_u32;  // epsilon of player 0 / of player 1 (each agent decays its own, agent.py:253)
     const void *pack;  // weight image of the variant
     uint4 *rl[2];
     uint4 *sl[2];

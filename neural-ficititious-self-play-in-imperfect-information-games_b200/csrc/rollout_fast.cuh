@@ -71,7 +71,7 @@ __device__ __forceinline__ void fast_begin(NfspFast &g, const FastLuts &L, const
     d.snap_a = g.SA;
     d.meta_a = ((g.PA >> 5) & 3u) | (g.p() << 16);
     d.pol = (g.PA & kPPol) != 0u;
-    d.random = d.pol && x.x < A.eps_u32;
+    d.random = d.pol && x.x < (g.p() ? A.eps1_u32 : A.eps_u32);
     if (d.random) {  // np.random.rand(1,1,3): rare, so it has its own Philox block
         const Philox4 y = game_block(A.keys, game, step, STREAM_VECTOR);
         d.r0 = (float)(y.x >> 8) * (1.0f / 16777216.0f);

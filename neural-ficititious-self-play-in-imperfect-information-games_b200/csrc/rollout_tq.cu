@@ -377,7 +377,7 @@ struct GameSet {
         obs = g.HX & (g.PA | 0x00FFFFFFu) & 0x3FFFFFFFu;
         const uint32_t pol = (g.PA >> 12) & 1u;
         flags |= pol << 1;
-        if (pol && x.x < A.eps_u32) flags |= 4u;
+        if (pol && x.x < (q ? A.eps1_u32 : A.eps_u32)) flags |= 4u;
         const uint32_t net = q * 2u + pol;
         // ---- ticket in the net's queue, operand row into the tile ------------------------------------------------
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? net : 4u);

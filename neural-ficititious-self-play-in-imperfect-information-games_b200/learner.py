@@ -8,12 +8,14 @@ nets, gradients into one flat fp32 buffer with the exploitability statistics beh
 all-reduce of that buffer over the GPUs (NCCL; C1 + C2 of SURVEY 2a), one `nfsp_sgd_apply` launch.
 Weights therefore stay bit-identical on every rank.
 
-What follows the reference literally (host arithmetic): the schedules of agent.py:245-253
-(`iteration` advanced twice per update, temperature, BR learning-rate decay, `epsilon ** 1/iteration`
-== epsilon/iteration by operator precedence) and the target-net copy every TargetModelUpdateRate
-updates (agent.py:266-273).  What does NOT (documented in DESIGN.md): the reference overwrites only row
-0 of the target batch (agent.py:241) and never treats a transition as terminal (agent.py:227, kept
-behind `terminal_bootstraps=True`); here every row gets its own TD target.  Keras shuffles the rows
+What follows the reference literally (host arithmetic): the schedules of agent.py:245-253 per player
+(`iteration` advanced twice per update, temperature, BR learning-rate decay, each agent's own
+`epsilon ** 1/iteration` == epsilon/iteration by operator precedence) and the target-net copy every
+TargetModelUpdateRate updates (agent.py:266-273).  What does NOT (documented in DESIGN.md): the reference
+overwrites only row 0 of the target batch (agent.py:241) and never treats a transition as terminal
+(agent.py:227, kept behind `terminal_bootstraps=True`); here every row gets its own TD target, and the two
+outputs a row did not take have zero error unless `others_to_target=True` (agent.py:220: they regress to the
+target net's predictions).  Keras shuffles the rows
 each epoch with an unseeded RNG; the minibatches here are the sampled rows in order.  The NN
 arithmetic itself is unpinned (no Keras/TensorFlow to compare with).
 """
@@ -39,7 +41,7 @@ def _world():
 
 class Learner:
     def __init__(self, selfplay, cfg=None, minibatch=128, fit_batch=32, epochs=2, lr_br=0.05, lr_ar=0.1, gamma=0.95,
-                 target_update_rate=150, terminal_bootstraps=False, fused=True, use_multicast=True):
+                 target_update_rate=150, terminal_bootstraps=False, fused=True, use_multicast=True, others_to_target=False):
         if cfg is not None:
             minibatch = cfg.getint("Agent", "MiniBatchSize")
             lr_br, lr_ar = cfg.getfloat("Agent", "LearningRateBR"), cfg.getfloat("Agent", "LearningRateAR")
@@ -52,6 +54,9 @@ class Learner:
         self.lr_br = [self.lr_br0, self.lr_br0]
         self.target_update_rate = int(target_update_rate)
         self.terminal_bootstraps = bool(terminal_bootstraps)
+        # the two Q outputs a row did not take: zero error (default), or regressed to the target net's predictions as the
+        # reference's `target = target_br_model.predict(s_batch)` does (agent.py:220,243)
+        self.others_to_target = bool(others_to_target)
         self.fused = bool(fused)  # single GPU: the whole fit() as one kernel; False = one launch pair per SGD step
         self.target = selfplay.weights[[1, 3]].clone().contiguous()   # agent.py:70-72
         self.flat = torch.zeros(GRAD + N_STATS, dtype=torch.float32, device=self.device)
@@ -95,6 +100,7 @@ class Learner:
             io.d_sl[p], io.d_sl_idx[p] = mem_sl[p].data_ptr(), idx_sl[p].data_ptr()
         io.row0, io.rows, io.gamma, io.net_mask = row0, rows, self.gamma, mask
         io.terminal_bootstraps = int(self.terminal_bootstraps)
+        io.others_to_target = int(self.others_to_target)
         io.d_grad, io.d_stats = self.flat.data_ptr(), self.flat[GRAD:].data_ptr()
         return io
 
@@ -304,9 +310,9 @@ class Learner:
                     self.target[p].copy_(w_new[2 * p + 1])
                 self.target_update_count[p] += 1
                 self.lr_br[p] = self.lr_br0 / (1 + 0.003 * math.sqrt(it))        # agent.py:251
-        if any((mask >> (2 * p + 1)) & 1 for p in range(2)):
-            it = max(self.iteration)
-            sp.epsilon = sp.epsilon ** 1 / it                                    # agent.py:253 (sic)
+        for p in range(2):
+            if (mask >> (2 * p + 1)) & 1:   # each agent decays its own epsilon by its own iteration count
+                sp.epsilons[p] = sp.epsilons[p] ** 1 / self.iteration[p]         # agent.py:253 (sic)
         if pack:
             sp.set_weights(sp.weights)  # rebuild the kernels' weight images
         self.updates += 1

@@ -17,7 +17,7 @@ def bits(m):
     return ((np.asarray(m, np.uint32)[:, None] >> np.arange(30)) & 1).astype(np.float64)
 
 
-def br_grad(w, w_target, s, s2, a, r, t, gamma, terminal_bootstraps=False):
+def br_grad(w, w_target, s, s2, a, r, t, gamma, terminal_bootstraps=False, others_to_target=False):
     """Mean gradient (flat, 2179) of the Huber loss on the taken action; also the exploitability proxy sum."""
     W1, b1, W2, b2 = split(w)
     T1, tb1, T2, tb2 = split(w_target)
@@ -32,10 +32,11 @@ def br_grad(w, w_target, s, s2, a, r, t, gamma, terminal_bootstraps=False):
     y = np.asarray(r, np.float64) + gamma * live * qn
     n = len(s)
     rows = np.arange(n)
-    err = y - q[rows, a]
-    dq = -np.where(np.abs(err) > 1, np.sign(err), err) / 3.0
-    dz = np.zeros_like(z)
-    dz[rows, a] = dq * (z[rows, a] > 0)
+    qs = np.maximum(np.maximum(x @ T1 + tb1, 0) @ T2 + tb2, 0)       # target net on s: agent.py:220
+    tgt = qs.copy() if others_to_target else q.copy()                   # outputs not taken: to qs, or zero error
+    tgt[rows, a] = y
+    err = tgt - q
+    dz = -np.where(np.abs(err) > 1, np.sign(err), err) / 3.0 * (z > 0)
     loss = (np.where(np.abs(err) > 1, np.abs(err) - 0.5, 0.5 * err * err) / 3.0).sum()
     return _backprop(x, h, W2, dz, n), expl, loss
 

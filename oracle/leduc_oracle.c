@@ -464,6 +464,13 @@ static void push_sl(OrcRolloutOut *out, int p, uint32_t s, const float a[3]) {
 void orc_nfsp_batch_rollout_act(OrcNfspBatch *b, uint64_t step0, int n_steps, const OrcNet nets[4],
                                 uint32_t eta_u32, uint32_t eps_u32, const float *forced_vec, float *vec_out,
                                 OrcTraceRec *trace, OrcRolloutOut *out, int n_threads) {
+    orc_nfsp_batch_rollout_act2(b, step0, n_steps, nets, eta_u32, eps_u32, eps_u32, forced_vec, vec_out, trace, out, n_threads);
+}
+
+/* the same with one epsilon per player: every Agent decays its own (agent.py:78,253) */
+void orc_nfsp_batch_rollout_act2(OrcNfspBatch *b, uint64_t step0, int n_steps, const OrcNet nets[4], uint32_t eta_u32,
+                                 uint32_t eps0_u32, uint32_t eps1_u32, const float *forced_vec, float *vec_out,
+                                 OrcTraceRec *trace, OrcRolloutOut *out, int n_threads) {
     (void)n_threads;
     int n = b->n;
     for (int t = 0; t < n_steps; ++t) {
@@ -490,7 +497,7 @@ void orc_nfsp_batch_rollout_act(OrcNfspBatch *b, uint64_t step0, int n_steps, co
             int is_br = g->policy[p];
             if (!is_br) {
                 orc_mlp_avg(&nets[p * 2 + 0], x, vec); /* agent.py:143 */
-            } else if (u[0] < eps_u32) {               /* agent.py:125-128: random score vector, stream 1 */
+            } else if (u[0] < (p ? eps1_u32 : eps0_u32)) { /* agent.py:125-128: random score vector, stream 1 */
                 uint32_t y[4];
                 game_block(b->seed, b->game0 + (uint64_t)gi, step, 1u, y);
                 for (int c = 0; c < 3; ++c) vec[c] = (float)(y[c] >> 8) * (1.0f / 16777216.0f);

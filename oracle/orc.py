@@ -86,6 +86,8 @@ def lib():
         L.orc_nfsp_batch_rollout_act.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32,
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_int]
+        L.orc_nfsp_batch_rollout_act2.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_nfsp_batch_env.restype = C.POINTER(NfspEnv)
         L.orc_nfsp_batch_env.argtypes = [C.c_void_p, C.c_int]
         L.orc_nfsp_batch_flags.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int * 4)]
@@ -229,7 +231,7 @@ class NfspBatch:
                                          None if p is None else p.ctypes.data, eta_u32, tr.ctypes.data, threads)
         return tr
 
-    def rollout_act(self, step0, n_steps, nets: Nets, eta_u32, eps_u32, forced_vec=None, rec_cap=None):
+    def rollout_act(self, step0, n_steps, nets: Nets, eta_u32, eps_u32, forced_vec=None, rec_cap=None, eps1_u32=None):
         n = self.n
         cap = rec_cap or (3 * n * n_steps + 8)
         tr = np.zeros((n_steps, n), TRACE_DT)
@@ -241,9 +243,10 @@ class NfspBatch:
             out.rl[p], out.cap_rl[p] = rl[p].ctypes.data, cap
             out.sl[p], out.cap_sl[p] = sl[p].ctypes.data, cap
         fv = None if forced_vec is None else np.ascontiguousarray(forced_vec, np.float32)
-        lib().orc_nfsp_batch_rollout_act(self.h, step0, n_steps, C.byref(nets.arr), eta_u32, eps_u32,
-                                         None if fv is None else fv.ctypes.data, vec.ctypes.data, tr.ctypes.data,
-                                         C.byref(out), 0)
+        lib().orc_nfsp_batch_rollout_act2(self.h, step0, n_steps, C.byref(nets.arr), eta_u32, eps_u32,
+                                          eps_u32 if eps1_u32 is None else eps1_u32,
+                                          None if fv is None else fv.ctypes.data, vec.ctypes.data, tr.ctypes.data,
+                                          C.byref(out), 0)
         return dict(trace=tr, vec=vec, rl=[rl[p][:out.n_rl[p]] for p in range(2)],
                     sl=[sl[p][:out.n_sl[p]] for p in range(2)],
                     actions=np.array(list(out.actions)).reshape(2, 3), played=np.array(list(out.played)),

@@ -620,3 +620,30 @@ def test_deterministic_record_order_above_one_warp_per_segment(nb):
         assert torch.equal(a.rl[p].store, b.rl[p].store) and torch.equal(a.sl[p].store, b.sl[p].store)
     with pytest.raises(ValueError):
         nb.SelfPlay(4096, rl_capacity=1 << 20, max_steps_per_call=8, direct_rings=True, deterministic=True)
+
+
+@pytest.mark.parametrize("variant", ["cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"])
+def test_one_epsilon_per_player(nb, variant):
+    """Each Agent of the reference decays its own epsilon (agent.py:78,253): epsilon = (0.6, 0.05) against the oracle;
+    the random-vector branch (agent.py:125-128) must fire at each player's own rate."""
+    n, steps, seed, eta, eps = 6000, 10, 77, 0.5, (0.6, 0.05)
+    w = random_nets(3)
+    sp = nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=eps, rl_capacity=1 << 12, sl_capacity=1 << 12,
+                     max_steps_per_call=steps, variant=variant)
+    assert sp.epsilons == [0.6, 0.05] and sp.epsilon == 0.6
+    out = sp.rollout(steps, insert=False, debug=True)
+    rl, sl = sp.staged()
+    vec = out["vec"].cpu().numpy()
+    b = orc.NfspBatch(n, seed)
+    b.reset(0, orc.u32_frac(eta))
+    ref = b.rollout_act(1, steps, oracle_nets(nb, w), orc.u32_frac(eta), orc.u32_frac(eps[0]), forced_vec=vec,
+                        eps1_u32=orc.u32_frac(eps[1]))
+    tr = out["raw"].cpu().numpy().view(np.uint32)
+    assert np.array_equal(tr[0], ref["trace"]["obs"]) and np.array_equal(tr[2], ref["trace"]["misc"])
+    assert np.abs(vec - ref["vec"]).max() <= TOL   # the oracle draws its random vectors at the same decisions
+    for p in range(2):
+        assert np.array_equal(canon(rl[p]), canon(ref["rl"][p])) and np.array_equal(canon(sl[p]), canon(ref["sl"][p]))
+    same = nb.SelfPlay(n, weights=torch.from_numpy(w), seed=seed, eta=eta, epsilon=0.6, rl_capacity=1 << 12, sl_capacity=1 << 12,
+                       max_steps_per_call=steps, variant=variant)
+    same.rollout(steps, insert=False)
+    assert not np.array_equal(same.env.state_words().cpu().numpy(), sp.env.state_words().cpu().numpy())

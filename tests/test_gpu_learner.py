@@ -65,7 +65,8 @@ def test_gradients_match_float64_oracle(nb):
     assert float(np.abs(flat[:GRAD]).max()) > 1e-4  # not vacuous
 
 
-def test_gradients_match_torch_autograd(nb):
+@pytest.mark.parametrize("others", [False, True])
+def test_gradients_match_torch_autograd(nb, others):
     """The same gradients against torch.autograd in float64 on the CPU: the backward pass is DERIVED by autograd from the
     forward definition (Dense-relu-Dense with a relu head and the Huber loss of agent.py:91-99 averaged over the three
     outputs as Keras does, resp. a softmax head with categorical cross-entropy), so nothing of the hand-written backward --
@@ -75,7 +76,7 @@ def test_gradients_match_torch_autograd(nb):
     from nfsp_b200.learner import GRAD, Learner
 
     sp = _filled_selfplay(nb)
-    L = Learner(sp, minibatch=128, gamma=0.95)
+    L = Learner(sp, minibatch=128, gamma=0.95, others_to_target=others)
     L.target = (sp.weights[[1, 3]] * 0.9 + 0.01).contiguous()
     idx_rl = [sp.rl[p].sample_slots(128)[0] for p in range(2)]
     idx_sl = [sp.sl[p].sample_slots(128)[0] for p in range(2)]
@@ -102,9 +103,13 @@ def test_gradients_match_torch_autograd(nb):
         with torch.no_grad():
             qn = F.relu(net(T[p], bits(rl["s2"]))).max(1).values
             y = torch.from_numpy(rl["r"].astype(np.float64)) + 0.95 * (1.0 - torch.from_numpy(rl["t"].astype(np.float64))) * qn
-        err = y - q[torch.arange(rows), torch.from_numpy(rl["a"].astype(np.int64))]
+        a_idx = torch.from_numpy(rl["a"].astype(np.int64))
+        with torch.no_grad():  # the fit's target matrix: the target net's predictions on s (agent.py:220) or, by default,
+            tgt = F.relu(net(T[p], bits(rl["s"]))) if others else q.detach().clone()   # the net's own (zero error)
+            tgt[torch.arange(rows), a_idx] = y                                          # agent.py:241, every row its own
+        err = tgt - q
         huber = torch.where(err.abs() > 1, err.abs() - 0.5, 0.5 * err * err)   # agent.py:91-99
-        (huber / 3.0).mean().backward()                                          # Keras: mean over the 3 outputs, mean over rows
+        huber.mean(dim=1).mean().backward()                                      # Keras: mean over the 3 outputs, mean over rows
         got = flat[(2 * p + 1) * 2179:(2 * p + 2) * 2179]
         assert float((got - w.grad).abs().max()) < 1e-5 and float(w.grad.abs().max()) > 1e-4
         sl = np.ascontiguousarray(sp.sl[p].data.cpu().numpy()).view(np.uint8).reshape(-1).view(orc.SL_DT)[idx_sl[p].cpu().numpy()][row0:row0 + rows]
