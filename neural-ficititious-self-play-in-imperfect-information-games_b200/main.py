@@ -94,6 +94,12 @@ def main(argv=None):
     ap.add_argument("--report-every", type=int, default=100)
     ap.add_argument("--no-true-exploitability", action="store_true")
     ap.add_argument("--pipelined", action="store_true", help="run the learner's update beside the next rollout")
+    ap.add_argument("--others-to-target", action="store_true",
+                    help="untaken Q outputs regress to the target net's predictions, as the reference's fit does (agent.py:220)")
+    ap.add_argument("--terminal-bootstraps", action="store_true",
+                    help="terminal transitions bootstrap too (the reference's `t is True` never holds, agent.py:227)")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="fix the order of the records in the memories (one staging segment per block of 32 games)")
     ap.add_argument("--updates-per-call", type=int, default=1,
                     help="update_strategy() calls per rollout call (the reference's cadence: games * steps / 256)")
     args = ap.parse_args(argv)
@@ -109,8 +115,9 @@ def main(argv=None):
     game0, n = sharding.shard_games(args.games, rank, world)
     sp = SelfPlay(n, seed=seed, game0=game0, device=dev, eta=cfg.getfloat("Agent", "Eta"),
                   epsilon=cfg.getfloat("Agent", "Epsilon"), rl_capacity=cfg.getint("Agent", "MRLSize"),
-                  sl_capacity=cfg.getint("Agent", "MSLSize"), max_steps_per_call=args.steps_per_call)
-    learner = Learner(sp, cfg=cfg)
+                  sl_capacity=cfg.getint("Agent", "MSLSize"), max_steps_per_call=args.steps_per_call,
+                  deterministic=args.deterministic, direct_rings=False if args.deterministic else "auto")
+    learner = Learner(sp, cfg=cfg, terminal_bootstraps=args.terminal_bootstraps, others_to_target=args.others_to_target)
     episodes = args.episodes if args.episodes is not None else cfg.getint("Common", "Episodes")
     rows = train(sp, learner, episodes, args.steps_per_call, args.report_every, world,
                  log=print if rank == 0 else (lambda *a, **k: None),
