@@ -344,6 +344,14 @@ typedef struct {
 } nfsp_peers;
 int nfsp_learner_fit_peers(const nfsp_learner_io *io, int minibatch, int fit_batch, int epochs, const float lr[4],
                            float *d_weights_out, const nfsp_peers *peers, void *stream);
+/* Exchange buffers for nfsp_learner_fit_peers without any framework help: a rank creates its buffer (cudaMalloc,
+ * zeroed) and gets its 64-byte CUDA IPC handle, sends the handle to the other ranks of the box over any channel, and
+ * opens theirs; nfsp_peers.d_buf[r] = rank r's buffer as this process maps it, d_mc = NULL (no multicast mapping on this
+ * route).  close = unmap a peer's buffer, destroy = free one's own (after every peer has closed it). */
+int nfsp_peer_buffer_create(int device, void **d_buf, unsigned char *handle64);
+int nfsp_peer_buffer_open(int device, const unsigned char *handle64, void **d_buf);
+int nfsp_peer_buffer_close(int device, void *d_buf);
+int nfsp_peer_buffer_destroy(int device, void *d_buf);
 /* keras SGD step (agent.py:45-46,243,261): w[k] -= lr[k] * scale * grad[k]; scale = 1/world after a SUM
  * all-reduce.  lr is a HOST array of 4 floats. */
 int nfsp_sgd_apply(float *d_weights, const float *d_grad, const float lr[4], float scale, void *stream);

@@ -28,6 +28,7 @@ SYMBOLS = [
     "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_with_weights", "nfsp_rollout_tune", "nfsp_rollout_profile",
     "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_insert_multi", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
+    "nfsp_peer_buffer_create", "nfsp_peer_buffer_open", "nfsp_peer_buffer_close", "nfsp_peer_buffer_destroy",
 ]
 
 
@@ -139,6 +140,10 @@ def lib():
     L.nfsp_learner_fit_peers.argtypes = [C.POINTER(LearnerIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp,
                                          C.POINTER(Peers), vp]
     L.nfsp_sgd_apply.argtypes = [vp, vp, C.POINTER(C.c_float * 4), C.c_float, vp]
+    L.nfsp_peer_buffer_create.argtypes = [C.c_int, C.POINTER(vp), C.c_char_p]
+    L.nfsp_peer_buffer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.nfsp_peer_buffer_close.argtypes = [C.c_int, vp]
+    L.nfsp_peer_buffer_destroy.argtypes = [C.c_int, vp]
     _lib = L
     return L
 

@@ -11,6 +11,8 @@
 // of W1, its row of W2 and the matching gradient accumulators in registers; the 64-wide reductions of layer 2 go
 // through shuffles and a 64-thread named barrier.  The groups take the minibatch rows round-robin (the kernel is
 // latency-bound: three dependent reductions per row) and their partial gradients are summed in a fixed order.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace nfsp {
@@ -692,5 +694,51 @@ extern "C" int nfsp_sgd_apply(float *d_weights, const float *d_grad, const float
     sgd_apply_kernel<<<(kGradFloats + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, d_grad, lr[0], lr[1], lr[2],
                                                                                   lr[3], scale);
     NFSP_LAUNCH_CHECK();
+    return NFSP_OK;
+}
+
+// ---- exchange buffers without torch's symmetric memory: plain CUDA IPC ---------------------------------------------
+// A rank allocates its buffer with cudaMalloc (zeroed), hands the 64-byte IPC handle to its peers through any channel
+// (the host code uses torch.distributed.all_gather_object), and maps theirs.  No multicast mapping on this route.
+extern "C" int nfsp_peer_buffer_create(int device, void **d_buf, unsigned char *handle64) {
+    NFSP_CHECK_ARG(d_buf && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", device);
+    void *p = nullptr;
+    NFSP_CUDA(cudaMalloc(&p, sizeof(float) * NFSP_PEER_BUF_FLOATS));
+    NFSP_CUDA(cudaMemset(p, 0, sizeof(float) * NFSP_PEER_BUF_FLOATS));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_error(NFSP_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *d_buf = p;
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_peer_buffer_open(int device, const unsigned char *handle64, void **d_buf) {
+    NFSP_CHECK_ARG(d_buf && handle64, "null argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    NFSP_CUDA(cudaIpcOpenMemHandle(d_buf, h, cudaIpcMemLazyEnablePeerAccess));
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_peer_buffer_close(int device, void *d_buf) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", device);
+    if (d_buf) NFSP_CUDA(cudaIpcCloseMemHandle(d_buf));
+    return NFSP_OK;
+}
+
+extern "C" int nfsp_peer_buffer_destroy(int device, void *d_buf) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", device);
+    if (d_buf) NFSP_CUDA(cudaFree(d_buf));
     return NFSP_OK;
 }

@@ -41,7 +41,8 @@ def _world():
 
 class Learner:
     def __init__(self, selfplay, cfg=None, minibatch=128, fit_batch=32, epochs=2, lr_br=0.05, lr_ar=0.1, gamma=0.95,
-                 target_update_rate=150, terminal_bootstraps=False, fused=True, use_multicast=True, others_to_target=False):
+                 target_update_rate=150, terminal_bootstraps=False, fused=True, use_multicast=True, others_to_target=False,
+                 peer_transport="auto"):
         if cfg is not None:
             minibatch = cfg.getint("Agent", "MiniBatchSize")
             lr_br, lr_ar = cfg.getfloat("Agent", "LearningRateBR"), cfg.getfloat("Agent", "LearningRateAR")
@@ -63,6 +64,9 @@ class Learner:
         self._peers = None
         self.peer_check_every = 64  # updates between two reads of the peer-exchange error word when nothing else syncs
         self.use_multicast = use_multicast
+        if peer_transport not in ("auto", "symm", "ipc"):
+            raise ValueError("peer_transport must be 'auto', 'symm' or 'ipc'")
+        self.peer_transport = peer_transport
         if self.fused and _world() > 1 and self.minibatch <= 256 and self.fit_batch <= 64:
             # every rank must take the same path (a rank in the peer exchange and one in an NCCL all-reduce would wait
             # for each other forever): _setup_peers agrees on every phase collectively
@@ -158,46 +162,116 @@ class Learner:
         warnings.warn("nfsp_b200 learner: %s; using one NCCL all-reduce per SGD step" % self._peer_note, RuntimeWarning)
 
     def _setup_peers(self):
-        """One exchange buffer per rank that every rank can address (torch symmetric memory: CUDA IPC under the hood).
-        Falls back to the NCCL path (one all-reduce per SGD step) if the ranks cannot map each other's memory.
+        """One exchange buffer per rank that every rank can address.  Two transports, tried in this order (or the one
+        `peer_transport` names): "symm" -- torch symmetric memory, which also offers the NVLS multicast mapping -- and
+        "ipc" -- buffers the library allocates itself and shares as plain CUDA IPC handles (no private torch module
+        involved).  Falls back to the NCCL path (one all-reduce per SGD step) if neither works.
 
         Collective-safe: each phase that can fail on one rank only runs under its own try, and the ranks AGREE on its
         outcome with an all-reduce before anybody enters the next collective -- no rank can sit in rendezvous / barrier
         while another has already fallen back."""
+        if dist.get_world_size() > _lib.MAX_PEERS:  # the same on every rank
+            return self._no_peers("more than %d ranks" % _lib.MAX_PEERS)
+        notes = []
+        for transport in (("symm", "ipc") if self.peer_transport == "auto" else (self.peer_transport,)):
+            why = self._setup_peers_symm() if transport == "symm" else self._setup_peers_ipc()
+            if why is None:
+                self._peer_transport = transport
+                return
+            notes.append("%s: %s" % (transport, why))
+        self._no_peers("; ".join(notes))
+
+    def _finish_peers(self, ptrs, mc, keep):
+        p = _lib.Peers()
+        p.world, p.rank = dist.get_world_size(), dist.get_rank()
+        for r in range(p.world):
+            p.d_buf[r] = int(ptrs[r])
+        self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        p.d_err = self._peer_err.data_ptr()
+        p.d_mc = mc or None
+        self._multicast = bool(mc)
+        self._peers, self._peer_keep, self._epoch = p, keep, 0
+
+    def _setup_peers_symm(self):
+        """torch symmetric memory; returns None on success, else why not (the same answer on every rank)."""
         symm_mem, buf, why = None, None, None
-        try:  # phase 1, local only: the import, the size limit, the allocation
+        try:  # phase 1, local only: the import and the allocation
             import torch.distributed._symmetric_memory as symm_mem
 
-            if dist.get_world_size() > _lib.MAX_PEERS:
-                raise RuntimeError("more than %d ranks" % _lib.MAX_PEERS)
             buf = symm_mem.empty(_lib.PEER_BUF_FLOATS, dtype=torch.float32, device=self.device)
             buf.zero_()
             torch.cuda.synchronize(self.device)
         except Exception as e:  # noqa: BLE001
             why = repr(e)
         if not self._agree(why is None):
-            return self._no_peers(why or "another rank could not allocate symmetric memory")
+            return why or "another rank could not allocate symmetric memory"
         hdl = None
         try:  # phase 2, collective: every rank is here
             hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
         except Exception as e:  # noqa: BLE001
             why = repr(e)
         if not self._agree(why is None):
-            return self._no_peers(why or "another rank could not map the peers' buffers")
-        dist.barrier()  # every buffer is zero before anybody's first flag can arrive
-        p = _lib.Peers()
-        p.world, p.rank = dist.get_world_size(), dist.get_rank()
-        for r in range(p.world):
-            p.d_buf[r] = int(hdl.buffer_ptrs[r])
-        self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        p.d_err = self._peer_err.data_ptr()
+            return why or "another rank could not map the peers' buffers"
+        dist.barrier()  # every buffer is zero before anybody's first word can arrive
         # NVLS: a multicast mapping of the same buffers, when the fabric has one -- a push then leaves the SM once.  Every
-        # rank must decide alike (a rank that multicasts while another unicasts is still correct, but keep them uniform)
+        # rank decides alike
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.use_multicast else 0
-        mc_ok = mc != 0 and buf.data_ptr() == int(hdl.buffer_ptrs[p.rank])
-        p.d_mc = mc if self._agree(mc_ok) else None
-        self._multicast = bool(p.d_mc)
-        self._peers, self._peer_keep, self._epoch = p, (buf, hdl), 0
+        mc_ok = mc != 0 and buf.data_ptr() == int(hdl.buffer_ptrs[dist.get_rank()])
+        self._finish_peers(hdl.buffer_ptrs, mc if self._agree(mc_ok) else 0, (buf, hdl))
+        return None
+
+    def _setup_peers_ipc(self):
+        """Buffers allocated by the library and shared as CUDA IPC handles (nfsp_peer_buffer_*); no multicast mapping."""
+        world, rank, dev = dist.get_world_size(), dist.get_rank(), self.device.index
+        mine, handle, why = C.c_void_p(), C.create_string_buffer(64), None
+        try:
+            check(lib().nfsp_peer_buffer_create(dev, C.byref(mine), handle))
+        except Exception as e:  # noqa: BLE001
+            why = repr(e)
+        if not self._agree(why is None):
+            if mine.value:
+                lib().nfsp_peer_buffer_destroy(dev, mine)
+            return why or "another rank could not create its exchange buffer"
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw)  # collective: every rank is here
+        ptrs, opened = [0] * world, []
+        try:
+            for r in range(world):
+                if r == rank:
+                    ptrs[r] = mine.value
+                    continue
+                q = C.c_void_p()
+                check(lib().nfsp_peer_buffer_open(dev, handles[r], C.byref(q)))
+                ptrs[r] = q.value
+                opened.append(q)
+        except Exception as e:  # noqa: BLE001
+            why = repr(e)
+        if not self._agree(why is None):
+            for q in opened:
+                lib().nfsp_peer_buffer_close(dev, q)
+            dist.barrier()  # nobody maps a buffer any more: its owner may free it
+            lib().nfsp_peer_buffer_destroy(dev, mine)
+            return why or "another rank could not map the peers' buffers"
+        dist.barrier()
+        self._finish_peers(ptrs, 0, ("ipc", mine, opened))
+        return None
+
+    def close_peers(self):
+        """Collective: unmap and free the exchange buffers (the IPC transport owns raw CUDA allocations; symmetric memory
+        is released with its tensors).  The learner continues on the NCCL path afterwards."""
+        keep = getattr(self, "_peer_keep", None)
+        if getattr(self, "_peers", None) is None or keep is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()  # no fit kernel of any rank still polls or pushes
+        if keep[0] == "ipc":
+            dev = self.device.index
+            for q in keep[2]:
+                lib().nfsp_peer_buffer_close(dev, q)
+            dist.barrier()  # nobody maps a buffer any more: its owner may free it
+            lib().nfsp_peer_buffer_destroy(dev, keep[1])
+        self._peers = self._peer_keep = None
+        self._peer_note = "peer exchange closed"
 
     def check_peers(self):
         """Raises if a peer GPU failed to answer during any gradient exchange so far (the kernel then gave up after ~2 s,

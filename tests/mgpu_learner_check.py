@@ -36,14 +36,17 @@ def filled():
     return sp
 
 
-a, b, c = filled(), filled(), filled()
+a, b, c, e4 = filled(), filled(), filled(), filled()
 La, Lb, Lc = Learner(a, fused=True), Learner(b, fused=False), Learner(c, fused=True, use_multicast=False)
+Ld = Learner(e4, fused=True, peer_transport="ipc")  # buffers shared as plain CUDA IPC handles by the library itself
 assert La._peers is not None, getattr(La, "_peer_note", "no peers")
+assert Ld._peers is not None and Ld._peer_transport == "ipc", getattr(Ld, "_peer_note", "no ipc peers")
 if rank == 0:
-    print("multicast (NVLS) pushes:", La._multicast)
+    print("transport:", La._peer_transport, " multicast (NVLS) pushes:", La._multicast)
 for k in range(4):
-    ra, rb, rc = La.update(), Lb.update(), Lc.update()
+    ra, rb, rc, rd = La.update(), Lb.update(), Lc.update(), Ld.update()
     assert torch.equal(a.weights, c.weights), "multicast and unicast pushes must give identical weights"
+    assert torch.equal(a.weights, e4.weights), "symmetric-memory and IPC buffers must give identical weights"
     assert ra["trained"] == rb["trained"] == 0xF, (ra, rb)
     assert np.allclose(ra["loss"], rb["loss"], rtol=1e-5, atol=1e-5), (ra["loss"], rb["loss"])
     assert abs(ra["exploitability"] - rb["exploitability"]) < 1e-5
@@ -54,7 +57,7 @@ for k in range(4):
     dist.broadcast(ref, 0)
     assert torch.equal(mine, ref), "peer path: weights differ between ranks"
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-for name, L in (("peer exchange", La), ("peer, unicast pushes", Lc), ("nccl per step", Lb)):
+for name, L in (("peer exchange", La), ("peer, unicast pushes", Lc), ("peer, CUDA IPC buffers", Ld), ("nccl per step", Lb)):
     dist.barrier()
     s, e = ev(), ev()
     s.record()
@@ -64,7 +67,11 @@ for name, L in (("peer exchange", La), ("peer, unicast pushes", Lc), ("nccl per 
     e.synchronize()
     if rank == 0:
         print("%-22s %.1f us per update" % (name, s.elapsed_time(e) * 100))
-assert int(La._peer_err.item()) == 0 and int(Lc._peer_err.item()) == 0
+assert int(La._peer_err.item()) == 0 and int(Lc._peer_err.item()) == 0 and int(Ld._peer_err.item()) == 0
+Ld.close_peers()  # unmaps and frees the IPC buffers; the learner carries on over NCCL
+assert Ld._peers is None
+Ld.update(), Lb.update()
+assert (e4.weights - b.weights).abs().max().item() < 1e-5
 if rank == 0:
     print("mgpu learner check ok: world", world)
 dist.destroy_process_group()
