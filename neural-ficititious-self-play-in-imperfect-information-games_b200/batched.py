@@ -407,7 +407,7 @@ class SelfPlay:
         self.rl = [DeviceRing(rl_capacity, seed + 1 + p, self.device) for p in range(2)]
         self.sl = [DeviceReservoir(sl_capacity, seed + 3 + p, self.device, reservoir_mode) for p in range(2)]
         sorted_variant = self.VARIANTS[variant] == 4
-        can_direct = self.VARIANTS[variant] in (0, 1, 4, 5) and 2 * self.n * self.max_steps <= int(rl_capacity)
+        can_direct = self.VARIANTS[variant] in (0, 1, 4, 5, 6) and 2 * self.n * self.max_steps <= int(rl_capacity)
         if direct_rings == "auto":
             direct_rings = can_direct
         if direct_rings and not can_direct:
@@ -477,7 +477,7 @@ class SelfPlay:
         check(fn(self.env._h, _ptr(o), _ptr(k), o.numel(), _ptr(out), _stream(self.device)))
         return out
 
-    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4, "pairs": 5}
+    VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4, "pairs": 5, "states": 6}
 
     def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None):
         """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
@@ -504,7 +504,7 @@ class SelfPlay:
                 self._io = io
         io.variant = self.VARIANTS[variant or self.variant]
         io.epsilon_per_player, io.epsilon_p1 = int(self.epsilons[0] != self.epsilons[1]), self.epsilons[1]
-        if self.direct_rings and io.variant not in (0, 1, 4, 5):
+        if self.direct_rings and io.variant not in (0, 1, 4, 5, 6):
             raise ValueError("this SelfPlay was built with direct_rings: only the CUDA-core variants can run on it")
         if (io.variant == 4) != (self.VARIANTS[self.variant] == 4):
             raise ValueError("variant 'sorted' appends through one cursor per memory: build the SelfPlay with variant='sorted'")

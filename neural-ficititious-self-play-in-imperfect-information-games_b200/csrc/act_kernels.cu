@@ -47,6 +47,7 @@ __device__ __forceinline__ float pack_weights_value(const float *__restrict__ w,
     }
 }
 
+static_assert((kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS) % 4 == 0, "the state table behind the images must be 16-byte aligned (bulk copy)");
 // both images in one launch: pack = [batched-forward image (kPackFloats) | rollout table image (kTabImageFloats)]
 // ... followed by a plain copy of the four nets (what the tensor-core variants' images are built from, on demand)
 __global__ void pack_images_kernel(const float *__restrict__ w, float *__restrict__ pack) {
@@ -187,8 +188,9 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
     if (!h->d_wpack) {
-        NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS)));
+        NFSP_CUDA(cudaMalloc(&h->d_wpack, sizeof(float) * (kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS + nfsp_states_floats())));
         h->d_wcopy = h->d_wpack + kPackFloats + kTabImageFloats;
+        h->d_states = h->d_wpack + kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS;
         NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
         NFSP_CUDA(cudaFuncSetAttribute(act_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackFloats * sizeof(float))));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
@@ -199,10 +201,12 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         if (rc != NFSP_OK) return rc;
         rc = nfsp_rollout_pairs_configure();
         if (rc != NFSP_OK) return rc;
+        rc = nfsp_rollout_states_configure();
+        if (rc != NFSP_OK) return rc;
     }
     pack_images_kernel<<<(kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weights, h->d_wpack);
     NFSP_LAUNCH_CHECK();
-    h->tc_dirty = h->tq_dirty = true;
+    h->tc_dirty = h->tq_dirty = h->st_dirty = true;
     h->has_weights = true;
     return NFSP_OK;
 }
@@ -287,9 +291,9 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     A.work = h->d_work;
     A.stats = (unsigned long long *)io->d_stats; A.trace = io->d_trace; A.vec = io->d_vec; A.forced = io->d_forced_vec;
     const bool debug = io->d_trace || io->d_vec || io->d_forced_vec;
-    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 5,
+    NFSP_CHECK_ARG(io->variant >= 0 && io->variant <= 6,
                    "variant must be 0 (default), 1 (CUDA cores), 2 (tcgen05, one tile per group), 3 (tcgen05, warp-specialised), "
-                   "4 (CUDA cores, net-sorted groups) or 5 (CUDA cores, two games per lane)");
+                   "4 (CUDA cores, net-sorted groups), 5 (CUDA cores, two games per lane) or 6 (table of the nets' outputs per decision state)");
     const int variant = io->variant == 0 ? NFSP_ROLLOUT_DEFAULT_VARIANT : io->variant;
     NFSP_CHECK_ARG(io->reserve_sms >= 0 && io->reserve_sms < h->sm_count, "reserve_sms must be in [0, %d)", h->sm_count);
     bool direct = false;
@@ -297,7 +301,16 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
         const int rc = nfsp_rollout_direct_args(io, A, &direct);
         if (rc != NFSP_OK) return rc;
     }
-    NFSP_CHECK_ARG(!direct || variant == 1 || variant == 4 || variant == 5, "the direct ring append (d_ring) exists in variants 1, 4 and 5 only");
+    NFSP_CHECK_ARG(!direct || variant == 1 || variant >= 4, "the direct ring append (d_ring) exists in variants 1, 4, 5 and 6 only");
+    if (variant == 6) {
+        int rc = nfsp_states_ensure(h, h->d_wpack + kPackFloats, h->d_states, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        A.pack = h->d_states;
+        rc = nfsp_rollout_states_launch(h, A, io, debug, (cudaStream_t)stream);
+        if (rc != NFSP_OK) return rc;
+        h->step += (uint64_t)n_steps;
+        return NFSP_OK;
+    }
     if (variant == 5) {
         const int rc = nfsp_rollout_pairs_launch(h, A, io, debug, (cudaStream_t)stream);
         if (rc != NFSP_OK) return rc;

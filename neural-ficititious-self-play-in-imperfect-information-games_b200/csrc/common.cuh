@@ -23,6 +23,8 @@ struct nfsp_env_s {
     // the tensor-core variants' weight images are built from the handle's own copy of the nets (behind the packed images
     // in d_wpack) the first time one of them runs after nfsp_act_set_weights: the default path pays for one pack launch
     bool tc_dirty = false, tq_dirty = false;
+    bool st_dirty = false;    // the table of the nets' outputs per decision state (rollout_states.cu), behind d_wcopy in d_wpack
+    float *d_states = nullptr;
     const float *d_wcopy = nullptr;
     // warp-specialised tcgen05 rollout (rollout_tq.cu)
     int w2_slot = -1;         // this handle's slot of the constant-bank image of the second layers, -1 = none yet

@@ -22,6 +22,12 @@ int nfsp_rollout_sorted_configure();
 int nfsp_rollout_pairs_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st);
 int nfsp_rollout_pairs_configure();
 
+// the rollout over a table of the nets' outputs per decision state (rollout_states.cu)
+int nfsp_rollout_states_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st);
+int nfsp_states_ensure(nfsp_env_t h, const float *d_tab, float *d_states, cudaStream_t st);
+int nfsp_states_floats();
+int nfsp_rollout_states_configure();
+
 namespace nfsp {
 
 // ---- warp-aggregated record append -------------------------------------------------------------

@@ -14,7 +14,7 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 T = 8
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for variant, direct in (("cuda", False), ("cuda", True), ("sorted", False), ("sorted", True)):
+for variant, direct in (("cuda", False), ("cuda", True), ("states", False), ("states", True)):
     sp = nfsp_b200.SelfPlay(n, seed=1234, rl_capacity=1 << 25, sl_capacity=1 << 23, max_steps_per_call=T, variant=variant,
                             direct_rings=direct)
     tot, ker = [], []

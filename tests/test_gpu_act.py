@@ -105,7 +105,7 @@ def test_forward_tensor_core_mixed_nets_ragged(nb):
         assert np.abs(got - ref).max() <= TOL and np.abs(base - ref).max() <= TOL, n
 
 
-@pytest.mark.parametrize("variant", ["pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["states", "pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
 @pytest.mark.parametrize("n,steps,eta,eps", [(1, 30, 0.5, 0.5), (1000, 12, 0.1, 0.06), (50_000, 8, 0.3, 0.2)])
 def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps, variant):
     """The fused act+step+remember kernel vs the oracle's restatement of Agent.play/main.train."""
@@ -142,7 +142,7 @@ def test_fused_rollout_vs_oracle(nb, n, steps, eta, eps, variant):
         assert abs(float(pol.mean()) - eta) < 5 * (eta * (1 - eta) / pol.numel()) ** 0.5 + 1e-3
 
 
-@pytest.mark.parametrize("variant", ["pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["states", "pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
 def test_fused_rollout_golden_hands(nb, golden_dir, variant):
     """All 20 352 reference hands (incl. zero vectors and argmax ties) through the fused kernel with the
     reference's scripted score vectors; records must equal the oracle's, which is pinned to the
@@ -293,7 +293,7 @@ def test_rollout_variants_agree_without_debug(nb):
     whenever no decision is a last-bit near-tie (seeded so that none is)."""
     n, steps = 20_000, 8
     res = []
-    for variant in ("cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"):
+    for variant in ("cuda", "states", "pairs", "sorted", "tcgen05", "tcgen05_ws"):
         sp = nb.SelfPlay(n, seed=77, eta=0.2, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12,
                          max_steps_per_call=steps, variant=variant)
         sp.rollout(steps, insert=False)
@@ -305,7 +305,7 @@ def test_rollout_variants_agree_without_debug(nb):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("variant", ["pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["states", "pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
 @pytest.mark.parametrize("n", [1, 31, 129, 1000])
 def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
     """One launch of 19 steps == 19 launches of one step (game words, counters, record multisets), for sizes that
@@ -333,7 +333,7 @@ def test_rollout_launch_batching_and_ragged_sizes(nb, n, variant):
     assert res[0][1]["transitions"] == n * steps and res[0][1]["dropped"] == 0
 
 
-@pytest.mark.parametrize("variant", ["pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["states", "pairs", "sorted", "cuda", "tcgen05", "tcgen05_ws"])
 def test_staging_overflow_drops_and_never_writes_past_a_segment(nb, variant):
     """compute-sanitizer is closed on this pool, so the bounds are checked by hand: staging segments far too small
     for the rollout, canary words behind every segment.  Records that do not fit are counted as dropped, the
@@ -408,7 +408,7 @@ def _rows(a):
     return list(map(bytes, np.ascontiguousarray(a).view(np.uint8).reshape(-1, 16)))
 
 
-@pytest.mark.parametrize("variant", ["cuda", "pairs", "sorted"])
+@pytest.mark.parametrize("variant", ["cuda", "states", "pairs", "sorted"])
 def test_direct_ring_append_equals_the_staged_insert(nb, variant):
     """direct_rings: the rollout kernel writes the RL records into the rings itself (ticket = atomic add on the ring's
     total, slot = ticket % capacity; replay_buffer.py:30-41).  Launch by launch the records are those the staged path
@@ -622,7 +622,7 @@ def test_deterministic_record_order_above_one_warp_per_segment(nb):
         nb.SelfPlay(4096, rl_capacity=1 << 20, max_steps_per_call=8, direct_rings=True, deterministic=True)
 
 
-@pytest.mark.parametrize("variant", ["cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"])
+@pytest.mark.parametrize("variant", ["cuda", "states", "pairs", "sorted", "tcgen05", "tcgen05_ws"])
 def test_one_epsilon_per_player(nb, variant):
     """Each Agent of the reference decays its own epsilon (agent.py:78,253): epsilon = (0.6, 0.05) against the oracle;
     the random-vector branch (agent.py:125-128) must fire at each player's own rate."""

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 from oracle import orc  # noqa: E402
 
 TOL = 1e-5  # BASELINE.json north_star: "within 1e-5 absolute (fp32)"
-VARIANTS = ["sorted", "cuda", "tcgen05", "tcgen05_ws"]
+VARIANTS = ["states", "sorted", "cuda", "tcgen05", "tcgen05_ws"]
 
 
 @pytest.fixture(scope="module")
