@@ -61,71 +61,97 @@ constexpr int kWarpBufQuads = 2 * kBufRL + 2 * kBufSL;   // 288 uint4 = 4 608 B 
 constexpr int kStatesSmemBytes = kStateBytes + (kStatesThreads / 32) * kWarpBufQuads * 16;
 static_assert(kBufRL >= 64 && kBufSL >= 32, "a buffer must take the records of one step");
 
-struct WarpBuf {
-    uint4 *rl0, *rl1, *sl0, *sl1;  // shared memory
-    uint32_t n0 = 0u, n1 = 0u, m0 = 0u, m1 = 0u;  // records held (warp-uniform): RL of player 0 / 1, SL of player 0 / 1
+// quad offsets of the four lists in a warp's buffer: RL of player 0 / 1, SL of player 0 / 1
+constexpr uint32_t kOffRL1 = kBufRL, kOffSL0 = 2 * kBufRL, kOffSL1 = 2 * kBufRL + kBufSL;
 
-    __device__ __forceinline__ void init(uint4 *base) {
-        rl0 = base; rl1 = base + kBufRL; sl0 = base + 2 * kBufRL; sl1 = sl0 + kBufSL;
-    }
+struct WarpBuf {
+    uint4 *b;            // this warp's kWarpBufQuads of shared memory
+    uint32_t cnt = 0u;   // records held, one byte per list: rl0 | rl1 << 8 | sl0 << 16 | sl1 << 24 (warp-uniform)
 };
 
-// moves n buffered records of one list to its destination: one atomic for the warp, then a coalesced copy
-template <bool kRing>
-__device__ __forceinline__ void buf_flush(const uint4 *buf, uint32_t &n, uint4 *dst, void *counter, uint32_t cap, uint64_t magic,
-                                          FastCounters &c) {
-    __syncwarp();
-    if (n) {
-        const uint32_t lane = threadIdx.x & 31u;
-        uint32_t base = 0u;
-        if (lane == 0) {
-            if (kRing) base = ring_slot(atomicAdd((unsigned long long *)counter, (unsigned long long)n), cap, magic);
-            else base = atomicAdd((uint32_t *)counter, n);
-        }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        int drop = 0;
-        for (uint32_t k = lane; k < n; k += 32u) {
-            const uint32_t off = base + k;
-            if (kRing) dst[off < cap ? off : off - cap] = buf[k];  // a launch never laps the ring
-            else if (off < cap) dst[off] = buf[k];
-            else ++drop;
-        }
-        c.wide.drop += drop;
-        n = 0u;
-    }
-    __syncwarp();
+// inclusive warp scan of four byte counters (no byte exceeds 255); the shuffle's own predicate says whether a lane has a
+// source, so a step is SHFL + a predicated add
+__device__ __forceinline__ uint32_t warp_scan_bytes_p(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{ .reg .pred p; .reg .u32 r; shfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, r; }" : "+r"(v) : "r"(o));
+    return v;
 }
 
-template <bool kDirect>
-__device__ __forceinline__ void buf_flush_rl(WarpBuf &B, const RolloutArgs &A, const WarpStage &W, FastCounters &c, bool p0, bool p1) {
-    if (p0) buf_flush<kDirect>(B.rl0, B.n0, W.rl0, kDirect ? (void *)A.ring_total[0] : (void *)W.cnt, W.cap_rl, A.ring_magic, c);
-    if (p1) buf_flush<kDirect>(B.rl1, B.n1, W.rl1, kDirect ? (void *)A.ring_total[1] : (void *)(W.cnt + W.n_seg), W.cap_rl, A.ring_magic, c);
+// copies the n buffered records of one list to base, base + 1, ... of its destination (coalesced: 512 B per warp store)
+template <bool kRing, int kCap>
+__device__ __forceinline__ void buf_copy(const uint4 *src, uint32_t n, uint4 *dst, uint32_t base, uint32_t cap, int &drop) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int it = 0; it < (kCap + 31) / 32; ++it) {
+        const uint32_t k = lane + 32u * it;
+        if (k < n) {
+            uint32_t off = base + k;
+            if (kRing) {
+                off = off < cap ? off : off - cap;  // a launch never laps the ring
+                dst[off] = src[k];
+            } else if (off < cap) {
+                dst[off] = src[k];
+            } else {
+                ++drop;
+            }
+        }
+    }
 }
-__device__ __forceinline__ void buf_flush_sl(WarpBuf &B, const WarpStage &W, FastCounters &c, bool p0, bool p1) {
-    if (p0) buf_flush<false>(B.sl0, B.m0, W.sl0, W.cnt + 2u * W.n_seg, W.cap_sl, 0ull, c);
-    if (p1) buf_flush<false>(B.sl1, B.m1, W.sl1, W.cnt + 3u * W.n_seg, W.cap_sl, 0ull, c);
+
+// moves the lists named in `which` (bit l = list l; warp-uniform) to their destinations: the claims of all lists go out
+// together (lanes 0-3, one round trip), then one coalesced copy per list
+template <bool kDirect>
+__device__ __forceinline__ void buf_flush(WarpBuf &B, const RolloutArgs &A, const WarpStage &W, FastCounters &c, uint32_t which) {
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0u;
+    if (lane < 4u) {
+        const uint32_t n = (B.cnt >> (8u * lane)) & 0xFFu;
+        if (n && ((which >> lane) & 1u)) {
+            if (kDirect && lane < 2u) base = ring_slot(atomicAdd(A.ring_total[lane], (unsigned long long)n), A.ring_cap, A.ring_magic);
+            else base = atomicAdd(W.cnt + lane * W.n_seg, n);
+        }
+    }
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, 0), b1 = __shfl_sync(0xFFFFFFFFu, base, 1);
+    const uint32_t b2 = __shfl_sync(0xFFFFFFFFu, base, 2), b3 = __shfl_sync(0xFFFFFFFFu, base, 3);
+    int drop = 0;
+    if (which & 1u) buf_copy<kDirect, kBufRL>(B.b, B.cnt & 0xFFu, W.rl0, b0, W.cap_rl, drop);
+    if (which & 2u) buf_copy<kDirect, kBufRL>(B.b + kOffRL1, (B.cnt >> 8) & 0xFFu, W.rl1, b1, W.cap_rl, drop);
+    if (which & 4u) buf_copy<false, kBufSL>(B.b + kOffSL0, (B.cnt >> 16) & 0xFFu, W.sl0, b2, W.cap_sl, drop);
+    if (which & 8u) buf_copy<false, kBufSL>(B.b + kOffSL1, B.cnt >> 24, W.sl1, b3, W.cap_sl, drop);
+    c.wide.drop += drop;
+    B.cnt &= ~(((which & 1u) ? 0xFFu : 0u) | ((which & 2u) ? 0xFF00u : 0u) | ((which & 4u) ? 0xFF0000u : 0u) | ((which & 8u) ? 0xFF000000u : 0u));
+    __syncwarp();
 }
 
 // a step's records into the warp's buffers (what warp_append does with global atomics).  All lanes call it.
 template <bool kDirect>
 __device__ __forceinline__ void buf_append(WarpBuf &B, const RolloutArgs &A, const WarpStage &W, const FastDecision &d,
                                            const FastRecords &R, float v0, float v1, float v2, FastCounters &c) {
-    const uint32_t q = R.q, sh = q * 8u;
-    const uint32_t mine = record_counts(R);
-    const uint32_t incl = warp_scan_bytes(mine);
+    const uint32_t q = R.q;
+    // actor-relative counts: own ring | other ring << 8 | own reservoir << 16; swapping the bytes of each half makes them
+    // absolute (rl0 | rl1 << 8 | sl0 << 16 | sl1 << 24) for player 1
+    const uint32_t rel = ((uint32_t)R.vA + (uint32_t)R.vB) | (uint32_t)R.vC << 8 | (uint32_t)R.vS << 16;
+    const uint32_t mine = q ? __byte_perm(rel, 0u, 0x2301u) : rel;
+    const uint32_t incl = warp_scan_bytes_p(mine);
     const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const uint32_t t0 = tot & 0xFFu, t1 = (tot >> 8) & 0xFFu, t2 = (tot >> 16) & 0xFFu, t3 = tot >> 24;
-    // make room first (warp-uniform branches; rare)
-    buf_flush_rl<kDirect>(B, A, W, c, B.n0 + t0 > (uint32_t)kBufRL, B.n1 + t1 > (uint32_t)kBufRL);
-    buf_flush_sl(B, W, c, B.m0 + t2 > (uint32_t)kBufSL, B.m1 + t3 > (uint32_t)kBufSL);
-    const uint32_t excl = incl - mine;
-    uint4 *rp = q ? B.rl1 : B.rl0, *ro = q ? B.rl0 : B.rl1, *sp = q ? B.sl1 : B.sl0;
-    uint32_t off = (q ? B.n1 : B.n0) + ((excl >> sh) & 0xFFu);
-    if (R.vA) rp[off++] = make_uint4(d.snap_a, d.obs, 0u, d.meta_a);
-    if (R.vB) rp[off] = R.recB;
-    if (R.vC) ro[(q ? B.n0 : B.n1) + ((excl >> (8u - sh)) & 0xFFu)] = R.recC;
-    if (R.vS) sp[(q ? B.m1 : B.m0) + ((excl >> (16u + sh)) & 0xFFu)] = make_uint4(d.obs, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2));
-    B.n0 += t0; B.n1 += t1; B.m0 += t2; B.m1 += t3;
+    // a list that cannot take this step's records is flushed first (warp-uniform, rare): byte > 112 <=> bit 7 of byte + 15,
+    // byte > 32 <=> bit 7 of byte + 95 (no byte carries: <= 112 + 64 and <= 32 + 32)
+    const uint32_t over = (B.cnt + tot + 0x5F5F0F0Fu) & 0x80808080u;
+    if (over) {
+        uint32_t which = ((over >> 7) & 1u) | ((over >> 14) & 2u) | ((over >> 21) & 4u) | ((over >> 28) & 8u);
+        if (which & 3u) which |= 3u;  // the two rings fill at the same pace: claim for both in one round trip
+        buf_flush<kDirect>(B, A, W, c, which);
+    }
+    const uint32_t pos = B.cnt + (incl - mine);                       // absolute positions, bytewise
+    const uint32_t prel = q ? __byte_perm(pos, 0u, 0x2301u) : pos;    // own ring | other ring | own reservoir
+    uint32_t own = q * kOffRL1 + (prel & 0xFFu);
+    if (R.vA) B.b[own++] = make_uint4(d.snap_a, d.obs, 0u, d.meta_a);
+    if (R.vB) B.b[own] = R.recB;
+    if (R.vC) B.b[(q ^ 1u) * kOffRL1 + ((prel >> 8) & 0xFFu)] = R.recC;
+    if (R.vS) B.b[kOffSL0 + q * (uint32_t)kBufSL + ((prel >> 16) & 0xFFu)] = make_uint4(d.obs, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2));
+    B.cnt += tot;
 }
 
 template <bool kDebug, bool kDirect>
@@ -159,7 +185,7 @@ rollout_states_kernel(const RolloutArgs A) {
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const uint32_t lane = threadIdx.x & 31u;
     WarpBuf B;
-    B.init(reinterpret_cast<uint4 *>(s_tab) + kStateQuads + (threadIdx.x >> 5) * kWarpBufQuads);
+    B.b = reinterpret_cast<uint4 *>(s_tab) + kStateQuads + (threadIdx.x >> 5) * kWarpBufQuads;
     WarpStage W;
     W.init(A, 0u, kDirect);
     const int64_t n_blocks = (A.n + 31) >> 5;  // CTA c owns blocks c, c + grid, ...; its warps take them dynamically
@@ -197,10 +223,9 @@ rollout_states_kernel(const RolloutArgs A) {
         if (live) A.state[i] = g.pack();
         c.wide.trans += live ? A.n_steps : 0;
         // a block's staged records belong to the block's segment; the rings have no segments, their records stay buffered
-        if (!kDirect) buf_flush_rl<false>(B, A, W, c, true, true);
-        buf_flush_sl(B, W, c, true, true);
+        buf_flush<kDirect>(B, A, W, c, kDirect ? 12u : 15u);
     }
-    if (kDirect) buf_flush_rl<true>(B, A, W, c, true, true);
+    if (kDirect) buf_flush<true>(B, A, W, c, 3u);
     if (!image_ready) mbar_wait(bar, 0);  // the copy into this CTA's shared memory must land before the CTA exits
     c.spill();
     if (A.stats) c.wide.commit(s_stats, A.stats);
@@ -223,7 +248,7 @@ int nfsp_rollout_states_configure() {
 // rebuilds the state table from the table image (both live in d_wpack) when the weights have changed since
 int nfsp_states_ensure(nfsp_env_t h, const float *d_tab, float *d_states, cudaStream_t st) {
     if (!h->st_dirty) return NFSP_OK;
-    states_pack_kernel<<<(kStateQuads + 127) / 128, 128, 0, st>>>(d_tab, reinterpret_cast<float4 *>(d_states));
+    states_pack_kernel<<<(kStateQuads + 31) / 32, 32, 0, st>>>(d_tab, reinterpret_cast<float4 *>(d_states));
     NFSP_LAUNCH_CHECK();
     h->st_dirty = false;
     return NFSP_OK;
