@@ -40,6 +40,11 @@ BYTES_PER_TRANSITION = 33.6  # SURVEY 8d cfg 3: state 16 + RL record 16 + eta * 
 ENV_BYTES_PER_TRANSITION = 28.0  # SURVEY 8d cfg 2: state 16 + 12-byte trace record
 
 
+KERNEL_OF_VARIANT = {"default": "rollout_states_kernel", "states": "rollout_states_kernel", "cuda": "rollout_kernel",
+                     "tcgen05": "rollout_tc_kernel", "tcgen05_ws": "rollout_tq_kernel", "sorted": "rollout_sorted_kernel",
+                     "pairs": "rollout_pairs_kernel"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,6 +242,9 @@ def workload_config():
             "games_per_gpu": GAMES_PER_GPU, "decisions_per_step": T_PER_CALL, "l2": "flushed between timed steps",
             "records": "RL records written straight into the rings by the rollout kernel (direct_rings), SL records "
                        "staged and moved into the reservoirs by one insert launch",
+            "nets": "default variant: the four nets are evaluated on the 702 decision states of the game (4 x 702 forwards, same "
+                    "arithmetic as the per-decision kernel) and the decisions read that table; the table is rebuilt from the "
+                    "weights inside every timed step.  extra.other_variants.cuda is the per-decision evaluation",
             "baseline_config": "BASELINE.json configs[4] per GPU (configs[2] at 1M games)"}
 
 
@@ -314,7 +322,7 @@ def run_gpu(args):
     game0, n = sharding.shard_games(GAMES_PER_GPU * world, rank, world)
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
                             sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
-                            direct_rings=args.variant in ("default", "cuda", "pairs"))
+                            direct_rings=args.variant in ("default", "states", "cuda", "pairs"))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
     stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
@@ -343,6 +351,14 @@ def run_gpu(args):
             a.record()
             # e2e: pinned host -> device copy of the four nets and the rebuild of the kernels' weight image, in the same
             # library call that launches the rollout
+            # value: the nets are resident in HBM; everything the kernels derive from them -- the weight images and, for the
+            # default variant, the table of the nets' outputs on the 702 decision states -- is rebuilt from them inside the
+            # timed region of EVERY step (as after a learner update): no step runs on outputs computed before its timer
+            a2 = a
+            if not e2e:
+                sp.set_weights(sp.weights)
+                a2 = ev()
+                a2.record()
             sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None)
             b.record()
             sp.flush()
@@ -352,7 +368,7 @@ def run_gpu(args):
             c.record()
             c.synchronize()
             tot_ms += a.elapsed_time(c)
-            ker_ms += a.elapsed_time(b)
+            ker_ms += a2.elapsed_time(b)
         return tot_ms, ker_ms
 
     timed_steps(args.warmup, False)
@@ -483,7 +499,7 @@ def run_gpu(args):
     buffers = buffer_kernels(nfsp_b200, dev, ev) if world == 1 else None
     # the other variants of the rollout kernel, kernel only, for the record
     others = {}
-    for other in ("pairs", "sorted", "tcgen05", "tcgen05_ws"):
+    for other in ("states", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"):
         spo = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=1 << 16,
                                  sl_capacity=1 << 16, max_steps_per_call=T_PER_CALL, variant=other)
         other_ms = 0.0
@@ -527,21 +543,31 @@ def run_gpu(args):
     hbm, which = peaks()
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
-    roofline = {"bound": "hbm", "kernel": {"tcgen05": "rollout_tc_kernel", "tcgen05_ws": "rollout_tq_kernel", "sorted": "rollout_sorted_kernel", "pairs": "rollout_pairs_kernel"}.get(args.variant, "rollout_kernel"), "achieved": achieved, "peak": hbm, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": KERNEL_OF_VARIANT[args.variant], "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_transition": BYTES_PER_TRANSITION,
                 "kernel_ms_per_launch": ker_ms / args.steps,
-                # what a dense 30x64 + 64x3 evaluation would cost; the kernel's first layer is two row adds, not 1 920 MACs
-                "dense_equivalent_tflops": kernel_rate * 4224 / 1e12}
+                "kernel_ms_note": "events around the rollout launch alone"}
+    if args.variant not in ("default", "states"):
+        # what a dense 30x64 + 64x3 evaluation per decision would cost; the kernel's first layer is two row adds, not 1 920 MACs
+        roofline["dense_equivalent_tflops"] = kernel_rate * 4224 / 1e12
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         tf = json.load(open(traffic_file))
-        roofline["traffic"] = tf.get("rollout_kernel_bytes_per_launch")
-        if args.variant in ("default", "cuda") and "rollout_kernel_ncu" in tf:
-            # what really bounds the kernel (ncu, not measured in this run): each decision has to bring 2 x 256 B of
-            # first-layer rows and 768 B of second-layer weights from shared memory into registers
-            roofline["limiter"] = "shared memory -> register bandwidth (LDS.128 instructions), not HBM"
-            roofline["ncu"] = tf["rollout_kernel_ncu"]
+        if args.variant in ("default", "states"):
+            roofline["traffic"] = tf.get("rollout_states_kernel_bytes_per_launch")
+            if "rollout_states_kernel_ncu" in tf:
+                # what bounds the kernel (ncu, not measured in this run): the game logic, Philox and the record append are
+                # integer instructions on the ALU pipe; DRAM carries the records and the game words only
+                roofline["limiter"] = "instruction issue on the integer ALU pipe, not HBM"
+                roofline["ncu"] = tf["rollout_states_kernel_ncu"]
+        elif args.variant == "cuda":
+            roofline["traffic"] = tf.get("rollout_kernel_bytes_per_launch")
+            if "rollout_kernel_ncu" in tf:
+                # each decision has to bring 2 x 256 B of first-layer rows and 768 B of second-layer weights from shared
+                # memory into registers
+                roofline["limiter"] = "shared memory -> register bandwidth (LDS.128 instructions), not HBM"
+                roofline["ncu"] = tf["rollout_kernel_ncu"]
     cpu, cpu_extra = None, {}
     if world == 1:
         cores = max(1, os.cpu_count() or 1)
@@ -598,7 +624,9 @@ def run_gpu(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 2 * args.steps,  # rollout_kernel (records into the rings in place) + insert_kernel (both reservoirs)
+            # per step: pack_images_kernel + states_pack_kernel (the nets' images and state table, rebuilt every step),
+            # rollout_states_kernel (records into the rings in place), insert_kernel (both reservoirs)
+            "gpu_launches": (4 if args.variant in ("default", "states") else 3) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "parity_checked": parity_ok, "parity": parity_info,
             # the iteration that communicates (BASELINE configs[4]): rollout + memories + update_strategy() of both agents
@@ -639,8 +667,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="default", choices=["default", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
-                    help="rollout kernel: CUDA-core row sums (default), net-sorted warp groups, tcgen05 tensor-core tiles")
+    ap.add_argument("--variant", default="default", choices=["default", "states", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
+                    help="rollout kernel: table of the nets' outputs per decision state (default), per-decision CUDA-core row sums, "
+                         "net-sorted warp groups, tcgen05 tensor-core tiles")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -173,10 +173,14 @@ typedef struct {
                              net-homogeneous M128 N64 tiles -> epilogue warpgroups (TMEM -> relu -> 64x3 with W2 from
                              the constant bank), 4 = CUDA cores with net-sorted warp groups (see below), 5 = CUDA cores, two
                              games per lane, the second layer's weights loaded once for a pair of same-net decisions
-                             (csrc/rollout_pairs.cu), 0 = library default */
-    int32_t reserve_sms;  /* variants 1, 3, 4 and 5: SMs left free for kernels of other streams (the learner's fit running
+                             (csrc/rollout_pairs.cu), 6 = no per-decision forward at all: the nets' outputs on the 702
+                             decision states of the game, recomputed by a 2 808-thread launch whenever the weights have
+                             changed (same arithmetic as variant 1), one 16-byte shared-memory read per decision, records
+                             collected in warp-private shared-memory buffers (csrc/rollout_states.cu: the default),
+                             0 = library default */
+    int32_t reserve_sms;  /* variants 1, 3, 4, 5 and 6: SMs left free for kernels of other streams (the learner's fit running
                              beside the rollout); the persistent grid is sm_count - reserve_sms CTAs.  0 = use them all */
-    /* variants 1, 4 and 5, all NULL / 0 otherwise: the RL records go straight into the players' rings instead of d_rl
+    /* variants 1, 4, 5 and 6, all NULL / 0 otherwise: the RL records go straight into the players' rings instead of d_rl
      * (ReplayBuffer.add, replay_buffer.py:30-41, done by the rollout kernel itself): ticket = atomic add on
      * *d_ring_total[p] (records ever inserted, advanced by the kernel), slot = ticket % ring_cap.  d_rl is not
      * written and needs no nfsp_ring_insert afterwards.  Requires 2 * n * n_steps <= ring_cap: the records of one
@@ -193,7 +197,7 @@ typedef struct {
  * with one set of atomics per group: n_segments must be 1 (csrc/rollout_sorted.cu).  An experiment kept for the record:
  * an LDS.128 costs four shared-memory cycles whatever its lanes read, so net-homogeneous warps save nothing
  * (profiles/r02/sorted_rollout_notes.txt) */
-#define NFSP_ROLLOUT_DEFAULT_VARIANT 1
+#define NFSP_ROLLOUT_DEFAULT_VARIANT 6
 
 /* The fused hot path: for n_steps, every game does one Agent.play decision (agent.py:130-156)
  * -- observe, remember the previous transition, eta-mixed policy (average net argmax /

@@ -208,7 +208,8 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
     NFSP_LAUNCH_CHECK();
     h->tc_dirty = h->tq_dirty = h->st_dirty = true;
     h->has_weights = true;
-    return NFSP_OK;
+    // the default rollout's table of the nets' outputs per decision state, from the table image just built
+    return nfsp_states_ensure(h, h->d_wpack + kPackFloats, h->d_states, (cudaStream_t)stream);
 }
 
 int nfsp_ensure_tc_images(nfsp_env_t h, bool tq, cudaStream_t st) {

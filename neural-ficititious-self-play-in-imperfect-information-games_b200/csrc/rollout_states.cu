@@ -11,8 +11,8 @@
 //
 // Everything around the forward -- fast_begin / fast_finish, block ownership, the staged or direct append, the
 // counters -- is variant 1's, so the records, game words and counters are those of variant 1 run on the same score
-// vectors; the score vectors differ from variant 1's only by the summation order of a lane's rotation (1e-5 parity
-// against the oracle, tests/test_gpu_act.py, tests/test_gpu_baseline_sizes.py).
+// vectors; the score vectors differ from variant 1's only by the summation order of a lane's rotation (held to 1e-5
+// of the CPU restatement in tests/test_gpu_act.py and tests/test_gpu_baseline_sizes.py).
 #include "rollout_fast.cuh"
 #include "rollout_tables.cuh"
 #include "ptx_helpers.cuh"
