@@ -91,20 +91,30 @@ struct FastRecords {
 
 // agent.py:142-156 after the forward + main.py:55-67 terminal observations; the records are returned, not appended.
 // `live` masks everything a phantom lane could emit.
+// np.argmax (first maximum) of a score vector | (np.average != 0, agent.py:134) << 2
+__device__ __forceinline__ uint32_t score_action(float v0, float v1, float v2) {
+    uint32_t a = 0u;
+    float best = v0;
+    if (v1 > best) { a = 1u; best = v1; }
+    if (v2 > best) a = 2u;
+    return a | (uint32_t)((v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f)) << 2;
+}
+
+// `pre`: score_action() of (v0, v1, v2) when the caller already has it (the state table stores it beside the scores),
+// kNoAction otherwise; a debug launch always recomputes it (the scores may be forced)
+constexpr uint32_t kNoAction = 0xFFFFFFFFu;
 template <bool kDebug>
 __device__ __forceinline__ void fast_decide(NfspFast &g, const FastLuts &L, const RolloutArgs &A, const FastDecision &d,
                                             float &v0, float &v1, float &v2, bool live, int64_t at, int64_t plane,
-                                            FastCounters &c, FastRecords &R) {
+                                            FastCounters &c, FastRecords &R, uint32_t pre = kNoAction) {
     if (kDebug && live) {
         if (A.vec) { A.vec[3 * at] = v0; A.vec[3 * at + 1] = v1; A.vec[3 * at + 2] = v2; }
         if (A.forced) { v0 = A.forced[3 * at]; v1 = A.forced[3 * at + 1]; v2 = A.forced[3 * at + 2]; }
     }
     const uint32_t q = g.p();
-    int a = 0;  // np.argmax: first maximum
-    float best = v0;
-    if (v1 > best) { a = 1; best = v1; }
-    if (v2 > best) a = 2;
-    const bool nz = (v0 != 0.f) || (v1 != 0.f) || (v2 != 0.f);
+    const uint32_t an = (kDebug || pre == kNoAction) ? score_action(v0, v1, v2) : pre;
+    const int a = (int)(an & 3u);
+    const bool nz = (an & 4u) != 0u;
     const int eff = (int)(g.step(L.step, a, nz) & 3u);
     c.small += live ? 1u << (5u * (3u * q + (uint32_t)a)) : 0u;
     bool vB = false, vC = false;

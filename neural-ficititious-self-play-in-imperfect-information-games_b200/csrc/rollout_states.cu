@@ -1,7 +1,7 @@
 // K2, variant 6: the fused rollout over a table of the nets' outputs on every decision state.
 //
 // Under main.train's turn order (the precondition of the factorised first layer, rollout_tables.cuh) the observation a
-// net sees at a decision is one of 702 values: the actor's card, the dealer and the betting sequence so far in round 0
+// net sees at a decision is one of 702 values (kept in 1 296 table slots so that one formula indexes both rounds): the actor's card, the dealer and the betting sequence so far in round 0
 // (54), or card, public card, dealer, the finished round-0 sequence and the round-1 sequence so far (648).  A net is a
 // pure function of the observation, so its three outputs on all 702 of them -- 4 nets x 702 forwards, built by
 // states_pack_kernel from the SAME table image and with the SAME arithmetic (mlp_forward_tables, rotation 0) every time
@@ -19,22 +19,20 @@
 
 namespace nfsp {
 
-constexpr int kNetStates = 54 + 72 * 9;          // 702
-constexpr int kStateQuads = 4 * kNetStates;      // one float4 {o0, o1, o2, 0} per net and state
-constexpr int kStateBytes = kStateQuads * 16;    // 44 928
+// Table slot of a decision state: x * 18 + sigma, x = ((card * 3 + public card) * 2 + dealer) * 4 + finished round-0
+// sequence, sigma = 9 * round + sequence id.  One formula for both rounds, no branch in the step loop: round 0 does not see
+// the public card and has no finished sequence yet (f = 0), so its 54 states are stored once per public card; slots with
+// round 0 and f != 0 are never read.  702 distinct states in 72 * 18 = 1 296 slots per net.
+constexpr int kNetStates = 72 * 18;
+constexpr int kStateQuads = 4 * kNetStates;      // one float4 {o0, o1, o2, argmax | non-zero << 2} per net and slot
+constexpr int kStateBytes = kStateQuads * 16;    // 82 944
 static_assert(kStateBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-// decision state -> rows of the factorised first layer (the inverse of the index the rollout computes)
+// table slot -> rows of the factorised first layer (the inverse of the index the rollout computes)
 __device__ __forceinline__ void state_rows(int s, uint32_t &xrow, uint32_t &yrow) {
-    if (s < 54) {  // (card * 2 + dealer) * 9 + sequence id
-        const int sg = s % 9, cd = s / 9;
-        xrow = (uint32_t)(cd >> 1);
-        yrow = 75u + (uint32_t)(cd & 1) * 18u + (uint32_t)sg;
-    } else {       // 54 + x * 9 + round-1 sequence id, x = ((card * 3 + pub) * 2 + dealer) * 4 + finished round-0 sequence
-        const int sg = (s - 54) % 9, x = (s - 54) / 9;
-        xrow = 3u + (uint32_t)x;
-        yrow = 75u + (uint32_t)((x >> 2) & 1) * 18u + 9u + (uint32_t)sg;
-    }
+    const uint32_t sg = (uint32_t)s % 18u, x = (uint32_t)s / 18u, dl = (x >> 2) & 1u;
+    xrow = sg >= 9u ? 3u + x : x / 24u;  // round 0: the private card alone
+    yrow = 75u + dl * 18u + sg;
 }
 
 __global__ void states_pack_kernel(const float *__restrict__ tab, float4 *__restrict__ states) {
@@ -44,7 +42,7 @@ __global__ void states_pack_kernel(const float *__restrict__ tab, float4 *__rest
     state_rows(e % kNetStates, xrow, yrow);
     float o0, o1, o2;
     mlp_forward_tables(tab, xrow, yrow, (uint32_t)(e / kNetStates), 0u, o0, o1, o2);
-    states[e] = make_float4(o0, o1, o2, 0.f);
+    states[e] = make_float4(o0, o1, o2, __uint_as_float(score_action(o0, o1, o2)));
 }
 
 constexpr int kStatesThreads = 1024;
@@ -56,8 +54,8 @@ constexpr int kStatesThreads = 1024;
 // 1's 0.37 ms of shared-memory traffic, the bound of this kernel once the forward is a table read.  Here a warp collects
 // its records in shared memory (the table leaves 180 KB free) and claims slots for a whole buffer at a time: one atomic
 // and one coalesced copy (512 B per warp instruction) per ~100 records.
-constexpr int kBufRL = 112, kBufSL = 32;                 // records per player and warp; >= a step's worst case (64, 32)
-constexpr int kWarpBufQuads = 2 * kBufRL + 2 * kBufSL;   // 288 uint4 = 4 608 B per warp
+constexpr int kBufRL = 104, kBufSL = 32;                 // records per player and warp; >= a step's worst case (64, 32)
+constexpr int kWarpBufQuads = 2 * kBufRL + 2 * kBufSL;   // 272 uint4 = 4 352 B per warp
 constexpr int kStatesSmemBytes = kStateBytes + (kStatesThreads / 32) * kWarpBufQuads * 16;
 static_assert(kBufRL >= 64 && kBufSL >= 32, "a buffer must take the records of one step");
 
@@ -136,9 +134,10 @@ __device__ __forceinline__ void buf_append(WarpBuf &B, const RolloutArgs &A, con
     const uint32_t mine = q ? __byte_perm(rel, 0u, 0x2301u) : rel;
     const uint32_t incl = warp_scan_bytes_p(mine);
     const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    // a list that cannot take this step's records is flushed first (warp-uniform, rare): byte > 112 <=> bit 7 of byte + 15,
-    // byte > 32 <=> bit 7 of byte + 95 (no byte carries: <= 112 + 64 and <= 32 + 32)
-    const uint32_t over = (B.cnt + tot + 0x5F5F0F0Fu) & 0x80808080u;
+    // a list that cannot take this step's records is flushed first (warp-uniform, rare): byte > cap <=> bit 7 of
+    // byte + 127 - cap (no byte carries: <= 104 + 64 and <= 32 + 32)
+    constexpr uint32_t kOverRL = 127u - (uint32_t)kBufRL, kOverSL = 127u - (uint32_t)kBufSL;
+    const uint32_t over = (B.cnt + tot + (kOverRL | kOverRL << 8 | kOverSL << 16 | kOverSL << 24)) & 0x80808080u;
     if (over) {
         uint32_t which = ((over >> 7) & 1u) | ((over >> 14) & 2u) | ((over >> 21) & 4u) | ((over >> 28) & 8u);
         if (which & 3u) which |= 3u;  // the two rings fill at the same pace: claim for both in one round trip
@@ -201,21 +200,21 @@ rollout_states_kernel(const RolloutArgs A) {
         W.init(A, (uint32_t)(base >> 5) & (A.n_seg - 1u), kDirect);
         NfspFast g;
         g.unpack(live ? A.state[i] : 0ull);
+        if (!image_ready) {  // the table's copy ran beside the set-up and the first loads of the game words
+            mbar_wait(bar, 0);
+            image_ready = true;
+        }
         for (int t = 0; t < A.n_steps; ++t) {
             FastDecision d;
             fast_begin(g, s_lut, A, game, A.step0 + (uint64_t)t, live, d, c);
-            const uint32_t sg = g.sigma(), dl = g.dealer(), ca = (g.PA >> 11) & 3u;
-            const uint32_t s = sg >= 9u ? 54u - 9u + (((((ca * 3u + g.pub()) * 2u + dl) << 2) | g.fin0()) * 9u + sg)
-                                        : (ca * 2u + dl) * 9u + sg;
-            if (!image_ready) {
-                mbar_wait(bar, 0);
-                image_ready = true;
-            }
-            const float4 o = s_tab[(g.p() * 2u + (uint32_t)d.pol) * (uint32_t)kNetStates + s];
+            const uint32_t ca = (g.PA >> 11) & 3u;
+            const uint32_t x = (((ca * 3u + g.pub()) * 2u + g.dealer()) << 2) | g.fin0();
+            const float4 o = s_tab[(g.p() * 2u + (uint32_t)d.pol) * (uint32_t)kNetStates + x * 18u + g.sigma()];
             float v0 = o.x, v1 = o.y, v2 = o.z;
-            if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; }
+            uint32_t pre = __float_as_uint(o.w);
+            if (d.random) { v0 = d.r0; v1 = d.r1; v2 = d.r2; pre = score_action(v0, v1, v2); }
             FastRecords R;
-            fast_decide<kDebug>(g, s_lut, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c, R);
+            fast_decide<kDebug>(g, s_lut, A, d, v0, v1, v2, live, (int64_t)t * A.n + i, plane, c, R, pre);
             buf_append<kDirect>(B, A, W, d, R, v0, v1, v2, c);
             if ((t & 15) == 15) c.spill();
         }
