@@ -354,12 +354,7 @@ def run_gpu(args):
             # value: the nets are resident in HBM; everything the kernels derive from them -- the weight images and, for the
             # default variant, the table of the nets' outputs on the 702 decision states -- is rebuilt from them inside the
             # timed region of EVERY step (as after a learner update): no step runs on outputs computed before its timer
-            a2 = a
-            if not e2e:
-                sp.set_weights(sp.weights)
-                a2 = ev()
-                a2.record()
-            sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None)
+            sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
             b.record()
             sp.flush()
             if e2e:  # the learner's four minibatches and the counters come back to the host: one slab, one copy each
@@ -368,7 +363,7 @@ def run_gpu(args):
             c.record()
             c.synchronize()
             tot_ms += a.elapsed_time(c)
-            ker_ms += a2.elapsed_time(b)
+            ker_ms += a.elapsed_time(b)
         return tot_ms, ker_ms
 
     timed_steps(args.warmup, False)
@@ -541,13 +536,17 @@ def run_gpu(args):
     ms64d, _ = time_64k(1 << 21, True)
     rate64d = (1 << 16) * T_PER_CALL * args.steps / (ms64d * 1e-3)
     hbm, which = peaks()
-    kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)  # this rank's rollout kernel alone
+    # the rollout kernel alone: CUDA events around its launch (for the default variant the timed steps' events also cover the
+    # two small launches that rebuild the images, so its kernel-only figure comes from the per-variant loop above)
+    if args.variant in ("default", "states"):
+        ker_ms = others["states"]["kernel_ms_per_launch"] * args.steps
+    kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
     roofline = {"bound": "hbm", "kernel": KERNEL_OF_VARIANT[args.variant], "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_transition": BYTES_PER_TRANSITION,
                 "kernel_ms_per_launch": ker_ms / args.steps,
-                "kernel_ms_note": "events around the rollout launch alone"}
+                "kernel_ms_note": "CUDA events around the rollout kernel's launch alone, L2 flushed before each launch"}
     if args.variant not in ("default", "states"):
         # what a dense 30x64 + 64x3 evaluation per decision would cost; the kernel's first layer is two row adds, not 1 920 MACs
         roofline["dense_equivalent_tflops"] = kernel_rate * 4224 / 1e12

@@ -206,7 +206,9 @@ typedef struct {
  * atomics; move them into the memories with nfsp_ring_insert / nfsp_reservoir_insert. */
 int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilon, const nfsp_rollout_io *io, void *stream);
 /* The learner -> actor hand-over and the rollout in one call (one trip through the binding instead of two at the head of
- * every step): nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream) followed by nfsp_rollout(...). */
+ * every step): nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream) followed by nfsp_rollout(...).  With
+ * h_weights = NULL the nets are already in d_weights (a learner on the same device has just written them):
+ * nfsp_act_set_weights(h, d_weights, stream) followed by nfsp_rollout(...). */
 int nfsp_rollout_with_weights(nfsp_env_t h, const float *h_weights, float *d_weights, int n_steps, double eta, double epsilon,
                               const nfsp_rollout_io *io, void *stream);
 /* Tuning of variant 3: SM cycles a partly filled tile of an average-policy / a best-response net may wait for more rows

@@ -479,13 +479,16 @@ class SelfPlay:
 
     VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4, "pairs": 5, "states": 6}
 
-    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None):
+    def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None,
+                refresh_weights=False):
         """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
         net), "tcgen05" / "tcgen05_ws" (first layer as tensor-core tiles with the accumulator in TMEM) or None =
         self.variant.  reserve_sms: SMs the persistent rollout grid
         leaves to kernels of other streams (the learner beside it, PipelinedTrainer).  weights_host: a pinned float32
         [4, 2179] host tensor with new acting nets -- copied to the device and packed by the same library call that launches
-        the rollout (`set_weights(host tensor)` + `rollout()` in one trip through the binding)."""
+        the rollout (`set_weights(host tensor)` + `rollout()` in one trip through the binding).  refresh_weights: the
+        device tensor self.weights has been written in place (a learner update): rebuild the kernels' images from it in the
+        same library call (`set_weights(self.weights)` + `rollout()` in one trip)."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
         want_debug = debug or forced_vec is not None
@@ -526,6 +529,9 @@ class SelfPlay:
                 raise ValueError("weights_host must be a contiguous float32 [4, 2179] host tensor")
             self._host_src = weights_host  # the copy is asynchronous: keep the source alive until the next hand-over
             check(lib().nfsp_rollout_with_weights(self.env._h, C.c_void_p(weights_host.data_ptr()), _ptr(self.weights), n_steps,
+                                                  self.eta, self.epsilons[0], C.byref(io), _stream(self.device)))
+        elif refresh_weights:
+            check(lib().nfsp_rollout_with_weights(self.env._h, None, _ptr(self.weights), n_steps,
                                                   self.eta, self.epsilons[0], C.byref(io), _stream(self.device)))
         else:
             check(lib().nfsp_rollout(self.env._h, n_steps, self.eta, self.epsilons[0], C.byref(io), _stream(self.device)))

@@ -352,7 +352,7 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
 
 extern "C" int nfsp_rollout_with_weights(nfsp_env_t h, const float *h_weights, float *d_weights, int n_steps, double eta,
                                          double epsilon, const nfsp_rollout_io *io, void *stream) {
-    const int rc = nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream);
+    const int rc = h_weights ? nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream) : nfsp_act_set_weights(h, d_weights, stream);
     if (rc != NFSP_OK) return rc;
     return nfsp_rollout(h, n_steps, eta, epsilon, io, stream);
 }
