@@ -240,6 +240,7 @@ def workload_config():
                         "ring %d + reservoir %d records per player, sample %d" %
                         (GAMES_PER_GPU, T_PER_CALL, ETA, EPS, RL_CAP, SL_CAP, BATCH),
             "games_per_gpu": GAMES_PER_GPU, "decisions_per_step": T_PER_CALL, "l2": "flushed between timed steps",
+            "memories": "both reservoirs are filled by untimed steps first: every timed insert is Algorithm R's random replacement",
             "records": "RL records written straight into the rings by the rollout kernel (direct_rings), SL records "
                        "staged and moved into the reservoirs by one insert launch",
             "nets": "default variant: the four nets are evaluated on the 702 decision states of the game (4 x 702 forwards, same "
@@ -366,6 +367,13 @@ def run_gpu(args):
             ker_ms += a.elapsed_time(b)
         return tot_ms, ker_ms
 
+    # steady state of the memories before anything is timed: both reservoirs full, so that every timed insert is
+    # Algorithm R's random replacement (the expensive regime: ~26 us per step while a reservoir still fills by appending,
+    # ~45 us once it replaces, profiles/time_flush.py); value and e2e are then measured in the same regime
+    prefill = 0
+    while min(int(m.total.item()) for m in sp.sl) < SL_CAP and prefill < 200:
+        sp.rollout(T_PER_CALL)
+        prefill += 1
     timed_steps(args.warmup, False)
     sampler = ClockSampler(local)
     if rank == 0:
