@@ -4,8 +4,8 @@
 // net sees at a decision is one of 702 values (kept in 1 296 table slots so that one formula indexes both rounds): the actor's card, the dealer and the betting sequence so far in round 0
 // (54), or card, public card, dealer, the finished round-0 sequence and the round-1 sequence so far (648).  A net is a
 // pure function of the observation, so its three outputs on all 702 of them -- 4 nets x 702 forwards, built by
-// states_pack_kernel from the SAME table image and with the SAME arithmetic (mlp_forward_tables, rotation 0) every time
-// the weights change -- stand for the 8.4 M forwards of a 2^20-game x 8-step launch.  A decision then costs ONE 16-byte
+// states_pack_kernel from the SAME table image and with the same operations (two rows added, relu, FFMA2 second layer,
+// head; the 16 hidden-unit quads summed in four interleaved groups) every time the weights change -- stand for the 8.4 M forwards of a 2^20-game x 8-step launch.  A decision then costs ONE 16-byte
 // shared-memory read instead of variant 1's 80 (32 row quads + 48 W2 quads, which bound that kernel: an LDS.128 holds
 // the pipe for four cycles), and what is left is the game logic, Philox and the record append.
 //
@@ -35,14 +35,36 @@ __device__ __forceinline__ void state_rows(int s, uint32_t &xrow, uint32_t &yrow
     yrow = 75u + dl * 18u + sg;
 }
 
+// One table slot per FOUR lanes: lane j of a quad takes hidden-unit quads j, j + 4, j + 8, j + 12 of mlp_forward_tables'
+// loop (two table rows added, relu, FFMA2 second layer), the three partial sums are combined with two shuffles, lane 0
+// applies the head.  All 20 loads of a lane are in flight at once: the launch is ~3 us on the step path.
 __global__ void states_pack_kernel(const float *__restrict__ tab, float4 *__restrict__ states) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= kStateQuads) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, e = t >> 2, j = t & 3;
+    const bool valid = e < kStateQuads;  // the grid is a whole number of warps: every lane reaches the shuffles
     uint32_t xrow, yrow;
-    state_rows(e % kNetStates, xrow, yrow);
-    float o0, o1, o2;
-    mlp_forward_tables(tab, xrow, yrow, (uint32_t)(e / kNetStates), 0u, o0, o1, o2);
-    states[e] = make_float4(o0, o1, o2, __uint_as_float(score_action(o0, o1, o2)));
+    state_rows(valid ? e % kNetStates : 0, xrow, yrow);
+    const uint32_t net = valid ? (uint32_t)(e / kNetStates) : 0u;
+    const float4 *T = reinterpret_cast<const float4 *>(tab);
+    const float4 *xr = T + (net * kNetRows + xrow) * kRowQuads, *yr = T + (net * kNetRows + yrow) * kRowQuads;
+    const float4 *wr = T + kTabRows * kRowQuads + net * (3 * kRowQuads);
+    Layer2Acc acc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int q = j + 4 * k;
+        acc.quad_sum(xr[q], yr[q], wr[q], wr[kRowQuads + q], wr[2 * kRowQuads + q]);
+    }
+    float s0 = hsum2(acc.z0), s1 = hsum2(acc.z1), s2 = hsum2(acc.z2);
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
+        s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+        s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    }
+    if (valid && j == 0) {
+        float o0, o1, o2;
+        Layer2Acc::head_of_sums(s0, s1, s2, reinterpret_cast<const float4 *>(tab + kTabFloats + kTabW2Floats)[net], net & 1u, o0, o1, o2);
+        states[e] = make_float4(o0, o1, o2, __uint_as_float(score_action(o0, o1, o2)));
+    }
 }
 
 constexpr int kStatesThreads = 1024;
@@ -247,7 +269,7 @@ int nfsp_rollout_states_configure() {
 // rebuilds the state table from the table image (both live in d_wpack) when the weights have changed since
 int nfsp_states_ensure(nfsp_env_t h, const float *d_tab, float *d_states, cudaStream_t st) {
     if (!h->st_dirty) return NFSP_OK;
-    states_pack_kernel<<<(kStateQuads + 31) / 32, 32, 0, st>>>(d_tab, reinterpret_cast<float4 *>(d_states));
+    states_pack_kernel<<<(4 * kStateQuads + 127) / 128, 128, 0, st>>>(d_tab, reinterpret_cast<float4 *>(d_states));
     NFSP_LAUNCH_CHECK();
     h->st_dirty = false;
     return NFSP_OK;
