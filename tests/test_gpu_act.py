@@ -600,6 +600,29 @@ def test_rollout_with_weights_from_host_equals_set_weights_then_rollout(nb):
         assert torch.equal(a.rl[p].data, b.rl[p].data) and torch.equal(a.sl[p].data, b.sl[p].data)
 
 
+def test_rollout_refresh_weights_equals_set_weights_then_rollout(nb):
+    """nfsp_rollout_with_weights with h_weights = NULL: the nets were written in place on the device (a learner update); the
+    kernels' images and the state table are rebuilt by the call that launches the rollout.  Without the refresh the rollout
+    would still act on the previous nets."""
+    n, steps = 5000, 6
+    mk = lambda: nb.SelfPlay(n, seed=9, eta=0.3, epsilon=0.1, rl_capacity=1 << 12, sl_capacity=1 << 12, max_steps_per_call=steps,  # noqa: E731
+                             deterministic=True)
+    a, b, stale = mk(), mk(), mk()
+    for k in range(3):
+        w = torch.from_numpy(random_nets(40 + k)).cuda()
+        for sp in (a, b, stale):
+            sp.weights.copy_(w)   # in place: the handle's images are now out of date
+        a.set_weights(a.weights)
+        a.rollout(steps)
+        b.rollout(steps, refresh_weights=True)
+        stale.rollout(steps)
+    torch.cuda.synchronize()
+    assert torch.equal(a.env.state_words(), b.env.state_words()) and a.read_stats() == b.read_stats()
+    for p in range(2):
+        assert torch.equal(a.rl[p].data, b.rl[p].data) and torch.equal(a.sl[p].data, b.sl[p].data)
+    assert not torch.equal(a.env.state_words(), stale.env.state_words())  # the stale images played other actions
+
+
 def test_deterministic_record_order_above_one_warp_per_segment(nb):
     """deterministic=True: one staging segment per block of 32 games, so two runs of one seed leave bit-identical
     memories even where the default layout (1 024 segments shared by several warps) does not fix the order."""
