@@ -67,7 +67,10 @@ __global__ void states_pack_kernel(const float *__restrict__ tab, float4 *__rest
     }
 }
 
-constexpr int kStatesThreads = 1024;
+// 1 024 threads per CTA for launches that keep every warp busy with several blocks of games; 512 (16 warps, 90 registers)
+// when the launch has no more blocks than that gives warps -- a warp then plays one block, and what counts is the latency
+// of its steps, which fewer warps per SM shorten (65 536 games: kernel 24.6 -> 21.3 us)
+constexpr int kStatesThreads = 1024, kStatesThreadsSmall = 512;
 
 // ---- warp-private record buffers -----------------------------------------------------------------
 // Variant 1 claims its slots with four global atomics per warp and step.  That is one round trip per step on every
@@ -78,7 +81,7 @@ constexpr int kStatesThreads = 1024;
 // and one coalesced copy (512 B per warp instruction) per ~100 records.
 constexpr int kBufRL = 104, kBufSL = 32;                 // records per player and warp; >= a step's worst case (64, 32)
 constexpr int kWarpBufQuads = 2 * kBufRL + 2 * kBufSL;   // 272 uint4 = 4 352 B per warp
-constexpr int kStatesSmemBytes = kStateBytes + (kStatesThreads / 32) * kWarpBufQuads * 16;
+constexpr int states_smem_bytes(int threads) { return kStateBytes + (threads / 32) * kWarpBufQuads * 16; }
 static_assert(kBufRL >= 64 && kBufSL >= 32, "a buffer must take the records of one step");
 
 // quad offsets of the four lists in a warp's buffer: RL of player 0 / 1, SL of player 0 / 1
@@ -175,8 +178,8 @@ __device__ __forceinline__ void buf_append(WarpBuf &B, const RolloutArgs &A, con
     B.cnt += tot;
 }
 
-template <bool kDebug, bool kDirect>
-__global__ void __launch_bounds__(kStatesThreads, 1)
+template <bool kDebug, bool kDirect, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
 rollout_states_kernel(const RolloutArgs A) {
     extern __shared__ __align__(128) float4 s_tab[];  // kStateQuads, then the warps' record buffers
     __shared__ unsigned long long s_stats[NFSP_STATS_FIELDS];
@@ -258,12 +261,19 @@ using namespace nfsp;
 
 int nfsp_states_floats() { return kStateQuads * 4; }
 
-int nfsp_rollout_states_configure() {
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatesSmemBytes));
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatesSmemBytes));
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatesSmemBytes));
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatesSmemBytes));
+template <int kThreads>
+static int configure_states() {
+    constexpr int kBytes = states_smem_bytes(kThreads);
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     return NFSP_OK;
+}
+
+int nfsp_rollout_states_configure() {
+    const int rc = configure_states<kStatesThreads>();
+    return rc != NFSP_OK ? rc : configure_states<kStatesThreadsSmall>();
 }
 
 // rebuilds the state table from the table image (both live in d_wpack) when the weights have changed since
@@ -275,13 +285,22 @@ int nfsp_states_ensure(nfsp_env_t h, const float *d_tab, float *d_states, cudaSt
     return NFSP_OK;
 }
 
-int nfsp_rollout_states_launch(nfsp_env_t h, const RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st) {
-    const bool direct = A.ring[0] != nullptr;
-    const int grid = grid_for(h->n, 32, h->sm_count - io->reserve_sms, 1);  // at least one block of 32 games per CTA
-    if (debug && direct) rollout_states_kernel<true, true><<<grid, kStatesThreads, kStatesSmemBytes, st>>>(A);
-    else if (debug) rollout_states_kernel<true, false><<<grid, kStatesThreads, kStatesSmemBytes, st>>>(A);
-    else if (direct) rollout_states_kernel<false, true><<<grid, kStatesThreads, kStatesSmemBytes, st>>>(A);
-    else rollout_states_kernel<false, false><<<grid, kStatesThreads, kStatesSmemBytes, st>>>(A);
+template <int kThreads>
+static int launch_states(const RolloutArgs &A, int grid, bool debug, bool direct, cudaStream_t st) {
+    constexpr int kBytes = states_smem_bytes(kThreads);
+    if (debug && direct) rollout_states_kernel<true, true, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else if (debug) rollout_states_kernel<true, false, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else if (direct) rollout_states_kernel<false, true, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else rollout_states_kernel<false, false, kThreads><<<grid, kThreads, kBytes, st>>>(A);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
+}
+
+int nfsp_rollout_states_launch(nfsp_env_t h, const RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st) {
+    const bool direct = A.ring[0] != nullptr;
+    const int sms = h->sm_count - io->reserve_sms;
+    const int grid = grid_for(h->n, 32, sms, 1);  // at least one block of 32 games per CTA
+    const int64_t blocks = (h->n + 31) / 32;
+    if (blocks <= (int64_t)sms * (kStatesThreadsSmall / 32)) return launch_states<kStatesThreadsSmall>(A, grid, debug, direct, st);
+    return launch_states<kStatesThreads>(A, grid, debug, direct, st);
 }
