@@ -132,6 +132,10 @@ class BatchedNfspEnv(_EnvBase):
         check(lib().nfsp_env_reset(self._h, _ptr(d), self.eta, _stream(self.device)))
 
     def set_hands(self, dealer, cards, policy=None):
+        if not (isinstance(cards, torch.Tensor) and cards.is_cuda):  # host input: ranks are 0 (Ace), 1, 2 (deck.py:21-33)
+            chk = np.asarray(cards)
+            if chk.size and (chk.min() < 0 or chk.max() > 2):
+                raise ValueError("card ranks must be 0, 1 or 2")
         d = _as(dealer, torch.int8, self.device, (self.n,))
         c = _as(cards, torch.int8, self.device, (self.n, 3))
         p = _as(policy, torch.int8, self.device, (self.n, 2))
