@@ -358,9 +358,8 @@ def run_gpu(args):
             sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
             b.record()
             sp.flush()
-            if e2e:  # the learner's four minibatches and the counters come back to the host: one slab, one copy each
-                sp.sample_minibatches(BATCH, to_host=True)
-                stats_host.copy_(sp.stats, non_blocking=True)
+            if e2e:  # the learner's four minibatches and the counters come back to the host in ONE slab, one copy
+                sp.sample_minibatches(BATCH, to_host=True, with_stats=True)
             c.record()
             c.synchronize()
             tot_ms += a.elapsed_time(c)

@@ -584,21 +584,29 @@ class SelfPlay:
         arr, n = self._flush_reqs
         check(lib().nfsp_insert_multi(arr, n, _stream(self.device)))
 
-    def sample_minibatches(self, batch=256, to_host=False):
+    def sample_minibatches(self, batch=256, to_host=False, with_stats=False):
         """sample_batch(batch) of all four memories (replay_buffer.py:46-59, ReservoirBuffer.py:33-43) into ONE
         float32 slab: per player RL s[b,30] a[b,3] r[b] s2[b,30] t[b], then SL s[b,30] a[b,3].  Returns
         (views, slab); with to_host=True the slab lands in a reused pinned host buffer with a single
-        device->host copy (the views then alias the host copy; the caller synchronises the stream)."""
+        device->host copy (the views then alias the host copy; the caller synchronises the stream).
+        with_stats: the rollout counters move to the tail of the slab (self.stats becomes a view of it, the rollout
+        kernel accumulates there), so the same copy brings them to the host: the int64 view slab[-26:] of the result."""
         b = int(batch)
         per = b * (65 + 33)
         key = ("slab", b)
         cache = self.__dict__.setdefault("_mb_cache", {})
         if key not in cache:
-            cache[key] = (torch.empty(2 * per, dtype=torch.float32, device=self.device),
-                          torch.empty(2 * per, dtype=torch.float32).pin_memory(),
+            tail = 2 * _lib.STATS_FIELDS  # room for the counters (int64 = two float32 words each), 8-byte aligned: per is even
+            cache[key] = (torch.empty(2 * per + tail, dtype=torch.float32, device=self.device),
+                          torch.empty(2 * per + tail, dtype=torch.float32).pin_memory(),
                           torch.empty((4, b), dtype=torch.int64, device=self.device),
                           torch.zeros(4, dtype=torch.int32, device=self.device))
         slab, host, idx, cnt = cache[key]
+        if with_stats and self.stats.data_ptr() != slab[2 * per:].data_ptr():
+            home = slab[2 * per:].view(torch.int64)
+            home.copy_(self.stats)
+            self.stats = home
+            self.__dict__.pop("_io", None)  # the rollout's argument block holds the counters' address
         st = _stream(self.device)
         lkey = ("layout", b)
         if lkey not in cache:

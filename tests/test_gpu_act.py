@@ -486,6 +486,24 @@ def test_sample_minibatches_slab_equals_per_memory_samples(nb):
         assert torch.equal(views[p]["sl_s"], s.cpu()) and torch.equal(views[p]["sl_a"], a.cpu())
 
 
+def test_counters_ride_in_the_minibatch_slab(nb):
+    """sample_minibatches(with_stats=True): the rollout counters live at the tail of the slab from then on, so the one
+    device->host copy of the minibatches brings them along; they keep accumulating there."""
+    sp = nb.SelfPlay(4096, seed=6, eta=0.3, epsilon=0.1, rl_capacity=1 << 16, sl_capacity=1 << 12, max_steps_per_call=4)
+    ref = nb.SelfPlay(4096, seed=6, eta=0.3, epsilon=0.1, rl_capacity=1 << 16, sl_capacity=1 << 12, max_steps_per_call=4)
+    sp.rollout(4)
+    ref.rollout(4)
+    before = sp.read_stats()
+    for _ in range(2):
+        views, slab = sp.sample_minibatches(64, to_host=True, with_stats=True)
+        torch.cuda.synchronize()
+        got = slab[-2 * sp.stats.numel():].view(torch.int64)
+        assert got.tolist() == sp.stats.cpu().tolist() and sp.read_stats() == ref.read_stats()
+        sp.rollout(4)
+        ref.rollout(4)
+    assert sp.read_stats() == ref.read_stats() and sp.read_stats()["transitions"] == 3 * before["transitions"]
+
+
 def test_segmented_batches_match_dense_order(nb):
     """A batch staged in segments inserts exactly like the same records staged densely in segment order."""
     rng = np.random.RandomState(8)
