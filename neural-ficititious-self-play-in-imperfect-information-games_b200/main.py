@@ -100,6 +100,8 @@ def main(argv=None):
                     help="terminal transitions bootstrap too (the reference's `t is True` never holds, agent.py:227)")
     ap.add_argument("--deterministic", action="store_true",
                     help="fix the order of the records in the memories (one staging segment per block of 32 games)")
+    ap.add_argument("--variant", default="default", choices=["default", "states", "cuda", "pairs", "tcgen05", "tcgen05_ws"],
+                    help="rollout kernel: the nets tabulated over the game's decision states (default) or evaluated per decision")
     ap.add_argument("--updates-per-call", type=int, default=1,
                     help="update_strategy() calls per rollout call (the reference's cadence: games * steps / 256)")
     args = ap.parse_args(argv)
@@ -116,7 +118,7 @@ def main(argv=None):
     sp = SelfPlay(n, seed=seed, game0=game0, device=dev, eta=cfg.getfloat("Agent", "Eta"),
                   epsilon=cfg.getfloat("Agent", "Epsilon"), rl_capacity=cfg.getint("Agent", "MRLSize"),
                   sl_capacity=cfg.getint("Agent", "MSLSize"), max_steps_per_call=args.steps_per_call,
-                  deterministic=args.deterministic, direct_rings=False if args.deterministic else "auto")
+                  deterministic=args.deterministic, direct_rings=False if args.deterministic else "auto", variant=args.variant)
     learner = Learner(sp, cfg=cfg, terminal_bootstraps=args.terminal_bootstraps, others_to_target=args.others_to_target)
     episodes = args.episodes if args.episodes is not None else cfg.getint("Common", "Episodes")
     rows = train(sp, learner, episodes, args.steps_per_call, args.report_every, world,
