@@ -121,6 +121,35 @@ def test_pipelined_trainer_equals_the_sequential_loop_run_with_one_update_of_lag
     assert La.iteration == Lb.iteration and abs(a.epsilon - b.epsilon) < 1e-15
 
 
+def test_state_table_rollout_trains_like_the_per_decision_rollout(nb):
+    """Self-play with the learner in the loop, once with the nets tabulated over the decision states (the default) and
+    once with a forward per decision: the same games, counters and RL memories after every iteration (the actions agree
+    although the scores differ in their last bits), SL records and trained nets within float rounding of each other."""
+    from nfsp_b200.learner import Learner
+
+    def make(variant):
+        return nb.SelfPlay(4096, seed=17, eta=0.3, epsilon=0.2, rl_capacity=1 << 15, sl_capacity=1 << 15, max_steps_per_call=8,
+                           deterministic=True, variant=variant)
+
+    a, b = make("states"), make("cuda")
+    La, Lb = Learner(a, cfg=nb.load_config(None)), Learner(b, cfg=nb.load_config(None))
+    w0 = a.weights.clone()
+    for j in range(10):
+        a.rollout(8)
+        b.rollout(8)
+        if j >= 2:
+            assert La.update(sync=False)["trained"] == Lb.update(sync=False)["trained"] == 0xF
+        assert torch.equal(a.env.state_words(), b.env.state_words()), j
+        assert a.read_stats() == b.read_stats()
+    torch.cuda.synchronize()
+    for p in range(2):
+        assert torch.equal(a.rl[p].data, b.rl[p].data) and int(a.sl[p].total.item()) == int(b.sl[p].total.item())
+        sa, sb = a.sl[p].data.cpu(), b.sl[p].data.cpu()
+        assert torch.equal(sa[:, 0], sb[:, 0])                                           # the observations
+        assert (sa[:, 1:].view(torch.float32) - sb[:, 1:].view(torch.float32)).abs().max() <= 1e-5   # the score vectors
+    assert (a.weights - b.weights).abs().max() <= 1e-4 and (a.weights - w0).abs().max() > 1e-3
+
+
 def test_pipelined_trainer_with_direct_rings(nb):
     """The production combination of bench.py: the rollout writes the rings in place while the previous update is still
     running.  The update works on a copy of its sampled records taken before the rollout may start (the `gathered`
