@@ -243,8 +243,8 @@ def workload_config():
             "memories": "both reservoirs are filled by untimed steps first: every timed insert is Algorithm R's random replacement",
             "records": "RL records written straight into the rings by the rollout kernel (direct_rings), SL records "
                        "staged and moved into the reservoirs by one insert launch",
-            "nets": "default variant: the four nets are evaluated on the 702 decision states of the game (4 x 702 forwards, same "
-                    "arithmetic as the per-decision kernel) and the decisions read that table; the table is rebuilt from the "
+            "nets": "default variant: the four nets are evaluated on the 702 decision states of the game (same operations as the "
+                    "per-decision kernel) and the decisions read that table; the table is rebuilt from the "
                     "weights inside every timed step.  extra.other_variants.cuda is the per-decision evaluation",
             "baseline_config": "BASELINE.json configs[4] per GPU (configs[2] at 1M games)"}
 

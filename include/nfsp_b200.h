@@ -174,7 +174,7 @@ typedef struct {
                              the constant bank), 4 = CUDA cores with net-sorted warp groups (see below), 5 = CUDA cores, two
                              games per lane, the second layer's weights loaded once for a pair of same-net decisions
                              (csrc/rollout_pairs.cu), 6 = no per-decision forward at all: the nets' outputs on the 702
-                             decision states of the game, recomputed by a 2 808-thread launch whenever the weights have
+                             decision states of the game, recomputed by one small launch whenever the weights have
                              changed (same arithmetic as variant 1), one 16-byte shared-memory read per decision, records
                              collected in warp-private shared-memory buffers (csrc/rollout_states.cu: the default),
                              0 = library default */
