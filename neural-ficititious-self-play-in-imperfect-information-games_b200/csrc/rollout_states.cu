@@ -1,18 +1,20 @@
 // K2, variant 6: the fused rollout over a table of the nets' outputs on every decision state.
 //
 // Under main.train's turn order (the precondition of the factorised first layer, rollout_tables.cuh) the observation a
-// net sees at a decision is one of 702 values (kept in 1 296 table slots so that one formula indexes both rounds): the actor's card, the dealer and the betting sequence so far in round 0
+// net sees at a decision is one of 702 values: the actor's card, the dealer and the betting sequence so far in round 0
 // (54), or card, public card, dealer, the finished round-0 sequence and the round-1 sequence so far (648).  A net is a
-// pure function of the observation, so its three outputs on all 702 of them -- 4 nets x 702 forwards, built by
-// states_pack_kernel from the SAME table image and with the same operations (two rows added, relu, FFMA2 second layer,
-// head; the 16 hidden-unit quads summed in four interleaved groups) every time the weights change -- stand for the 8.4 M forwards of a 2^20-game x 8-step launch.  A decision then costs ONE 16-byte
-// shared-memory read instead of variant 1's 80 (32 row quads + 48 W2 quads, which bound that kernel: an LDS.128 holds
-// the pipe for four cycles), and what is left is the game logic, Philox and the record append.
+// pure function of the observation, so its three outputs on all of them -- computed by states_pack_kernel from the SAME
+// table image and with the same operations as variant 1 (two rows added, relu, FFMA2 second layer, head; the 16
+// hidden-unit quads summed in four interleaved groups) every time the weights change -- stand for the 8.4 M forwards
+// of a 2^20-game x 8-step launch.  A decision then costs ONE 16-byte shared-memory read instead of variant 1's 80 (32
+// row quads + 48 W2 quads, which bound that kernel: an LDS.128 holds the pipe for four cycles), and what is left is the
+// game logic, Philox and the record append.
 //
-// Everything around the forward -- fast_begin / fast_finish, block ownership, the staged or direct append, the
-// counters -- is variant 1's, so the records, game words and counters are those of variant 1 run on the same score
-// vectors; the score vectors differ from variant 1's only by the summation order of a lane's rotation (held to 1e-5
-// of the CPU restatement in tests/test_gpu_act.py and tests/test_gpu_baseline_sizes.py).
+// The decision logic around the forward -- fast_begin / fast_decide, block ownership, the counters -- is variant 1's, so
+// the records, game words and counters are those of variant 1 run on the same score vectors; the score vectors differ
+// from variant 1's only by the summation order of a lane's rotation (held to 1e-5 of the CPU restatement in
+// tests/test_gpu_act.py and tests/test_gpu_baseline_sizes.py).  The append is this kernel's own: warp-private buffers
+// in shared memory (below).
 #include "rollout_fast.cuh"
 #include "rollout_tables.cuh"
 #include "ptx_helpers.cuh"
