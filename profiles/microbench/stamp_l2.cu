@@ -17,6 +17,24 @@ __global__ void red64(unsigned long long *a, uint32_t n_slots, uint32_t n, uint3
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         atomicMax(a + 4ull * (mix(i * 2654435761u + salt) % n_slots) + 2, (unsigned long long)(i + salt));
 }
+// the same random slots: plain loads / L2 prefetches of the stamp words, and prefetch followed by the atomic
+__global__ void ld64(const unsigned long long *a, uint32_t n_slots, uint32_t n, uint32_t salt, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        acc += __ldcg(a + 4ull * (mix(i * 2654435761u + salt) % n_slots) + 2);
+    if (acc == 0x123456789ull) *out = acc;
+}
+__global__ void pf64(const unsigned long long *a, uint32_t n_slots, uint32_t n, uint32_t salt) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 4ull * (mix(i * 2654435761u + salt) % n_slots) + 2));
+}
+__global__ void pf_red64(unsigned long long *a, uint32_t n_slots, uint32_t n, uint32_t salt) {
+    const uint32_t stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = i0; i < n; i += stride)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 4ull * (mix(i * 2654435761u + salt) % n_slots) + 2));
+    for (uint32_t i = i0; i < n; i += stride)
+        atomicMax(a + 4ull * (mix(i * 2654435761u + salt) % n_slots) + 2, (unsigned long long)(i + salt));
+}
 __global__ void stream(uint4 *p, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(i, 1, 2, 3);
 }
@@ -52,6 +70,10 @@ int main() {
     time("u32 stamps, nothing in between (previous launch's lines)", [&](int r) { red32<<<592, 256, 0, st>>>(s32, slots, n, r * 7919u + 1); }, false, false);
     time("u32 stamps, 128 MB streamed, no touch", [&](int r) { red32<<<592, 256, 0, st>>>(s32, slots, n, r * 7919u + 1); }, true, false);
     time("u64 stamps in 32-byte slots (today), 128 MB streamed", [&](int r) { red64<<<592, 256, 0, st>>>(s64, slots, n, r * 7919u + 1); }, true, false);
+    unsigned long long *sink; cudaMalloc(&sink, 8);
+    time("u64 stamps in slots: plain loads of the same sectors, streamed", [&](int r) { ld64<<<592, 256, 0, st>>>(s64, slots, n, r * 7919u + 1, sink); }, true, false);
+    time("u64 stamps in slots: L2 prefetches only, streamed", [&](int r) { pf64<<<592, 256, 0, st>>>(s64, slots, n, r * 7919u + 1); }, true, false);
+    time("u64 stamps in slots: prefetch all, then the atomics, streamed", [&](int r) { pf_red64<<<592, 256, 0, st>>>(s64, slots, n, r * 7919u + 1); }, true, false);
     // persisting window over the u32 array
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
     cudaStreamAttrValue v = {};
