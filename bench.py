@@ -634,6 +634,10 @@ def run_gpu(args):
             # rollout_states_kernel (records into the rings in place), insert_kernel (both reservoirs)
             "gpu_launches": (4 if args.variant in ("default", "states") else 3) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
+            # the same workload with the nets evaluated at every decision (variant "cuda", the default until the state table):
+            # the rollout kernel alone, same launch shape -- for readers who want the figure without the table
+            "per_decision_forward": dict(others.get("cuda", {}), kernel="rollout_kernel",
+                                         note="python bench.py --variant cuda runs the whole line on it"),
             "parity_checked": parity_ok, "parity": parity_info,
             # the iteration that communicates (BASELINE configs[4]): rollout + memories + update_strategy() of both agents
             "training_step": training, "weights_identical_on_all_ranks": weights_same,
