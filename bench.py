@@ -235,8 +235,12 @@ def parity_check(nfsp_b200, dev, game0):
                               "debug and production launch"}
 
 
-def workload_config():
-    return {"workload": "nfsp_rollout: %d games/GPU x %d decisions per step, eta=%.2f eps=%.2f, 4 acting nets 30-64-3, "
+def workload_config(schedule="sequential"):
+    return {"schedule": "every timed step = one rollout launch + one insert launch; " +
+                        ("the insert is that of the PREVIOUS step's staged records and runs on a second stream beside the rollout "
+                         "(both finish inside the step's timed region)" if schedule == "overlap" else
+                         "the insert follows the rollout that staged its records"),
+            "workload": "nfsp_rollout: %d games/GPU x %d decisions per step, eta=%.2f eps=%.2f, 4 acting nets 30-64-3, "
                         "ring %d + reservoir %d records per player, sample %d" %
                         (GAMES_PER_GPU, T_PER_CALL, ETA, EPS, RL_CAP, SL_CAP, BATCH),
             "games_per_gpu": GAMES_PER_GPU, "decisions_per_step": T_PER_CALL, "l2": "flushed between timed steps",
@@ -324,6 +328,14 @@ def run_gpu(args):
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
                             sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
                             direct_rings=args.variant in ("default", "states", "cuda", "pairs"))
+    # the same workload with the insert launch of step k beside the rollout of step k + 1 (SelfPlay(overlap_insert=True));
+    # --schedule auto times both after the warm-up and runs the headline on the faster one
+    can_overlap = args.variant in ("default", "states")
+    sp_ov = None
+    if args.schedule != "sequential" and can_overlap:
+        sp_ov = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
+                                   sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
+                                   direct_rings=True, overlap_insert=True)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
     stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
@@ -336,15 +348,15 @@ def run_gpu(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def timed_steps(k, e2e):
+    def timed_steps(k, e2e, obj=None):
         gc.collect()
         gc.disable()  # a collector pause inside a host-driven step shows up as a straggler rank (max over ranks)
         try:
-            return _timed_steps(k, e2e)
+            return _timed_steps(k, e2e, sp if obj is None else obj)
         finally:
             gc.enable()
 
-    def _timed_steps(k, e2e):
+    def _timed_steps(k, e2e, sp):
         tot_ms, ker_ms = 0.0, 0.0
         for _ in range(k):
             flush_buf.zero_()  # L2 flush, outside the timed events
@@ -355,9 +367,13 @@ def run_gpu(args):
             # value: the nets are resident in HBM; everything the kernels derive from them -- the weight images and, for the
             # default variant, the table of the nets' outputs on the 702 decision states -- is rebuilt from them inside the
             # timed region of EVERY step (as after a learner update): no step runs on outputs computed before its timer
-            sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
-            b.record()
-            sp.flush()
+            if sp.overlap_insert:  # one rollout and one insert per step as well: the insert is the previous step's, beside
+                sp.rollout(T_PER_CALL, weights_host=w_host if e2e else None, refresh_weights=not e2e)  # this rollout
+                b.record()
+            else:
+                sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
+                b.record()
+                sp.flush()
             if e2e:  # the learner's four minibatches and the counters come back to the host in ONE slab, one copy
                 sp.sample_minibatches(BATCH, to_host=True, with_stats=True)
             c.record()
@@ -374,23 +390,48 @@ def run_gpu(args):
         sp.rollout(T_PER_CALL)
         prefill += 1
     timed_steps(args.warmup, False)
+    schedules = {"sequential": "rollout k, then the insert launch of its staged records"}
+    head = sp
+    if sp_ov is not None:
+        prefill = 0
+        while min(int(m.total.item()) for m in sp_ov.sl) < SL_CAP and prefill < 200:
+            sp_ov.rollout(T_PER_CALL)
+            prefill += 1
+        timed_steps(args.warmup, False, sp_ov)
+        barrier()
+        cal = {}
+        for name, obj in (("sequential", sp), ("overlap", sp_ov)):
+            ms, _ = timed_steps(5, False, obj)
+            cal[name] = sharding.max_over_ranks(ms, dev) / 5  # every rank takes the same decision
+        schedules = {"sequential_ms_per_step": cal["sequential"], "overlap_ms_per_step": cal["overlap"],
+                     "what": "5 steps each after the warm-up; overlap = the insert launch of step k - 1 on a second stream "
+                             "beside the rollout of step k (768-thread rollout CTAs + one insert CTA per SM)"}
+        if args.schedule == "overlap" or cal["overlap"] < cal["sequential"]:
+            head = sp_ov
+    schedules["chosen"] = "overlap" if head is sp_ov else "sequential"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    tot_ms, ker_ms = timed_steps(args.steps, False)
+    tot_ms, ker_ms = timed_steps(args.steps, False, head)
     barrier()
-    t_e2e, _ = timed_steps(max(1, min(args.warmup, 2)), True)  # e2e warm-up (pinned buffers, sample kernels)
+    t_e2e, _ = timed_steps(max(1, min(args.warmup, 2)), True, head)  # e2e warm-up (pinned buffers, sample kernels)
     barrier()
-    e2e_ms, _ = timed_steps(args.steps, True)
+    e2e_ms, _ = timed_steps(args.steps, True, head)
     barrier()
     sampler.stop_flag = True
+    if sp_ov is not None:
+        sp_ov.drain()
     tot_ms = sharding.max_over_ranks(tot_ms, dev)
     e2e_ms = sharding.max_over_ranks(e2e_ms, dev)
     trans_all = GAMES_PER_GPU * world * T_PER_CALL * args.steps
     value = trans_all / (tot_ms * 1e-3)
     e2e_value = trans_all / (e2e_ms * 1e-3)
-    st = sharding.allreduce_stats(sp.stats)
+    st = sharding.allreduce_stats(head.stats)
+    if sp_ov is not None:  # the rest of the line (learner, training step) runs on the plain object
+        torch.cuda.synchronize()
+        del sp_ov
+        head = None
 
     # learner beside it (BASELINE configs[4]): update_strategy() of both agents = 8 SGD steps of the
     # four nets, each with ONE all-reduce of the flat gradient+stats buffer (NCCL when world > 1)
@@ -517,6 +558,20 @@ def run_gpu(args):
                 other_ms += a.elapsed_time(b)
         others[other] = {"kernel_transitions_per_sec": n * T_PER_CALL * args.steps / (other_ms * 1e-3),
                          "kernel_ms_per_launch": other_ms / args.steps}
+        if other == "states":  # the launch shape of the overlap schedule, alone: 768-thread CTAs
+            other_ms = 0.0
+            for k in range(3 + args.steps):
+                flush_buf.zero_()
+                a, b = ev(), ev()
+                a.record()
+                spo.rollout(T_PER_CALL, insert=False, share_sms=True)
+                b.record()
+                b.synchronize()
+                spo.counts.zero_()
+                if k >= 3:
+                    other_ms += a.elapsed_time(b)
+            others["states_768_threads"] = {"kernel_transitions_per_sec": n * T_PER_CALL * args.steps / (other_ms * 1e-3),
+                                            "kernel_ms_per_launch": other_ms / args.steps}
         del spo
     # BASELINE configs[2] + configs[3] as stated: 65 536 parallel games, ring of 200 000 + reservoir of 2 000 000 records per
     # player, rollout(8) + the move of the records into the memories (a launch laps the ring: staged path) + 256-row sample
@@ -546,7 +601,7 @@ def run_gpu(args):
     # the rollout kernel alone: CUDA events around its launch (for the default variant the timed steps' events also cover the
     # two small launches that rebuild the images, so its kernel-only figure comes from the per-variant loop above)
     if args.variant in ("default", "states"):
-        ker_ms = others["states"]["kernel_ms_per_launch"] * args.steps
+        ker_ms = others["states_768_threads" if schedules["chosen"] == "overlap" else "states"]["kernel_ms_per_launch"] * args.steps
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
     roofline = {"bound": "hbm", "kernel": KERNEL_OF_VARIANT[args.variant], "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -626,8 +681,8 @@ def run_gpu(args):
     d2h = int(2 * BATCH * (30 + 3 + 1 + 30 + 1) * 4 + 2 * BATCH * 33 * 4 + sp.stats.numel() * 8)
     line = {"metric": "leduc_transitions_per_sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-            "clocks": sampler.summary(),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(schedules["chosen"]),
+            "clocks": sampler.summary(), "schedule": schedules,
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             # per step: pack_images_kernel + states_pack_kernel (the nets' images and state table, rebuilt every step),
@@ -680,6 +735,9 @@ def main():
     ap.add_argument("--variant", default="default", choices=["default", "states", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
                     help="rollout kernel: table of the nets' outputs per decision state (default), per-decision CUDA-core row sums, "
                          "net-sorted warp groups, tcgen05 tensor-core tiles")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "sequential", "overlap"],
+                    help="insert launch after its rollout (sequential) or beside the next one (overlap); auto times both and "
+                         "runs the headline on the faster")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -501,13 +501,13 @@ static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet
 }
 
 // one cooperative launch: every CTA must be resident for the grid barriers
-static int launch_insert(MemSet &S, cudaStream_t st) {
+static int launch_insert(MemSet &S, cudaStream_t st, int max_per_sm = 8) {
     int dev = 0, sms = 0, per_sm = 0;
     NFSP_CUDA(cudaGetDevice(&dev));
     NFSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     NFSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel, kBufThreads, 0));
     if (per_sm < 1) return set_error(NFSP_E_CUDA, "insert_kernel does not fit an SM");
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
     int64_t items = 0;
     for (int k = 0; k < S.n; ++k) items += (int64_t)S.m[k].B.n_seg * S.gx;
     int64_t grid = (int64_t)sms * per_sm;
@@ -525,6 +525,16 @@ extern "C" int nfsp_insert_multi(const nfsp_insert_req *reqs, int n, void *strea
     if (rc != NFSP_OK) return rc;
     if (seg_cap == 0) return NFSP_OK;
     return launch_insert(S, (cudaStream_t)stream);
+}
+
+extern "C" int nfsp_insert_multi_beside(const nfsp_insert_req *reqs, int n, int ctas_per_sm, void *stream) {
+    NFSP_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm must be in [1, 8]");
+    MemSet S;
+    int64_t seg_cap;
+    const int rc = make_memset(reqs, n, -1, S, &seg_cap);
+    if (rc != NFSP_OK) return rc;
+    if (seg_cap == 0) return NFSP_OK;
+    return launch_insert(S, (cudaStream_t)stream, ctas_per_sm);
 }
 
 extern "C" int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {
