@@ -332,7 +332,9 @@ def run_gpu(args):
     # --schedule auto times both after the warm-up and runs the headline on the faster one
     can_overlap = args.variant in ("default", "states")
     sp_ov = None
-    if args.schedule != "sequential" and can_overlap:
+    # default (--schedule sequential): the headline runs the plain schedule; on one GPU the overlap schedule is timed beside
+    # it for the record (schedule.overlap_ms_per_step).  --schedule overlap / auto run the headline on it / on the faster one
+    if can_overlap and (args.schedule != "sequential" or world == 1):
         sp_ov = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
                                    sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
                                    direct_rings=True, overlap_insert=True)
@@ -356,8 +358,11 @@ def run_gpu(args):
         finally:
             gc.enable()
 
+    per_step_ms = []  # of the last timed_steps call
+
     def _timed_steps(k, e2e, sp):
         tot_ms, ker_ms = 0.0, 0.0
+        per_step_ms.clear()
         for _ in range(k):
             flush_buf.zero_()  # L2 flush, outside the timed events
             a, b, c = ev(), ev(), ev()
@@ -380,6 +385,7 @@ def run_gpu(args):
             c.synchronize()
             tot_ms += a.elapsed_time(c)
             ker_ms += a.elapsed_time(b)
+            per_step_ms.append(a.elapsed_time(c))
         return tot_ms, ker_ms
 
     # steady state of the memories before anything is timed: both reservoirs full, so that every timed insert is
@@ -399,14 +405,47 @@ def run_gpu(args):
             prefill += 1
         timed_steps(args.warmup, False, sp_ov)
         barrier()
-        cal = {}
+        cal, cal_steps = {}, {}
+        # where the insert launch sits inside an overlap step: events around it on its own stream, against the step's start
+        marks, windows, orig_flush = {}, [], sp_ov._flush_set
+
+        def traced_flush(k, beside=False):
+            st_ = torch.cuda.current_stream(dev)
+            marks["i0"], marks["i1"], marks["a"] = ev(), ev(), ev()
+            marks["a"].record(torch.cuda.default_stream(dev))
+            marks["i0"].record(st_)
+            orig_flush(k, beside)
+            marks["i1"].record(st_)
+
         for name, obj in (("sequential", sp), ("overlap", sp_ov)):
-            ms, _ = timed_steps(5, False, obj)
-            cal[name] = sharding.max_over_ranks(ms, dev) / 5  # every rank takes the same decision
+            if obj is sp_ov:
+                sp_ov._flush_set = traced_flush
+                for _ in range(4):
+                    flush_buf.zero_()
+                    sp_ov.rollout(T_PER_CALL, refresh_weights=True)
+                    c_ = ev()
+                    c_.record()
+                    torch.cuda.synchronize()
+                    windows.append((marks["a"].elapsed_time(marks["i0"]) * 1e3, marks["a"].elapsed_time(marks["i1"]) * 1e3,
+                                    marks["a"].elapsed_time(c_) * 1e3))
+                sp_ov._flush_set = orig_flush
+            else:
+                for _ in range(4):  # the same number of steps as the traced ones of the other object: both reservoirs are
+                    sp.rollout(T_PER_CALL, refresh_weights=True)  # equally full when their steps are timed
+            timed_steps(12, False, obj)
+            cal_steps[name] = [round(x, 4) for x in per_step_ms]
+            med = sorted(per_step_ms[2:])[len(per_step_ms[2:]) // 2]  # the first steps after a change of object run slow
+            cal[name] = sharding.max_over_ranks(med, dev)  # every rank takes the same decision
         schedules = {"sequential_ms_per_step": cal["sequential"], "overlap_ms_per_step": cal["overlap"],
-                     "what": "5 steps each after the warm-up; overlap = the insert launch of step k - 1 on a second stream "
-                             "beside the rollout of step k (768-thread rollout CTAs + one insert CTA per SM)"}
-        if args.schedule == "overlap" or cal["overlap"] < cal["sequential"]:
+                     "steps_ms": cal_steps, "overlap_insert_window_us": [[round(x, 1) for x in w] for w in windows],
+                     "tickets_over_capacity_after": min(int(m.total.item()) for m in sp_ov.sl) / float(SL_CAP),
+                     "what": "median of 10 steps each (12 run, 2 dropped) after the warm-up; overlap = the insert launch of step "
+                             "k - 1 on a second stream beside the rollout of step k (768-thread rollout CTAs + one insert "
+                             "CTA per SM; the rollout's stream is held until the insert's CTAs are resident).  "
+                             "overlap_insert_window_us: [insert starts, insert ends, step ends] after the insert was submitted, "
+                             "four steps.  The gain grows with tickets / capacity (the fewer records Algorithm R accepts, the "
+                             "less the insert disturbs the rollout): profiles/r02/overlap_insert_notes.txt"}
+        if args.schedule == "overlap" or (args.schedule == "auto" and cal["overlap"] < cal["sequential"]):
             head = sp_ov
     schedules["chosen"] = "overlap" if head is sp_ov else "sequential"
     sampler = ClockSampler(local)
@@ -735,9 +774,10 @@ def main():
     ap.add_argument("--variant", default="default", choices=["default", "states", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
                     help="rollout kernel: table of the nets' outputs per decision state (default), per-decision CUDA-core row sums, "
                          "net-sorted warp groups, tcgen05 tensor-core tiles")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "sequential", "overlap"],
-                    help="insert launch after its rollout (sequential) or beside the next one (overlap); auto times both and "
-                         "runs the headline on the faster")
+    ap.add_argument("--schedule", default="sequential", choices=["sequential", "overlap", "auto"],
+                    help="insert launch after its rollout (sequential, the headline) or beside the next one (overlap: "
+                         "SelfPlay(overlap_insert=True)); auto times both and runs the headline on the faster.  With one GPU "
+                         "the other schedule is always timed for the record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -129,7 +129,7 @@ def lib():
     L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
     L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp, vp]
     L.nfsp_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
-    L.nfsp_insert_multi_beside.argtypes = [C.POINTER(InsertReq), C.c_int, C.c_int, vp]
+    L.nfsp_insert_multi_beside.argtypes = [vp, C.POINTER(InsertReq), C.c_int, C.c_int, vp]
     L.nfsp_ring_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_reservoir_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]

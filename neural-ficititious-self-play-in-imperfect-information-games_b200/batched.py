@@ -517,9 +517,12 @@ class SelfPlay:
             if not insert or reserve_sms:
                 raise ValueError("overlap_insert: rollout() always inserts (one call behind) and reserves no SMs")
             main = torch.cuda.current_stream(self.device)
-            if self._pending is not None:  # the previous call's records: their insert starts now, beside this rollout
-                self._ev_roll.record(main)  # after everything the caller has queued so far (the rollout that staged them,
-                self._ins_stream.wait_event(self._ev_roll)  # a minibatch gather that still reads the reservoirs)
+            if self._pending is not None:
+                # the insert of the previous call's records starts once everything the caller has queued so far is done (the
+                # rollout that staged them, a minibatch gather that still reads the reservoirs); the library holds this
+                # call's rollout until the insert's CTAs sit one per SM (nfsp_insert_multi_beside)
+                self._ev_roll.record(main)
+                self._ins_stream.wait_event(self._ev_roll)
                 with torch.cuda.stream(self._ins_stream):
                     self._flush_set(self._pending, beside=True)
                 self._ev_ins.record(self._ins_stream)
@@ -600,7 +603,7 @@ class SelfPlay:
             cache[k] = (arr, [m._scratch.data_ptr() for m in self.sl])
         arr = cache[k][0]
         if beside:
-            check(lib().nfsp_insert_multi_beside(arr, 2, 1, _stream(self.device)))
+            check(lib().nfsp_insert_multi_beside(self.env._h, arr, 2, 1, _stream(self.device)))
         else:
             check(lib().nfsp_insert_multi(arr, 2, _stream(self.device)))
 

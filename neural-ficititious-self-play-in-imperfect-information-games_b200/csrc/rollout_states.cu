@@ -270,10 +270,14 @@ static int configure_states() {
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+    // one carve-out for every kernel of a step (see nfsp_act_set_weights): the largest
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return NFSP_OK;
 }
 
 int nfsp_rollout_states_configure() {
+    NFSP_CUDA(cudaFuncSetAttribute(states_pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int rc = configure_states<kStatesThreads>();
     return rc != NFSP_OK ? rc : configure_states<kStatesThreadsSmall>();
 }
