@@ -235,12 +235,8 @@ def parity_check(nfsp_b200, dev, game0):
                               "debug and production launch"}
 
 
-def workload_config(schedule="sequential"):
-    return {"schedule": "every timed step = one rollout launch + one insert launch; " +
-                        ("the insert is that of the PREVIOUS step's staged records and runs on a second stream beside the rollout "
-                         "(both finish inside the step's timed region)" if schedule == "overlap" else
-                         "the insert follows the rollout that staged its records"),
-            "workload": "nfsp_rollout: %d games/GPU x %d decisions per step, eta=%.2f eps=%.2f, 4 acting nets 30-64-3, "
+def workload_config():
+    return {"workload": "nfsp_rollout: %d games/GPU x %d decisions per step, eta=%.2f eps=%.2f, 4 acting nets 30-64-3, "
                         "ring %d + reservoir %d records per player, sample %d" %
                         (GAMES_PER_GPU, T_PER_CALL, ETA, EPS, RL_CAP, SL_CAP, BATCH),
             "games_per_gpu": GAMES_PER_GPU, "decisions_per_step": T_PER_CALL, "l2": "flushed between timed steps",
@@ -328,16 +324,6 @@ def run_gpu(args):
     sp = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
                             sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
                             direct_rings=args.variant in ("default", "states", "cuda", "pairs"))
-    # the same workload with the insert launch of step k beside the rollout of step k + 1 (SelfPlay(overlap_insert=True));
-    # --schedule auto times both after the warm-up and runs the headline on the faster one
-    can_overlap = args.variant in ("default", "states")
-    sp_ov = None
-    # default (--schedule sequential): the headline runs the plain schedule; on one GPU the overlap schedule is timed beside
-    # it for the record (schedule.overlap_ms_per_step).  --schedule overlap / auto run the headline on it / on the faster one
-    if can_overlap and (args.schedule != "sequential" or world == 1):
-        sp_ov = nfsp_b200.SelfPlay(n, seed=SEED, game0=game0, device=dev, eta=ETA, epsilon=EPS, rl_capacity=RL_CAP,
-                                   sl_capacity=SL_CAP, max_steps_per_call=T_PER_CALL, variant=args.variant,
-                                   direct_rings=True, overlap_insert=True)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     w_host = sp.weights.cpu().pin_memory()
     stats_host = torch.empty(sp.stats.shape, dtype=sp.stats.dtype).pin_memory()
@@ -350,19 +336,16 @@ def run_gpu(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def timed_steps(k, e2e, obj=None):
+    def timed_steps(k, e2e):
         gc.collect()
         gc.disable()  # a collector pause inside a host-driven step shows up as a straggler rank (max over ranks)
         try:
-            return _timed_steps(k, e2e, sp if obj is None else obj)
+            return _timed_steps(k, e2e)
         finally:
             gc.enable()
 
-    per_step_ms = []  # of the last timed_steps call
-
-    def _timed_steps(k, e2e, sp):
+    def _timed_steps(k, e2e):
         tot_ms, ker_ms = 0.0, 0.0
-        per_step_ms.clear()
         for _ in range(k):
             flush_buf.zero_()  # L2 flush, outside the timed events
             a, b, c = ev(), ev(), ev()
@@ -372,20 +355,15 @@ def run_gpu(args):
             # value: the nets are resident in HBM; everything the kernels derive from them -- the weight images and, for the
             # default variant, the table of the nets' outputs on the 702 decision states -- is rebuilt from them inside the
             # timed region of EVERY step (as after a learner update): no step runs on outputs computed before its timer
-            if sp.overlap_insert:  # one rollout and one insert per step as well: the insert is the previous step's, beside
-                sp.rollout(T_PER_CALL, weights_host=w_host if e2e else None, refresh_weights=not e2e)  # this rollout
-                b.record()
-            else:
-                sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
-                b.record()
-                sp.flush()
+            sp.rollout(T_PER_CALL, insert=False, weights_host=w_host if e2e else None, refresh_weights=not e2e)
+            b.record()
+            sp.flush()
             if e2e:  # the learner's four minibatches and the counters come back to the host in ONE slab, one copy
                 sp.sample_minibatches(BATCH, to_host=True, with_stats=True)
             c.record()
             c.synchronize()
             tot_ms += a.elapsed_time(c)
             ker_ms += a.elapsed_time(b)
-            per_step_ms.append(a.elapsed_time(c))
         return tot_ms, ker_ms
 
     # steady state of the memories before anything is timed: both reservoirs full, so that every timed insert is
@@ -396,81 +374,23 @@ def run_gpu(args):
         sp.rollout(T_PER_CALL)
         prefill += 1
     timed_steps(args.warmup, False)
-    schedules = {"sequential": "rollout k, then the insert launch of its staged records"}
-    head = sp
-    if sp_ov is not None:
-        prefill = 0
-        while min(int(m.total.item()) for m in sp_ov.sl) < SL_CAP and prefill < 200:
-            sp_ov.rollout(T_PER_CALL)
-            prefill += 1
-        timed_steps(args.warmup, False, sp_ov)
-        barrier()
-        cal, cal_steps = {}, {}
-        # where the insert launch sits inside an overlap step: events around it on its own stream, against the step's start
-        marks, windows, orig_flush = {}, [], sp_ov._flush_set
-
-        def traced_flush(k, beside=False):
-            st_ = torch.cuda.current_stream(dev)
-            marks["i0"], marks["i1"], marks["a"] = ev(), ev(), ev()
-            marks["a"].record(torch.cuda.default_stream(dev))
-            marks["i0"].record(st_)
-            orig_flush(k, beside)
-            marks["i1"].record(st_)
-
-        for name, obj in (("sequential", sp), ("overlap", sp_ov)):
-            if obj is sp_ov:
-                sp_ov._flush_set = traced_flush
-                for _ in range(4):
-                    flush_buf.zero_()
-                    sp_ov.rollout(T_PER_CALL, refresh_weights=True)
-                    c_ = ev()
-                    c_.record()
-                    torch.cuda.synchronize()
-                    windows.append((marks["a"].elapsed_time(marks["i0"]) * 1e3, marks["a"].elapsed_time(marks["i1"]) * 1e3,
-                                    marks["a"].elapsed_time(c_) * 1e3))
-                sp_ov._flush_set = orig_flush
-            else:
-                for _ in range(4):  # the same number of steps as the traced ones of the other object: both reservoirs are
-                    sp.rollout(T_PER_CALL, refresh_weights=True)  # equally full when their steps are timed
-            timed_steps(12, False, obj)
-            cal_steps[name] = [round(x, 4) for x in per_step_ms]
-            med = sorted(per_step_ms[2:])[len(per_step_ms[2:]) // 2]  # the first steps after a change of object run slow
-            cal[name] = sharding.max_over_ranks(med, dev)  # every rank takes the same decision
-        schedules = {"sequential_ms_per_step": cal["sequential"], "overlap_ms_per_step": cal["overlap"],
-                     "steps_ms": cal_steps, "overlap_insert_window_us": [[round(x, 1) for x in w] for w in windows],
-                     "tickets_over_capacity_after": min(int(m.total.item()) for m in sp_ov.sl) / float(SL_CAP),
-                     "what": "median of 10 steps each (12 run, 2 dropped) after the warm-up; overlap = the insert launch of step "
-                             "k - 1 on a second stream beside the rollout of step k (768-thread rollout CTAs + one insert "
-                             "CTA per SM; the rollout's stream is held until the insert's CTAs are resident).  "
-                             "overlap_insert_window_us: [insert starts, insert ends, step ends] after the insert was submitted, "
-                             "four steps.  The gain grows with tickets / capacity (the fewer records Algorithm R accepts, the "
-                             "less the insert disturbs the rollout): profiles/r02/overlap_insert_notes.txt"}
-        if args.schedule == "overlap" or (args.schedule == "auto" and cal["overlap"] < cal["sequential"]):
-            head = sp_ov
-    schedules["chosen"] = "overlap" if head is sp_ov else "sequential"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    tot_ms, ker_ms = timed_steps(args.steps, False, head)
+    tot_ms, ker_ms = timed_steps(args.steps, False)
     barrier()
-    t_e2e, _ = timed_steps(max(1, min(args.warmup, 2)), True, head)  # e2e warm-up (pinned buffers, sample kernels)
+    t_e2e, _ = timed_steps(max(1, min(args.warmup, 2)), True)  # e2e warm-up (pinned buffers, sample kernels)
     barrier()
-    e2e_ms, _ = timed_steps(args.steps, True, head)
+    e2e_ms, _ = timed_steps(args.steps, True)
     barrier()
     sampler.stop_flag = True
-    if sp_ov is not None:
-        sp_ov.drain()
     tot_ms = sharding.max_over_ranks(tot_ms, dev)
     e2e_ms = sharding.max_over_ranks(e2e_ms, dev)
     trans_all = GAMES_PER_GPU * world * T_PER_CALL * args.steps
     value = trans_all / (tot_ms * 1e-3)
     e2e_value = trans_all / (e2e_ms * 1e-3)
-    st = sharding.allreduce_stats(head.stats)
-    if sp_ov is not None:  # the rest of the line (learner, training step) runs on the plain object
-        torch.cuda.synchronize()
-        del sp_ov
-        head = None
+    st = sharding.allreduce_stats(sp.stats)
 
     # learner beside it (BASELINE configs[4]): update_strategy() of both agents = 8 SGD steps of the
     # four nets, each with ONE all-reduce of the flat gradient+stats buffer (NCCL when world > 1)
@@ -597,20 +517,6 @@ def run_gpu(args):
                 other_ms += a.elapsed_time(b)
         others[other] = {"kernel_transitions_per_sec": n * T_PER_CALL * args.steps / (other_ms * 1e-3),
                          "kernel_ms_per_launch": other_ms / args.steps}
-        if other == "states":  # the launch shape of the overlap schedule, alone: 768-thread CTAs
-            other_ms = 0.0
-            for k in range(3 + args.steps):
-                flush_buf.zero_()
-                a, b = ev(), ev()
-                a.record()
-                spo.rollout(T_PER_CALL, insert=False, share_sms=True)
-                b.record()
-                b.synchronize()
-                spo.counts.zero_()
-                if k >= 3:
-                    other_ms += a.elapsed_time(b)
-            others["states_768_threads"] = {"kernel_transitions_per_sec": n * T_PER_CALL * args.steps / (other_ms * 1e-3),
-                                            "kernel_ms_per_launch": other_ms / args.steps}
         del spo
     # BASELINE configs[2] + configs[3] as stated: 65 536 parallel games, ring of 200 000 + reservoir of 2 000 000 records per
     # player, rollout(8) + the move of the records into the memories (a launch laps the ring: staged path) + 256-row sample
@@ -640,7 +546,7 @@ def run_gpu(args):
     # the rollout kernel alone: CUDA events around its launch (for the default variant the timed steps' events also cover the
     # two small launches that rebuild the images, so its kernel-only figure comes from the per-variant loop above)
     if args.variant in ("default", "states"):
-        ker_ms = others["states_768_threads" if schedules["chosen"] == "overlap" else "states"]["kernel_ms_per_launch"] * args.steps
+        ker_ms = others["states"]["kernel_ms_per_launch"] * args.steps
     kernel_rate = n * T_PER_CALL * args.steps / (ker_ms * 1e-3)
     achieved = kernel_rate * BYTES_PER_TRANSITION / 1e9
     roofline = {"bound": "hbm", "kernel": KERNEL_OF_VARIANT[args.variant], "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -720,8 +626,8 @@ def run_gpu(args):
     d2h = int(2 * BATCH * (30 + 3 + 1 + 30 + 1) * 4 + 2 * BATCH * 33 * 4 + sp.stats.numel() * 8)
     line = {"metric": "leduc_transitions_per_sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(schedules["chosen"]),
-            "clocks": sampler.summary(), "schedule": schedules,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+            "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             # per step: pack_images_kernel + states_pack_kernel (the nets' images and state table, rebuilt every step),
@@ -774,10 +680,6 @@ def main():
     ap.add_argument("--variant", default="default", choices=["default", "states", "cuda", "pairs", "sorted", "tcgen05", "tcgen05_ws"],
                     help="rollout kernel: table of the nets' outputs per decision state (default), per-decision CUDA-core row sums, "
                          "net-sorted warp groups, tcgen05 tensor-core tiles")
-    ap.add_argument("--schedule", default="sequential", choices=["sequential", "overlap", "auto"],
-                    help="insert launch after its rollout (sequential, the headline) or beside the next one (overlap: "
-                         "SelfPlay(overlap_insert=True)); auto times both and runs the headline on the faster.  With one GPU "
-                         "the other schedule is always timed for the record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -191,10 +191,6 @@ typedef struct {
     /* each Agent of the reference decays its own epsilon (agent.py:253): with epsilon_per_player != 0 the `epsilon`
      * argument of nfsp_rollout is player 0's and epsilon_p1 player 1's; otherwise both use `epsilon` */
     int32_t epsilon_per_player;
-    /* variant 6: != 0 launches 768-thread CTAs that leave every SM room for one 256-thread CTA of another stream's kernel
-     * (registers, warp slots, shared memory) -- the insert of the PREVIOUS launch's staged records running beside this
-     * rollout, nfsp_insert_multi_beside.  0 = the rollout takes the whole SM */
-    int32_t share_sms;
     double epsilon_p1;
 } nfsp_rollout_io;
 /* 4 = CUDA cores, the decisions of a four-warp group sorted by net so that warps are net-homogeneous, records appended
@@ -265,13 +261,6 @@ typedef struct {
     int32_t reservoir;
 } nfsp_insert_req;
 int nfsp_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
-/* nfsp_insert_multi with at most ctas_per_sm (1..8) CTAs of 256 threads per SM, for a launch that has to be resident
- * BESIDE another stream's persistent kernel -- a rollout launched with nfsp_rollout_io.share_sms leaves every SM room for
- * exactly one: the records staged by rollout k (ReservoirBuffer.add / ReplayBuffer.add, as above) then reach the memories
- * while rollout k + 1 plays, from a staging set of its own.  Call it BEFORE that rollout.  h = the environment the rollout
- * belongs to, or NULL: with h the next share_sms rollout of h is held back, on the device, until every CTA of this insert
- * is resident (one per SM on a quiet GPU) -- launches that become ready together would otherwise fight for the SMs. */
-int nfsp_insert_multi_beside(nfsp_env_t h, const nfsp_insert_req *reqs, int n, int ctas_per_sm, void *stream);
 int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 int nfsp_reservoir_insert_multi(const nfsp_insert_req *reqs, int n, void *stream);
 /* random.sample(buffer, batch) (replay_buffer.py:46-51, ReservoirBuffer.py:33-37): `batch`

@@ -26,7 +26,7 @@ SYMBOLS = [
     "nfsp_legacy_rollout", "nfsp_legacy_export",
     "nfsp_expand_obs",
     "nfsp_act_set_weights", "nfsp_act_set_weights_from_host", "nfsp_act_forward", "nfsp_act_forward_tc", "nfsp_rollout", "nfsp_rollout_with_weights", "nfsp_rollout_tune", "nfsp_rollout_profile",
-    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_insert_multi", "nfsp_insert_multi_beside", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
+    "nfsp_ring_insert", "nfsp_reservoir_insert", "nfsp_insert_multi", "nfsp_ring_insert_multi", "nfsp_reservoir_insert_multi", "nfsp_sample_indices", "nfsp_sample_minibatches", "nfsp_gather_rl", "nfsp_gather_sl",
     "nfsp_learner_grads", "nfsp_learner_fit", "nfsp_learner_fit_peers", "nfsp_sgd_apply",
     "nfsp_peer_buffer_create", "nfsp_peer_buffer_open", "nfsp_peer_buffer_close", "nfsp_peer_buffer_destroy",
 ]
@@ -37,7 +37,7 @@ class RolloutIO(C.Structure):
                 ("n_segments", C.c_int32), ("d_counts", C.c_void_p), ("d_stats", C.c_void_p), ("d_trace", C.c_void_p), ("d_vec", C.c_void_p),
                 ("d_forced_vec", C.c_void_p), ("variant", C.c_int32), ("reserve_sms", C.c_int32),
                 ("d_ring", C.c_void_p * 2), ("d_ring_total", C.c_void_p * 2), ("ring_cap", C.c_int64),
-                ("epsilon_per_player", C.c_int32), ("share_sms", C.c_int32), ("epsilon_p1", C.c_double)]
+                ("epsilon_per_player", C.c_int32), ("epsilon_p1", C.c_double)]
 
 
 class InsertReq(C.Structure):
@@ -129,7 +129,6 @@ def lib():
     L.nfsp_ring_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
     L.nfsp_reservoir_insert.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int64, C.c_uint64, C.c_int, vp, vp]
     L.nfsp_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
-    L.nfsp_insert_multi_beside.argtypes = [vp, C.POINTER(InsertReq), C.c_int, C.c_int, vp]
     L.nfsp_ring_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_reservoir_insert_multi.argtypes = [C.POINTER(InsertReq), C.c_int, vp]
     L.nfsp_sample_indices.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp]

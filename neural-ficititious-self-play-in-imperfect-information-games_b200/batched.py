@@ -394,19 +394,13 @@ class SelfPlay:
 
     def __init__(self, n_games, weights=None, seed=1234, game0=0, device=None, eta=0.1, epsilon=0.06,
                  rl_capacity=200000, sl_capacity=2000000, max_steps_per_call=8, reservoir_mode="R",
-                 variant="default", direct_rings=False, deterministic=False, overlap_insert=False):
+                 variant="default", direct_rings=False, deterministic=False):
         """direct_rings: the rollout kernel writes the RL records straight into the players' rings (variants "cuda" and
         "sorted"; needs 2 * n_games * max_steps_per_call <= rl_capacity so that one launch cannot lap a ring): no staging
         copy, `flush()` then only moves the SL records into the reservoirs.  "auto" = on when that condition holds.
         deterministic: every block of 32 games stages into a segment of its own, so the order in which the records reach
         the memories -- ring slots, reservoir tickets, the rows a minibatch draws -- is the same in every run (up to
-        1 048 576 games per GPU; staged records only, the warp-per-block variants only).
-        overlap_insert: the memories' insert launch of rollout k runs on a second stream BESIDE rollout k + 1 instead of
-        after rollout k (default variant with direct_rings only).  The rollout then runs 768-thread CTAs, which leave every
-        SM room for one CTA of the insert launch (`nfsp_rollout_io.share_sms`, `nfsp_insert_multi_beside`), and the SL
-        records alternate between two staging sets.  The reservoirs lag the games by one call; `drain()` inserts what is
-        still staged.  Every call still performs one rollout and one insert, and returns with both ordered on the
-        caller's stream."""
+        1 048 576 games per GPU; staged records only, the warp-per-block variants only)."""
         self.variant = variant
         self.env = BatchedNfspEnv(n_games, seed, game0, device, eta)
         self.device, self.n = self.env.device, self.env.n
@@ -450,16 +444,6 @@ class SelfPlay:
         self.stage_sl = [torch.empty((self.n_seg * self.cap_sl, 4), dtype=torch.int32, device=self.device) for _ in range(2)]
         self.counts = torch.zeros((4, self.n_seg), dtype=torch.int32, device=self.device)
         self.stats = torch.zeros(_lib.STATS_FIELDS, dtype=torch.int64, device=self.device)
-        self.overlap_insert = bool(overlap_insert)
-        if self.overlap_insert:
-            if not self.direct_rings or self.VARIANTS[variant] not in (0, 6):
-                raise ValueError("overlap_insert needs the default (state-table) variant and direct_rings")
-            # two staging sets of SL records + counters: rollout k + 1 fills one while the insert of rollout k empties the other
-            self._sets = [(self.stage_sl, self.counts),
-                          ([torch.empty_like(t) for t in self.stage_sl], torch.zeros_like(self.counts))]
-            self._set, self._pending = 0, None
-            self._ins_stream = torch.cuda.Stream(self.device)
-            self._ev_roll, self._ev_ins = torch.cuda.Event(), torch.cuda.Event()
         self.set_weights(glorot_nets(seed, self.device) if weights is None else weights)
         self.env.reset()
 
@@ -500,7 +484,7 @@ class SelfPlay:
     VARIANTS = {"default": 0, "cuda": 1, "tcgen05": 2, "tcgen05_ws": 3, "sorted": 4, "pairs": 5, "states": 6}
 
     def rollout(self, n_steps=1, insert=True, debug=False, forced_vec=None, variant=None, reserve_sms=0, weights_host=None,
-                refresh_weights=False, share_sms=False):
+                refresh_weights=False):
         """variant: "cuda" (CUDA cores, one warp per 32 games: the default), "sorted" (CUDA cores, warp groups sorted by
         net), "tcgen05" / "tcgen05_ws" (first layer as tensor-core tiles with the accumulator in TMEM) or None =
         self.variant.  reserve_sms: SMs the persistent rollout grid
@@ -508,24 +492,9 @@ class SelfPlay:
         [4, 2179] host tensor with new acting nets -- copied to the device and packed by the same library call that launches
         the rollout (`set_weights(host tensor)` + `rollout()` in one trip through the binding).  refresh_weights: the
         device tensor self.weights has been written in place (a learner update): rebuild the kernels' images from it in the
-        same library call (`set_weights(self.weights)` + `rollout()` in one trip).  share_sms: the state-table rollout as
-        768-thread CTAs that leave every SM room for one 256-thread CTA of another stream (what overlap_insert launches)."""
+        same library call (`set_weights(self.weights)` + `rollout()` in one trip)."""
         if n_steps > self.max_steps:
             raise ValueError("n_steps %d exceeds max_steps_per_call %d" % (n_steps, self.max_steps))
-        overlap = self.overlap_insert
-        if overlap:
-            if not insert or reserve_sms:
-                raise ValueError("overlap_insert: rollout() always inserts (one call behind) and reserves no SMs")
-            main = torch.cuda.current_stream(self.device)
-            if self._pending is not None:
-                # the insert of the previous call's records starts once everything the caller has queued so far is done (the
-                # rollout that staged them, a minibatch gather that still reads the reservoirs); the library holds this
-                # call's rollout until the insert's CTAs sit one per SM (nfsp_insert_multi_beside)
-                self._ev_roll.record(main)
-                self._ins_stream.wait_event(self._ev_roll)
-                with torch.cuda.stream(self._ins_stream):
-                    self._flush_set(self._pending, beside=True)
-                self._ev_ins.record(self._ins_stream)
         want_debug = debug or forced_vec is not None
         io = None if want_debug else getattr(self, "_io", None)  # the production argument block is built once
         if io is None:
@@ -547,12 +516,6 @@ class SelfPlay:
         if (io.variant == 4) != (self.VARIANTS[self.variant] == 4):
             raise ValueError("variant 'sorted' appends through one cursor per memory: build the SelfPlay with variant='sorted'")
         io.reserve_sms = int(reserve_sms)
-        io.share_sms = int(overlap or share_sms)
-        if overlap:
-            stage_sl, counts = self._sets[self._set]
-            for p in range(2):
-                io.d_sl[p] = stage_sl[p].data_ptr()
-            io.d_counts = counts.data_ptr()
         dbg = None
         if want_debug:
             tr = torch.empty((3, n_steps, self.n), dtype=torch.int32, device=self.device)
@@ -580,46 +543,13 @@ class SelfPlay:
         if dbg is not None:
             out = decode_trace(dbg[0])
             out["vec"] = dbg[1]
-        if overlap:
-            if self._pending is not None:
-                main.wait_event(self._ev_ins)  # the call ends with its rollout AND its insert ordered on the caller's stream
-            self._pending, self._set = self._set, self._set ^ 1
-        elif insert:
+        if insert:
             self.flush()
         return out
 
-    def _flush_set(self, k, beside=False):
-        """overlap_insert: the insert launch of staging set k on the current stream (request blocks built once per set)."""
-        cache = self.__dict__.setdefault("_flush_sets", {})
-        if k not in cache or any(m._scratch is None or m._scratch.data_ptr() != p_ for m, p_ in zip(self.sl, cache[k][1])):
-            stage_sl, counts = self._sets[k]
-            arr = (_lib.InsertReq * 2)()
-            for p, r in enumerate(arr):
-                mem = self.sl[p]
-                r.d_mem, r.cap, r.d_total = mem.store.data_ptr(), mem.capacity, mem.total.data_ptr()
-                r.d_scratch = mem.scratch(self.n_seg).data_ptr()
-                r.d_recs, r.d_counts = stage_sl[p].data_ptr(), counts[2 + p].data_ptr()
-                r.n_segments, r.seg_cap, r.seed, r.mode, r.reservoir = self.n_seg, self.cap_sl, mem.seed, mem.mode, 1
-            cache[k] = (arr, [m._scratch.data_ptr() for m in self.sl])
-        arr = cache[k][0]
-        if beside:
-            check(lib().nfsp_insert_multi_beside(self.env._h, arr, 2, 1, _stream(self.device)))
-        else:
-            check(lib().nfsp_insert_multi(arr, 2, _stream(self.device)))
-
-    def drain(self):
-        """overlap_insert: insert the records the last rollout staged (on the caller's stream); afterwards the memories
-        hold every record played so far, as after the same calls without overlap."""
-        if self.overlap_insert and self._pending is not None:
-            self._flush_set(self._pending)
-            self._pending = None
-
     def staged(self):
         """Host copies of the staged records in batch order (segment by segment): ([rl0, rl1], [sl0, sl1])."""
-        stage_sl, counts = self.stage_sl, self.counts
-        if self.overlap_insert and self._pending is not None:
-            stage_sl, counts = self._sets[self._pending]  # what the last rollout staged
-        c = counts.cpu().numpy()
+        c = self.counts.cpu().numpy()
 
         def take(stage, cnt, cap, dt):
             a = stage.cpu().numpy().reshape(self.n_seg, cap, 4)
@@ -630,7 +560,7 @@ class SelfPlay:
             rl = [np.zeros(0, dtype=RL_DT) for _ in range(2)]
         else:
             rl = [take(self.stage_rl[p], c[p], self.cap_rl, RL_DT) for p in range(2)]
-        sl = [take(stage_sl[p], c[2 + p], self.cap_sl, SL_DT) for p in range(2)]
+        sl = [take(self.stage_sl[p], c[2 + p], self.cap_sl, SL_DT) for p in range(2)]
         return rl, sl
 
     def flush(self):
@@ -638,8 +568,6 @@ class SelfPlay:
         players' rings and reservoirs (`nfsp_insert_multi`: segment prefixes, ring copies beside the reservoirs' stamp
         pass, their write pass, totals committed and counts cleared).  With direct_rings the rings were written by the
         rollout kernel itself and only the two reservoirs travel."""
-        if self.overlap_insert:
-            return self.drain()
         mems_now = self.sl if self.direct_rings else self.sl + self.rl
         if hasattr(self, "_flush_reqs") and any(m._scratch is None or m._scratch.data_ptr() != p_ for m, p_ in zip(mems_now, self._flush_scratch)):
             del self._flush_reqs  # somebody inserted into a memory with a larger geometry: its scratch block moved

@@ -192,17 +192,11 @@ extern "C" int nfsp_act_set_weights(nfsp_env_t h, const float *d_weights, void *
         h->d_wcopy = h->d_wpack + kPackFloats + kTabImageFloats;
         h->d_states = h->d_wpack + kPackFloats + kTabImageFloats + 4 * NFSP_NET_PARAMS;
         NFSP_CUDA(cudaMalloc(&h->d_work, sizeof(uint32_t)));
-        NFSP_CUDA(cudaMalloc(&h->d_started, sizeof(uint32_t)));
-        NFSP_CUDA(cudaMemset(h->d_started, 0, sizeof(uint32_t)));
         NFSP_CUDA(cudaFuncSetAttribute(act_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPackFloats * sizeof(float))));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
         NFSP_CUDA(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabImageBytes));
-        // the image rebuild runs just before the rollout and, with share_sms, beside the insert launch of another stream:
-        // an SM whose carve-out one of its CTAs had shrunk could not take a rollout CTA (190 KB of shared memory) until every
-        // insert CTA on it had finished -- the carve-out of a busy SM does not change (profiles/r02/overlap_insert_notes.txt)
-        NFSP_CUDA(cudaFuncSetAttribute(pack_images_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int rc = nfsp_rollout_sorted_configure();
         if (rc != NFSP_OK) return rc;
         rc = nfsp_rollout_pairs_configure();
@@ -287,10 +281,6 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
     if (!h->has_weights) return set_error(NFSP_E_STATE, "nfsp_act_set_weights has not been called");
     DeviceGuard guard(h->device);
     if (!guard.ok) return set_error(NFSP_E_CUDA, "cannot select device %d", h->device);
-    if (io->share_sms) {
-        const int rg = nfsp_beside_gate(h, (cudaStream_t)stream);  // no-op when nfsp_rollout_with_weights has already held the stream
-        if (rg != NFSP_OK) return rg;
-    }
     RolloutArgs A;
     A.keys = philox_keys(h->seed);
     A.state = h->d_state; A.n = h->n; A.seed = h->seed; A.game0 = h->game0; A.step0 = h->step; A.n_steps = n_steps;
@@ -362,10 +352,6 @@ extern "C" int nfsp_rollout(nfsp_env_t h, int n_steps, double eta, double epsilo
 
 extern "C" int nfsp_rollout_with_weights(nfsp_env_t h, const float *h_weights, float *d_weights, int n_steps, double eta,
                                          double epsilon, const nfsp_rollout_io *io, void *stream) {
-    if (h != nullptr && io != nullptr && io->share_sms) {  // before the image rebuild: its CTAs would disturb the placement too
-        const int rg = nfsp_beside_gate(h, (cudaStream_t)stream);
-        if (rg != NFSP_OK) return rg;
-    }
     const int rc = h_weights ? nfsp_act_set_weights_from_host(h, h_weights, d_weights, stream) : nfsp_act_set_weights(h, d_weights, stream);
     if (rc != NFSP_OK) return rc;
     return nfsp_rollout(h, n_steps, eta, epsilon, io, stream);

@@ -46,7 +46,6 @@ struct MemSet {
     uint32_t gx;     // CTAs' worth of work items per segment
     uint64_t chunk;  // records per stamp / write round of the reservoirs
     int small;       // every memory's batch has at most kSmallSegs segments
-    uint32_t *started;  // nfsp_insert_multi_beside: every CTA adds 1 when it starts (the rollout's gate reads it), else nullptr
 };
 constexpr int kScratchHead = 2;
 constexpr uint64_t kResChunk = 1ull << 21;  // records per stamp / write round: the 64 MB of slots they touch stay in L2
@@ -217,13 +216,8 @@ __device__ __forceinline__ void for_items(const MemSet &S, int k, const uint64_t
 
 constexpr int kSmallSegs = 32;  // up to this many segments per memory every CTA scans the counts itself (one warp each)
 
-// kBeside: the instantiation nfsp_insert_multi_beside launches next to a rollout.  Same code; it exists so that its
-// shared-memory carve-out preference (the largest: an SM that already runs one of its CTAs must still be able to take a
-// rollout CTA with 190 KB of shared memory -- the carve-out of a busy SM cannot change) does not touch the plain launch.
-template <bool kBeside>
 __global__ void __launch_bounds__(kBufThreads, 4) insert_kernel(const MemSet S) {
     __shared__ uint64_t s_pre[NFSP_MAX_INSERT_REQS][kSmallSegs + 1];
-    if (kBeside && S.started != nullptr && threadIdx.x == 0) atomicAdd(S.started, 1u);
     uint64_t *ctrl = S.m[0].scratch;
     uint64_t total[NFSP_MAX_INSERT_REQS], m_all[NFSP_MAX_INSERT_REQS];
     const uint64_t *pre[NFSP_MAX_INSERT_REQS];
@@ -487,7 +481,6 @@ static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet
         rows += r.n_segments;
     }
     S.n = n;
-    S.started = nullptr;
     // work items per segment: about 8 CTAs' worth per SM in total, never more than a segment has 256-record slices
     int64_t g = (*seg_cap_max + kBufThreads - 1) / kBufThreads;
     const int64_t lim = rows >= 148 * 8 ? 1 : (148 * 8 + rows - 1) / rows;
@@ -508,33 +501,20 @@ static int make_memset(const nfsp_insert_req *reqs, int n, int want_kind, MemSet
 }
 
 // one cooperative launch: every CTA must be resident for the grid barriers
-static int launch_insert(MemSet &S, cudaStream_t st, int max_per_sm = 0, int64_t *grid_out = nullptr) {
-    const bool beside = max_per_sm > 0;
-    const void *fn = beside ? (const void *)insert_kernel<true> : (const void *)insert_kernel<false>;
+static int launch_insert(MemSet &S, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     NFSP_CUDA(cudaGetDevice(&dev));
     NFSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (beside) {
-        static bool configured[64] = {};
-        if (dev < 64 && !configured[dev]) {
-            NFSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured[dev] = true;
-        }
-        NFSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<true>, kBufThreads, 0));
-    } else {
-        NFSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<false>, kBufThreads, 0));
-    }
+    NFSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel, kBufThreads, 0));
     if (per_sm < 1) return set_error(NFSP_E_CUDA, "insert_kernel does not fit an SM");
-    const int cap = beside ? max_per_sm : 8;
-    if (per_sm > cap) per_sm = cap;
+    if (per_sm > 8) per_sm = 8;
     int64_t items = 0;
     for (int k = 0; k < S.n; ++k) items += (int64_t)S.m[k].B.n_seg * S.gx;
     int64_t grid = (int64_t)sms * per_sm;
     if (items < grid) grid = items;
     if (grid < S.n) grid = S.n;
-    if (grid_out) *grid_out = grid;
     void *args[] = {(void *)&S};
-    NFSP_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kBufThreads), args, 0, st));
+    NFSP_CUDA(cudaLaunchCooperativeKernel((const void *)insert_kernel, dim3((unsigned)grid), dim3(kBufThreads), args, 0, st));
     return NFSP_OK;
 }
 
@@ -545,49 +525,6 @@ extern "C" int nfsp_insert_multi(const nfsp_insert_req *reqs, int n, void *strea
     if (rc != NFSP_OK) return rc;
     if (seg_cap == 0) return NFSP_OK;
     return launch_insert(S, (cudaStream_t)stream);
-}
-
-// Holds the rollout's stream until every CTA of the insert launched beside it is resident (each counts itself in *started).
-// On a quiet GPU the block scheduler spreads the insert's CTAs one per SM, and each SM keeps exactly the room a 768-thread
-// rollout CTA needs.  When the insert's CTAs are dispatched TOGETHER with those of the rollout's stream (the image rebuild,
-// the rollout itself), some SMs receive two of them and their rollout CTA (49 152 registers) waits until one has finished:
-// the step then ran 20-50 us longer (profiles/r02/overlap_insert_notes.txt).  Bounded: after ~50 us the rollout goes anyway.
-__global__ void beside_gate_kernel(const uint32_t *started, uint32_t want) {
-    if (threadIdx.x == 0) {
-        const volatile uint32_t *s = started;
-        const long long t0 = clock64();
-        while ((int32_t)(*s - want) < 0 && clock64() - t0 < 100000ll) __nanosleep(64);
-    }
-}
-
-int nfsp_beside_gate(nfsp_env_t h, cudaStream_t st) {
-    if (!h->share_pending || h->d_started == nullptr) return NFSP_OK;
-    static bool gate_configured = false;
-    if (!gate_configured) {  // the gate's own SM must stay able to take its rollout CTA (190 KB of shared memory)
-        NFSP_CUDA(cudaFuncSetAttribute(beside_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        gate_configured = true;
-    }
-    beside_gate_kernel<<<1, 32, 0, st>>>(h->d_started, h->started_total);
-    NFSP_LAUNCH_CHECK();
-    h->share_pending = false;
-    return NFSP_OK;
-}
-
-extern "C" int nfsp_insert_multi_beside(nfsp_env_t h, const nfsp_insert_req *reqs, int n, int ctas_per_sm, void *stream) {
-    NFSP_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm must be in [1, 8]");
-    MemSet S;
-    int64_t seg_cap;
-    const int rc = make_memset(reqs, n, -1, S, &seg_cap);
-    if (rc != NFSP_OK) return rc;
-    if (seg_cap == 0) return NFSP_OK;
-    int64_t grid = 0;
-    if (h != nullptr && h->d_started != nullptr) S.started = h->d_started;
-    const int rl = launch_insert(S, (cudaStream_t)stream, ctas_per_sm, &grid);
-    if (rl == NFSP_OK && S.started != nullptr) {
-        h->started_total += (uint32_t)grid;  // the count at which every CTA of this launch is resident
-        h->share_pending = true;
-    }
-    return rl;
 }
 
 extern "C" int nfsp_ring_insert_multi(const nfsp_insert_req *reqs, int n, void *stream) {

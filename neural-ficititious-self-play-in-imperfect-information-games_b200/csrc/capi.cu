@@ -98,7 +98,6 @@ extern "C" int nfsp_env_destroy(nfsp_env_t h) {
     if (h->d_fsm) cudaFree(h->d_fsm);
     if (h->d_wpack) cudaFree(h->d_wpack);
     if (h->d_work) cudaFree(h->d_work);
-    if (h->d_started) cudaFree(h->d_started);
     if (h->d_wtc_wide) cudaFree(h->d_wtc_wide);
     nfsp_tq_release(h);
     delete h;

@@ -31,11 +31,6 @@ struct nfsp_env_s {
     void *d_w2img = nullptr;  // device copy of that image
     uint32_t *d_err = nullptr;  // protocol-error word of the rollout kernel (0 = none), see nfsp_env_kernel_error
     uint32_t tq_patience[2] = {1500u, 700u};  // cycles a partly filled tile of an average / best-response net may wait
-    // an insert launched beside a share_sms rollout (nfsp_insert_multi_beside): every CTA of it counts itself in *d_started
-    // when it starts; the rollout's stream is held back until the count reaches started_total (buffer_kernels.cu)
-    uint32_t *d_started = nullptr;
-    uint32_t started_total = 0;
-    bool share_pending = false;
 };
 
 // builds and uploads the table image of nfsp_step_fsm_kernel (env_kernels.cu); the handle's device is current

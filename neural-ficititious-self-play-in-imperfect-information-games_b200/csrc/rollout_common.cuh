@@ -11,8 +11,6 @@ namespace nfsp { struct RolloutArgs; }
 // launches the tcgen05 variant of the fused rollout (act_tc_kernels.cu)
 int nfsp_rollout_tc_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug, cudaStream_t st);
 // launches the warp-specialised tcgen05 rollout (rollout_tq.cu)
-// holds `st` until the CTAs of the insert launched beside (nfsp_insert_multi_beside) are resident (buffer_kernels.cu)
-int nfsp_beside_gate(nfsp_env_t h, cudaStream_t st);
 int nfsp_rollout_tq_launch(nfsp_env_t h, const nfsp::RolloutArgs &A, bool debug, int reserve_sms, cudaStream_t st);
 
 // launches the net-sorted CUDA-core rollout (rollout_sorted.cu); sets its kernels' shared-memory attribute once per device

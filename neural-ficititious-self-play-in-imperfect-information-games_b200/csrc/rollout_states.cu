@@ -270,14 +270,10 @@ static int configure_states() {
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<true, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
     NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
-    // one carve-out for every kernel of a step (see nfsp_act_set_weights): the largest
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, true, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    NFSP_CUDA(cudaFuncSetAttribute(rollout_states_kernel<false, false, kThreads>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return NFSP_OK;
 }
 
 int nfsp_rollout_states_configure() {
-    NFSP_CUDA(cudaFuncSetAttribute(states_pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int rc = configure_states<kStatesThreads>();
     return rc != NFSP_OK ? rc : configure_states<kStatesThreadsSmall>();
 }
@@ -291,29 +287,22 @@ int nfsp_states_ensure(nfsp_env_t h, const float *d_tab, float *d_states, cudaSt
     return NFSP_OK;
 }
 
-// `threads` <= kThreads: the launch bound fixes the register budget (64 at 1 024), the block size is the caller's
 template <int kThreads>
-static int launch_states(const RolloutArgs &A, int grid, int threads, bool debug, bool direct, cudaStream_t st) {
-    const int bytes = states_smem_bytes(threads);
-    if (debug && direct) rollout_states_kernel<true, true, kThreads><<<grid, threads, bytes, st>>>(A);
-    else if (debug) rollout_states_kernel<true, false, kThreads><<<grid, threads, bytes, st>>>(A);
-    else if (direct) rollout_states_kernel<false, true, kThreads><<<grid, threads, bytes, st>>>(A);
-    else rollout_states_kernel<false, false, kThreads><<<grid, threads, bytes, st>>>(A);
+static int launch_states(const RolloutArgs &A, int grid, bool debug, bool direct, cudaStream_t st) {
+    constexpr int kBytes = states_smem_bytes(kThreads);
+    if (debug && direct) rollout_states_kernel<true, true, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else if (debug) rollout_states_kernel<true, false, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else if (direct) rollout_states_kernel<false, true, kThreads><<<grid, kThreads, kBytes, st>>>(A);
+    else rollout_states_kernel<false, false, kThreads><<<grid, kThreads, kBytes, st>>>(A);
     NFSP_LAUNCH_CHECK();
     return NFSP_OK;
 }
-
-// share_sms: 768-thread CTAs of the 64-register instantiation -- 24 warps x 2 048 registers leave every SM the 16 384
-// registers, the 8 warp slots and the shared memory one 256-thread CTA of another stream's kernel needs (the memories'
-// insert launch running beside the rollout, nfsp_insert_multi_beside)
-constexpr int kStatesThreadsShared = 768;
 
 int nfsp_rollout_states_launch(nfsp_env_t h, const RolloutArgs &A, const nfsp_rollout_io *io, bool debug, cudaStream_t st) {
     const bool direct = A.ring[0] != nullptr;
     const int sms = h->sm_count - io->reserve_sms;
     const int grid = grid_for(h->n, 32, sms, 1);  // at least one block of 32 games per CTA
     const int64_t blocks = (h->n + 31) / 32;
-    if (io->share_sms) return launch_states<kStatesThreads>(A, grid, kStatesThreadsShared, debug, direct, st);
-    if (blocks <= (int64_t)sms * (kStatesThreadsSmall / 32)) return launch_states<kStatesThreadsSmall>(A, grid, kStatesThreadsSmall, debug, direct, st);
-    return launch_states<kStatesThreads>(A, grid, kStatesThreads, debug, direct, st);
+    if (blocks <= (int64_t)sms * (kStatesThreadsSmall / 32)) return launch_states<kStatesThreadsSmall>(A, grid, debug, direct, st);
+    return launch_states<kStatesThreads>(A, grid, debug, direct, st);
 }

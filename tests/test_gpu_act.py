@@ -459,83 +459,6 @@ def test_direct_ring_append_equals_the_staged_insert(nb, variant):
                 break
 
 
-@pytest.mark.parametrize("n", [3000, 1 << 17])
-def test_overlapped_insert_equals_the_insert_after_each_rollout(nb, n):
-    """overlap_insert: the insert launch of rollout k runs on a second stream beside rollout k + 1 (768-thread rollout
-    CTAs, one insert CTA per SM, two staging sets).  Same games, counters and ring records as the plain sequence; the
-    reservoirs lag one call and hold the same records once drained (capacities large enough that a reservoir only fills:
-    ReservoirBuffer.py:22-24, so its contents do not depend on the order of the tickets)."""
-    steps, seed, calls = 8, 33, 5
-    rl_cap = 2 * n * steps * calls
-    mk = lambda ov: nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=rl_cap, sl_capacity=n * steps * calls,  # noqa: E731
-                                max_steps_per_call=steps, direct_rings=True, overlap_insert=ov)
-    so, ss = mk(True), mk(False)
-    for k in range(calls):
-        ss.rollout(steps)
-        before = [int(so.sl[p].total.item()) for p in range(2)]
-        so.rollout(steps, refresh_weights=bool(k & 1))
-        _, sl = so.staged()  # what this call staged: in the reservoirs one call later
-        torch.cuda.synchronize()
-        assert np.array_equal(so.env.state_words().cpu().numpy(), ss.env.state_words().cpu().numpy())
-        for p in range(2):
-            assert int(so.rl[p].total.item()) == int(ss.rl[p].total.item())
-            assert int(so.sl[p].total.item()) + len(sl[p]) == int(ss.sl[p].total.item())
-            assert k == 0 or int(so.sl[p].total.item()) > before[p]  # the previous call's records went in beside this rollout
-    so.drain()
-    so.drain()  # idempotent
-    torch.cuda.synchronize()
-    assert so.read_stats() == ss.read_stats() and so.read_stats()["dropped"] == 0
-    for counts in (so._sets[0][1], so._sets[1][1]):
-        assert int(counts.sum().item()) == 0
-    for p in range(2):
-        t = int(ss.rl[p].total.item())
-        assert np.array_equal(canon(so.rl[p].data[:t].cpu().numpy()), canon(ss.rl[p].data[:t].cpu().numpy()))
-        t = int(ss.sl[p].total.item())
-        assert int(so.sl[p].total.item()) == t and t < so.sl[p].capacity
-        assert np.array_equal(canon(so.sl[p].data[:t].cpu().numpy()), canon(ss.sl[p].data[:t].cpu().numpy()))
-        assert np.array_equal(np.sort(so.sl[p].stamp[:t].cpu().numpy()), np.arange(1, t + 1))
-
-
-def test_overlapped_insert_into_full_reservoirs(nb):
-    """The same with reservoirs that replace (Algorithm R): which records survive depends on the order of the tickets,
-    so the check is structural -- totals as without overlap, every stored record is one that was staged, every stamp is
-    the ticket + 1 of a distinct inserted record."""
-    from collections import Counter
-
-    n, steps, seed, calls = 20000, 8, 5, 6
-    mk = lambda ov: nb.SelfPlay(n, seed=seed, eta=0.3, epsilon=0.1, rl_capacity=2 * n * steps, sl_capacity=30000,  # noqa: E731
-                                max_steps_per_call=steps, direct_rings=True, overlap_insert=ov)
-    so, ss = mk(True), mk(False)
-    staged = [Counter(), Counter()]
-    for _ in range(calls):
-        ss.rollout(steps)
-        so.rollout(steps)
-        _, sl = so.staged()
-        for p in range(2):
-            staged[p].update(_rows(sl[p]))
-    so.flush()  # = drain()
-    torch.cuda.synchronize()
-    assert np.array_equal(so.env.state_words().cpu().numpy(), ss.env.state_words().cpu().numpy())
-    assert so.read_stats() == ss.read_stats()
-    for p in range(2):
-        t = int(so.sl[p].total.item())
-        assert t == int(ss.sl[p].total.item()) == sum(staged[p].values()) and t > 2 * so.sl[p].capacity
-        assert not (Counter(_rows(so.sl[p].data.cpu().numpy())) - staged[p])
-        stamps = so.sl[p].stamp.cpu().numpy()
-        assert stamps.min() >= 1 and stamps.max() <= t and len(np.unique(stamps)) == len(stamps)
-
-
-def test_overlapped_insert_refuses_what_it_cannot_pipeline(nb):
-    with pytest.raises(ValueError):
-        nb.SelfPlay(3000, rl_capacity=1 << 20, sl_capacity=1 << 12, max_steps_per_call=4, direct_rings=False, overlap_insert=True)
-    with pytest.raises(ValueError):
-        nb.SelfPlay(3000, rl_capacity=1 << 20, sl_capacity=1 << 12, max_steps_per_call=4, variant="cuda", direct_rings=True,
-                    overlap_insert=True)
-    sp = nb.SelfPlay(3000, rl_capacity=1 << 20, sl_capacity=1 << 12, max_steps_per_call=4, direct_rings=True, overlap_insert=True)
-    with pytest.raises(ValueError):
-        sp.rollout(4, insert=False)
-
-
 def test_direct_ring_refuses_a_ring_one_launch_could_lap(nb):
     with pytest.raises(ValueError):
         nb.SelfPlay(3000, rl_capacity=2 * 3000 * 4 - 1, sl_capacity=1 << 12, max_steps_per_call=4, variant="sorted", direct_rings=True)
