@@ -23,7 +23,8 @@ namespace nfsp {
 // per-player word P
 //   0-3  bets in half chips      4 policy ('b' = 1)      5-6 last raw action     7 acted with a non-zero vector
 //   8-10 time of the last step() call (7 = never)        11-12 card rank       13-14 public card rank (copy)
-//   15-16 who wins a showdown of this deal: 0 player 0, 1 player 1, 2 nobody, 3 the actor (newenv.py:261-298)
+//   15-16 outcome code of a showdown in which THIS player is the actor (newenv.py:261-298): 1 it wins, 2 the other player
+//         wins, 3 nobody -- precomputed with the deal, so that the step reads it instead of comparing winner and actor
 //   24-26 one-hot private card (obs bits 24-26)          27-29 private | public one-hot (obs bits 27-29, shown in round 1)
 constexpr uint32_t kPBets = 0xFu, kPPol = 1u << 4, kPNz = 1u << 7;
 constexpr uint32_t kRound0Cards = 0x07000000u, kRound1Cards = 0x3F000000u;
@@ -86,16 +87,20 @@ __device__ __forceinline__ uint32_t showdown_winner(uint32_t c0, uint32_t c1, ui
     if (c0 == pub && c1 == pub) return 3u;
     return c0 == pub ? 0u : (c1 == pub ? 1u : (c0 < c1 ? 0u : (c0 > c1 ? 1u : 2u)));
 }
-__device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub, uint32_t winner) {
+// outcome code of a showdown for player p as the actor, from showdown_winner's value
+__device__ __forceinline__ uint32_t showdown_code(uint32_t winner, uint32_t p) {
+    return winner == 2u ? 3u : ((winner == p || winner == 3u) ? 1u : 2u);
+}
+__device__ __forceinline__ uint32_t deal_word(uint32_t c, uint32_t pub, uint32_t code) {
     const uint32_t row0 = 1u << c;
-    return (7u << 8) | (c << 11) | (pub << 13) | (winner << 15) | (row0 << 24) | ((row0 | (1u << pub)) << 27);
+    return (7u << 8) | (c << 11) | (pub << 13) | (code << 15) | (row0 << 24) | ((row0 | (1u << pub)) << 27);
 }
 __device__ __forceinline__ void fill_deal_lut(uint32_t *lut) {
     for (uint32_t i = threadIdx.x; i < 120u; i += blockDim.x) {
         const uint32_t c = deal_ranks(i);
         const uint32_t w = showdown_winner(c & 3u, (c >> 2) & 3u, (c >> 4) & 3u);
-        lut[i] = deal_word(c & 3u, (c >> 4) & 3u, w);
-        lut[120u + i] = deal_word((c >> 2) & 3u, (c >> 4) & 3u, w);
+        lut[i] = deal_word(c & 3u, (c >> 4) & 3u, showdown_code(w, 0u));
+        lut[120u + i] = deal_word((c >> 2) & 3u, (c >> 4) & 3u, showdown_code(w, 1u));
         lut[240u + i] = ((c & 3u) << 6) | (((c >> 2) & 3u) << 8) | (((c >> 4) & 3u) << 10);
     }
 }
@@ -127,7 +132,8 @@ struct NfspFast {
     __device__ __forceinline__ static uint32_t make_p(const NfspW &g, int q) {
         const uint32_t c = g.card(q), row0 = 1u << c, row1 = row0 | (1u << g.pub());
         return g.bets(q) | (g.policy(q) << 4) | (g.last_a(q) << 5) | ((uint32_t)g.acted_nz(q) << 7) | (g.t_snap(q) << 8) |
-               (c << 11) | (g.pub() << 13) | (showdown_winner(g.card(0), g.card(1), g.pub()) << 15) | (row0 << 24) | (row1 << 27);
+               (c << 11) | (g.pub() << 13) | (showdown_code(showdown_winner(g.card(0), g.card(1), g.pub()), (uint32_t)q) << 15) |
+               (row0 << 24) | (row1 << 27);
     }
 
     __device__ __forceinline__ void unpack(uint64_t w) {
@@ -188,8 +194,7 @@ struct NfspFast {
         // branch-free tail: a warp's 32 games are in different phases, so branches would run every side anyway
         cmask = kind == KIND_ROUND ? kRound1Cards : cmask;
         const bool term = kind >= KIND_SHOWDOWN;
-        const uint32_t win = (PA >> 15) & 3u;  // outcome: 1 the actor wins, 2 the opponent wins, 3 draw; 0 = fold
-        const uint32_t oc = kind != KIND_SHOWDOWN ? 0u : (win == 2u ? 3u : ((win == q || win == 3u) ? 1u : 2u));
+        const uint32_t oc = kind != KIND_SHOWDOWN ? 0u : (PA >> 15) & 3u;  // 1 the actor wins, 2 the opponent, 3 draw; 0 = fold
         F |= term ? (kFTerm | kFNeedReset | (q << 17) | (oc << 18)) : 0u;
         // round 1 opens with the dealer, otherwise players alternate; nobody moves after the end of the hand
         const bool pass = !term && (kind == KIND_PASS || q != dealer());
