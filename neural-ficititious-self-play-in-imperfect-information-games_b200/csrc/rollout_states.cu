@@ -211,7 +211,9 @@ rollout_states_kernel(const RolloutArgs A) {
     const int64_t plane = (int64_t)A.n_steps * A.n;
     const uint32_t lane = threadIdx.x & 31u;
     WarpBuf B;
-    B.b = reinterpret_cast<uint4 *>(s_tab) + kStateQuads + (threadIdx.x >> 5) * kWarpBufQuads;
+    // the warp's offset goes through a shuffle so that it lives in a register: left as arithmetic on threadIdx.x, it was
+    // recomputed at each of the step's four buffer stores (16 instructions per warp-step in ncu's source view)
+    B.b = reinterpret_cast<uint4 *>(s_tab) + kStateQuads + __shfl_sync(0xFFFFFFFFu, (threadIdx.x >> 5) * (uint32_t)kWarpBufQuads, 0);
     WarpStage W;
     W.init(A, 0u, kDirect);
     const int64_t n_blocks = (A.n + 31) >> 5;  // CTA c owns blocks c, c + grid, ...; its warps take them dynamically
